@@ -1,0 +1,152 @@
+/*
+ * libmixq_sm100 — C ABI of the B200-native MixLinear hot path.
+ *
+ * This is the drop-in boundary for the reference's native extension module `mixlib`
+ * (github.com/Qcompiler/QComplier, quantkernel; NOT vendored in /root/reference — only its call
+ * sites are).  Each entry point below names the `mixlib.*` call it replaces, cited by
+ * file:line under /root/reference.  `mixq_b200/mixlib.py` is the ctypes binding a maintainer
+ * would drop in as the `mixlib` module.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless it says "host";
+ *   - the caller owns every buffer, nothing is allocated inside; `stream` is a cudaStream_t
+ *     (NULL = legacy default stream); calls are asynchronous on that stream;
+ *   - return 0 on success, a cudaError_t (>0) or a MIXQ_E* code (<0) otherwise;
+ *     mixq_last_error() returns a human-readable message for the calling thread;
+ *   - matrices are row-major and dense unless an explicit leading dimension `ld*` (in elements)
+ *     is given; fp16 = IEEE binary16; activations x[M,K], weights q_w[N,K] (K contiguous);
+ *   - M >= 1; K % 16 == 0; N % 8 == 0 (TMA / 16-byte vector alignment); base pointers 16-byte aligned.
+ *   - thread-compatible, not thread-safe on the same buffers (the reference shares one
+ *     MixLibCache across all layers and relies on single-stream order: Cache.py:5-25).
+ */
+#ifndef MIXQ_H_
+#define MIXQ_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIXQ_EINVAL (-1)   /* bad argument (shape/alignment/bit width) */
+#define MIXQ_EARCH (-2)    /* device is not sm_100 */
+#define MIXQ_EDRIVER (-3)  /* cuTensorMapEncodeTiled unavailable / failed */
+
+#define MIXQ_ACT_NONE 0
+#define MIXQ_ACT_SILU 1
+
+const char* mixq_last_error(void);
+int mixq_version(void);
+/* Number of kernels this library has launched on the calling process so far (bench.py's gpu_launches). */
+unsigned long long mixq_launch_count(void);
+/* Tuning/testing override of the GEMM tile width for calls that do not carry their own tile_n:
+ * 0 = heuristic (default), 128 or 256. */
+int mixq_set_tile_n(int tile_n);
+
+/* ---- mixlib.FindRowScale(x, x_scale, M, K, bit) -> q_x        (linear.py:190-193, :221)
+ * x_scale[m] = fp16(max_k |x[m,k]| / (2^(bit-1)-1));  q_x[m,k] = clamp(rint(x/x_scale)).
+ * q_x is int8 [M,K] for bit 8 AND bit 4 (bit 4: values in [-7,7], one per byte — the packed form is
+ * opaque to the reference's Python, and Blackwell has no int4 MMA to feed it to). */
+int mixq_find_row_scale(const void* x, void* x_scale, void* q_x, int M, int K, int bit, void* stream);
+
+/* ---- mixlib.ExtractOutliersAndSetToZeros(ind, x) -> out[M,n]   (linear.py:189, :205)
+ * out[m,j] = x[m,ind[j]];  x[m,ind[j]] = 0 IN PLACE.  ld_out >= n_ind. */
+int mixq_extract_outliers_and_set_to_zeros(const int32_t* ind, int n_ind, void* x, void* out, int ld_out, int M,
+                                           int K, void* stream);
+
+/* ---- mixlib.int8FusedDequantize / int8FusedDequantizeSilu      (linear.py:251-256, :268-273, :337-351)
+ * y[m,n] = act( fp16( (float(sum_k q_x[m,k]*q_w[n,k]) * x_scale[m]) * scale_col[n] + outl[m,n] ) )
+ * outl may be NULL (== the reference passing cache.zeros).  ld_outl in elements.
+ * tcgen05 kind::i8 GEMM on TMA-staged tiles, fused epilogue. */
+int mixq_int8_fused_dequantize(const void* q_x, const void* q_w, const void* x_scale, const void* scale_col,
+                               const void* outl, int ld_outl, void* y, int M, int N, int K, int act,
+                               void* stream);
+
+/* ---- mixlib.int4FusedDequantize / ...Silu                      (linear.py:259-265, :278-283, :360-366)
+ * q_w is the packed-nibble weight uint8 [N,K/2] (low nibble = even k, two's complement, linear.py:14-18);
+ * q_x is int8 [M,K] as produced by mixq_find_row_scale(bit=4).  K is the LOGICAL K (the reference passes K/2). */
+int mixq_int4_fused_dequantize(const void* q_x, const void* q_w_packed, const void* x_scale,
+                               const void* scale_col, const void* outl, int ld_outl, void* y, int M, int N,
+                               int K, int act, void* stream);
+
+/* ---- mixlib.gemm(q_x, q_w, M, N, K) -> int32 [M,N]             (linear.py:235, :321; arch==9 split path) */
+int mixq_gemm_i8(const void* q_x, const void* q_w, int32_t* y, int M, int N, int K, void* stream);
+
+/* ---- mixlib.dequantizeInt8 / dequantizeInt8Silu                (linear.py:238, :241, :324, :327) */
+int mixq_dequantize_int8(const int32_t* acc, const void* x_scale, const void* scale_col, const void* outl,
+                         int ld_outl, void* y, int M, int N, int act, void* stream);
+
+/* ---- mixlib.unpack_int4_to_fp16(q_w, ind) -> fp16 [N, n]       (linear.py:20-22)
+ * out[n,j] = sign-extended nibble of column ind[j] (un-scaled). */
+int mixq_unpack_int4_to_fp16(const void* q_w_packed, const int32_t* ind, int n_ind, void* out, int ld_out, int N,
+                             int K, void* stream);
+
+/* ---- mixlib.layernorm_forward_cuda(x, w, out, eps)             (fused/norm.py:21) — RMSNorm */
+int mixq_rmsnorm(const void* x, const void* w, void* out, float eps, int M, int K, void* stream);
+
+/* ---- mixlib.layernorm_forward_cuda_extract_outliers[_int4](x, w, out, eps, ind, x_scale) -> (outl, q_x)
+ *      (fused/norm.py:25-33).  out has the ind columns zeroed (same as the unfused path, linear.py:189). */
+int mixq_rmsnorm_extract_outliers(const void* x, const void* w, void* out, float eps, const int32_t* ind,
+                                  int n_ind, void* x_scale, void* act_out, int ld_ao, void* q_x, int M, int K,
+                                  int bit, void* stream);
+
+/* ---- weight_cache columns: q_weight[:,ind].half() * scale_col.T  (linear.py:207, :209-210, :305-308)
+ * wc[n, col0 + j] = fp16(q_w[n, ind[j]]) * scale_col[n]   (fp16 multiply, like the reference) */
+int mixq_gather_weight_columns(const void* q_w, const void* scale_col, const int32_t* ind, int n_ind, void* wc,
+                               int ld_wc, int col0, int N, int K, int bit, void* stream);
+
+/* ---- FindOutliers (linear.py:157-161) on the device: compact col_over[K] (bytes set by the scan) into
+ * ascending column ids appended at ind[n_ind...] ; *n_new (device int32) receives the count; col_over is
+ * cleared.  At most max_new ids are written. */
+int mixq_compact_outlier_columns(uint8_t* col_over, int K, int32_t* ind_out, int max_new, int32_t* n_new,
+                                 void* stream);
+
+/* ---- the north-star entry: steady-state MixLinear_GEMM.forward as ONE launch (linear.py:165-289, :291-376).
+ * Phase A (every CTA): [RMSNorm ->] gather+zero outlier columns -> row absmax -> x_scale -> int8 q_x,
+ * outlier scan against sigma; one grid barrier; phase B: persistent warp-specialised tcgen05 GEMM:
+ * int8 x int8 -> int32 in TMEM over K, fp16 x fp16 -> fp32 in TMEM over the outlier columns, epilogue
+ * y = act(fp16((acc*x_scale[m])*scale_col[n] + acc_outl + bias[n])). */
+typedef struct mixq_linear_args {
+  /* activations */
+  void* x;                 /* fp16 [M,K]; outlier columns zeroed in place unless norm_weight is set */
+  const void* norm_weight; /* optional fp16 [K]: x is un-normed, norm_out receives RMSNorm(x)*w */
+  void* norm_out;          /* fp16 [M,K] (required with norm_weight) */
+  float eps;
+  int M, N, K;
+  /* weights */
+  const void* q_weight;    /* int8 [N,K] (bit 8) | uint8 [N,K/2] packed nibbles (bit 4) */
+  const void* scale_col;   /* fp16 [N] */
+  const void* bias;        /* fp16 [N] or NULL */
+  int bit;                 /* 8 or 4 */
+  /* fp16 outlier path */
+  const int32_t* ind;      /* [n_ind] */
+  int n_ind;
+  const void* weight_cache;/* fp16 [N, ld_wc], first n_ind columns valid */
+  int ld_wc;               /* multiple of 8 */
+  /* caller-owned scratch (what MixLibCache carries: Cache.py:8,17 + linear.py:190) */
+  void* q_x;               /* int8 [M,K] */
+  void* x_scale;           /* fp16 [>=M] */
+  void* act_outliers;      /* fp16 [M, ld_ao] */
+  int ld_ao;               /* multiple of 8 */
+  /* outlier scan */
+  float sigma;             /* threshold (Cache.py:6,12: 6) */
+  uint8_t* col_over;       /* [K] bytes or NULL */
+  uint32_t* over_flag;     /* or NULL; |= 1 when max(x_scale) > fp16(sigma/qmax) (linear.py:201) */
+  /* output */
+  void* y;                 /* fp16 [M,N] */
+  int act;                 /* MIXQ_ACT_* */
+  /* control */
+  int skip_prologue;       /* 1: q_x / x_scale / act_outliers already valid (gate_proj, linear.py:291-376) */
+  uint32_t* grid_sync;     /* one zero-initialised u32 in device memory, reused across launches */
+  int tile_n;              /* 0 = auto, else 128 or 256 */
+} mixq_linear_args;
+
+int mixq_linear_fused(const mixq_linear_args* args /* host */, void* stream);
+
+/* elementwise gate *= up (mlp.py:64) kept for the decode harness */
+int mixq_mul_inplace(void* a, const void* b, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIXQ_H_ */

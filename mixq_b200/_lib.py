@@ -1,0 +1,108 @@
+"""ctypes loader for libmixq_sm100.so (the C ABI declared in include/mixq.h).
+
+There is no fallback: if the shared library is missing the import raises, and every call that
+returns non-zero raises `MixqError` with the library's own message.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "lib" / "libmixq_sm100.so"
+
+
+class MixqError(RuntimeError):
+    pass
+
+
+class LinearArgs(C.Structure):
+    """Mirror of `mixq_linear_args` (include/mixq.h)."""
+
+    _fields_ = [
+        ("x", C.c_void_p),
+        ("norm_weight", C.c_void_p),
+        ("norm_out", C.c_void_p),
+        ("eps", C.c_float),
+        ("M", C.c_int),
+        ("N", C.c_int),
+        ("K", C.c_int),
+        ("q_weight", C.c_void_p),
+        ("scale_col", C.c_void_p),
+        ("bias", C.c_void_p),
+        ("bit", C.c_int),
+        ("ind", C.c_void_p),
+        ("n_ind", C.c_int),
+        ("weight_cache", C.c_void_p),
+        ("ld_wc", C.c_int),
+        ("q_x", C.c_void_p),
+        ("x_scale", C.c_void_p),
+        ("act_outliers", C.c_void_p),
+        ("ld_ao", C.c_int),
+        ("sigma", C.c_float),
+        ("col_over", C.c_void_p),
+        ("over_flag", C.c_void_p),
+        ("y", C.c_void_p),
+        ("act", C.c_int),
+        ("skip_prologue", C.c_int),
+        ("grid_sync", C.c_void_p),
+        ("tile_n", C.c_int),
+    ]
+
+
+_vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+
+# name -> argtypes; every function returns int unless listed in _RESTYPES
+SIGNATURES = {
+    "mixq_find_row_scale": [_vp, _vp, _vp, _i, _i, _i, _vp],
+    "mixq_extract_outliers_and_set_to_zeros": [_vp, _i, _vp, _vp, _i, _i, _i, _vp],
+    "mixq_int8_fused_dequantize": [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp],
+    "mixq_int4_fused_dequantize": [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp],
+    "mixq_gemm_i8": [_vp, _vp, _vp, _i, _i, _i, _vp],
+    "mixq_dequantize_int8": [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp],
+    "mixq_unpack_int4_to_fp16": [_vp, _vp, _i, _vp, _i, _i, _i, _vp],
+    "mixq_rmsnorm": [_vp, _vp, _vp, _f, _i, _i, _vp],
+    "mixq_rmsnorm_extract_outliers": [_vp, _vp, _vp, _f, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _vp],
+    "mixq_gather_weight_columns": [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
+    "mixq_compact_outlier_columns": [_vp, _i, _vp, _i, _vp, _vp],
+    "mixq_linear_fused": [C.POINTER(LinearArgs), _vp],
+    "mixq_mul_inplace": [_vp, _vp, _ll, _vp],
+    "mixq_set_tile_n": [_i],
+    "mixq_version": [],
+    "mixq_launch_count": [],
+    "mixq_last_error": [],
+}
+_RESTYPES = {"mixq_launch_count": C.c_ulonglong, "mixq_last_error": C.c_char_p}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once).  Raises MixqError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = Path(os.environ.get("MIXQ_LIB", LIB_PATH))
+    if not path.exists():
+        raise MixqError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C mixq_b200/csrc` — there is no CPU or PyTorch fallback for the MixLinear path"
+        )
+    lib = C.CDLL(str(path))
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here == header/library drift
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, C.c_int)
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().mixq_last_error()
+        raise MixqError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")
+
+
+def launch_count() -> int:
+    return int(load().mixq_launch_count())

@@ -1,0 +1,446 @@
+// extern "C" surface of libmixq_sm100 (see include/mixq.h).  Host-side only: argument checks,
+// TMA tensor-map encoding, launch configuration.  No allocation, no synchronisation.
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
+#include "../../include/mixq.h"
+#include "mixq_gemm.cuh"
+#include "mixq_kernels.cuh"
+
+namespace {
+
+using namespace mixq;
+
+thread_local std::string g_err;
+std::atomic<unsigned long long> g_launches{0};
+std::atomic<int> g_tile_n{0};
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+  g_err = std::string(where) + ": " + cudaGetErrorString(e);
+  return static_cast<int>(e);
+}
+#define MIXQ_CUDA(call)                                   \
+  do {                                                    \
+    cudaError_t e__ = (call);                             \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+struct DeviceInfo {
+  int sms = 0;
+  int cc_major = 0;
+  bool ok = false;
+};
+int device_info(DeviceInfo* out) {
+  static std::mutex mu;
+  static std::unordered_map<int, DeviceInfo> cache;
+  int dev = 0;
+  MIXQ_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(dev);
+  if (it == cache.end()) {
+    DeviceInfo d;
+    MIXQ_CUDA(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+    MIXQ_CUDA(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    d.ok = true;
+    it = cache.emplace(dev, d).first;
+  }
+  *out = it->second;
+  if (out->cc_major != 10) return fail(MIXQ_EARCH, "libmixq_sm100 needs a compute-capability 10.x device (B200)");
+  return 0;
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// 2-D row-major tensor [rows, cols] of `elt` bytes, row pitch `pitch_bytes`; box = box_cols x box_rows.
+int make_map(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int elt, long long cols, long long rows,
+             long long pitch_bytes, int box_cols, int box_rows, CUtensorMapSwizzle sw) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return fail(MIXQ_EDRIVER, "cuTensorMapEncodeTiled not available from the driver");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(MIXQ_EINVAL, "TMA operand not 16-byte aligned");
+  if (pitch_bytes % 16 != 0) return fail(MIXQ_EINVAL, "TMA operand row pitch not a multiple of 16 bytes");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(pitch_bytes)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  (void)elt;
+  CUresult r = fn(m, dt, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MIXQ_EDRIVER, "cuTensorMapEncodeTiled failed (CUresult " + std::to_string(r) + ")");
+  return 0;
+}
+
+template <int BN, bool W4>
+int launch_linear(const LinearParams& p, int grid, bool cooperative, cudaStream_t st) {
+  using Cfg = GemmCfg<BN, W4>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(mixq_linear_kernel<BN, W4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg::SMEM_BYTES);
+  });
+  // the attribute is per device; set it again cheaply if we are on another device
+  static thread_local int last_dev = -1;
+  int dev = 0;
+  MIXQ_CUDA(cudaGetDevice(&dev));
+  if (dev != last_dev) {
+    MIXQ_CUDA(cudaFuncSetAttribute(mixq_linear_kernel<BN, W4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Cfg::SMEM_BYTES));
+    last_dev = dev;
+  }
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(smem)");
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(Cfg::NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeCooperative;
+  attrs[0].val.cooperative = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = cooperative ? 1 : 0;
+  MIXQ_CUDA(cudaLaunchKernelEx(&cfg, mixq_linear_kernel<BN, W4>, p));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int pick_tile_n(int requested, int M, int N, int sms, bool tmem_outliers) {
+  if (requested == 128 || requested == 256) return requested;
+  const int forced = g_tile_n.load(std::memory_order_relaxed);
+  if (forced == 128 || forced == 256) return forced;
+  // Fewest "waves x tile width" wins; 256-wide tiles lose accumulator double-buffering when the
+  // fp32 outlier accumulator also lives in TMEM.
+  const int mb = (M + 127) / 128;
+  auto cost = [&](int bn) {
+    const int tiles = mb * ((N + bn - 1) / bn);
+    const int waves = (tiles + sms - 1) / sms;
+    double c = static_cast<double>(waves) * bn;
+    if (bn == 256 && tmem_outliers) c *= 1.15;
+    if (bn == 128) c *= 1.08;  // narrower tile: more smem traffic per MMA
+    return c;
+  };
+  return cost(256) < cost(128) ? 256 : 128;
+}
+
+struct GemmCall {
+  const void* q_x;
+  const void* q_w;
+  int bit;
+  const void* x_scale;
+  const void* scale_col;
+  const void* bias;
+  const void* outl;
+  int ld_outl;
+  const void* act_outliers;
+  int ld_ao;
+  const void* weight_cache;
+  int ld_wc;
+  int n_out;
+  void* y;
+  int32_t* y_i32;
+  int M, N, K, act, epilogue, tile_n;
+  const RowQuantArgs* rq;  // non-null => fused prologue
+  uint32_t* grid_sync;
+};
+
+int run_gemm(const GemmCall& c, cudaStream_t st) {
+  DeviceInfo di;
+  if (int r = device_info(&di)) return r;
+  if (c.M < 1 || c.N < 8 || c.K < 16) return fail(MIXQ_EINVAL, "M>=1, N>=8, K>=16 required");
+  if (c.K % 16 != 0 || c.N % 8 != 0) return fail(MIXQ_EINVAL, "K % 16 == 0 and N % 8 == 0 required");
+  if (c.bit != 8 && c.bit != 4) return fail(MIXQ_EINVAL, "bit must be 8 or 4");
+  if (c.bit == 4 && c.K % 32 != 0) return fail(MIXQ_EINVAL, "bit 4 needs K % 32 == 0");
+  if (c.n_out > 0 && (c.ld_ao % 8 != 0 || c.ld_wc % 8 != 0 || c.ld_ao < c.n_out || c.ld_wc < c.n_out))
+    return fail(MIXQ_EINVAL, "outlier buffers need ld % 8 == 0 and ld >= n_ind");
+  const bool w4 = (c.bit == 4);
+  const int bn = pick_tile_n(c.tile_n, c.M, c.N, di.sms, c.n_out > 0);
+
+  LinearParams p{};
+  if (int r = make_map(&p.tm_a, c.q_x, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, c.K, c.M, c.K, 128, 128,
+                       CU_TENSOR_MAP_SWIZZLE_128B))
+    return r;
+  if (w4) {
+    if (int r = make_map(&p.tm_b, c.q_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, c.K / 2, c.N, c.K / 2, 64, bn,
+                         CU_TENSOR_MAP_SWIZZLE_NONE))
+      return r;
+  } else {
+    if (int r = make_map(&p.tm_b, c.q_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, c.K, c.N, c.K, 128, bn,
+                         CU_TENSOR_MAP_SWIZZLE_128B))
+      return r;
+  }
+  if (c.n_out > 0) {
+    if (int r = make_map(&p.tm_oa, c.act_outliers, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c.n_out, c.M,
+                         static_cast<long long>(c.ld_ao) * 2, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))
+      return r;
+    if (int r = make_map(&p.tm_ob, c.weight_cache, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c.n_out, c.N,
+                         static_cast<long long>(c.ld_wc) * 2, 64, bn, CU_TENSOR_MAP_SWIZZLE_128B))
+      return r;
+  }
+  if (c.rq != nullptr) {
+    p.rq = *c.rq;
+    p.fused_prologue = 1;
+  }
+  p.x_scale = static_cast<const __half*>(c.x_scale);
+  p.scale_col = static_cast<const __half*>(c.scale_col);
+  p.bias = static_cast<const __half*>(c.bias);
+  p.outl = static_cast<const __half*>(c.outl);
+  p.ld_outl = c.ld_outl;
+  p.y = static_cast<__half*>(c.y);
+  p.y_i32 = c.y_i32;
+  p.M = c.M;
+  p.N = c.N;
+  p.K = c.K;
+  p.n_out = c.n_out;
+  p.act = c.act;
+  p.epilogue = c.epilogue;
+  p.grid_sync = c.grid_sync;
+
+  const int tiles = ((c.M + 127) / 128) * ((c.N + bn - 1) / bn);
+  const bool coop = p.fused_prologue != 0;
+  const int grid = coop ? di.sms : (tiles < di.sms ? tiles : di.sms);
+  if (w4) return bn == 256 ? launch_linear<256, true>(p, grid, coop, st) : launch_linear<128, true>(p, grid, coop, st);
+  return bn == 256 ? launch_linear<256, false>(p, grid, coop, st) : launch_linear<128, false>(p, grid, coop, st);
+}
+
+int grid_for(long long work_items, int threads, int sms, int per_sm = 8) {
+  long long blocks = (work_items + threads - 1) / threads;
+  long long cap = static_cast<long long>(sms) * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+int fill_rowquant(RowQuantArgs* a, void* x, const void* norm_w, void* norm_out, float eps, const int32_t* ind,
+                  int n_ind, void* act_out, int ld_ao, void* q_x, void* x_scale, int M, int K, int bit, float sigma,
+                  uint8_t* col_over, uint32_t* over_flag) {
+  if (M < 1 || K < 8 || K % 8 != 0) return fail(MIXQ_EINVAL, "M >= 1 and K % 8 == 0 required");
+  if (q_x != nullptr && bit != 8 && bit != 4) return fail(MIXQ_EINVAL, "bit must be 8 or 4");
+  if (n_ind > 0 && (ind == nullptr || act_out == nullptr || ld_ao < n_ind))
+    return fail(MIXQ_EINVAL, "outlier gather needs ind, act_out and ld_ao >= n_ind");
+  a->x = static_cast<__half*>(x);
+  a->norm_w = static_cast<const __half*>(norm_w);
+  a->norm_out = static_cast<__half*>(norm_out);
+  a->eps = eps;
+  a->ind = ind;
+  a->n_ind = n_ind;
+  a->act_out = static_cast<__half*>(act_out);
+  a->ld_ao = ld_ao;
+  a->q_x = static_cast<int8_t*>(q_x);
+  a->x_scale = static_cast<__half*>(x_scale);
+  a->M = M;
+  a->K = K;
+  a->bit = bit;
+  const float qmax = (bit == 4) ? 7.f : 127.f;
+  a->sigma = __float2half_rn(sigma);
+  // torch: fp16 tensor / python int -> computed in fp32, rounded to fp16 (linear.py:201)
+  a->thr = __float2half_rn(__half2float(a->sigma) / qmax);
+  a->col_over = col_over;
+  a->over_flag = over_flag;
+  return 0;
+}
+
+int launch_rowquant(const RowQuantArgs& a, cudaStream_t st) {
+  DeviceInfo di;
+  if (int r = device_info(&di)) return r;
+  const int threads = 256;
+  const int grid = grid_for(static_cast<long long>(a.M) * 32, threads, di.sms, 8);
+  rowquant_kernel<<<grid, threads, 0, st>>>(a);
+  MIXQ_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mixq_last_error(void) { return g_err.c_str(); }
+int mixq_version(void) { return 100; }
+unsigned long long mixq_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+int mixq_set_tile_n(int tile_n) {
+  if (tile_n != 0 && tile_n != 128 && tile_n != 256) return fail(MIXQ_EINVAL, "tile_n must be 0, 128 or 256");
+  g_tile_n.store(tile_n, std::memory_order_relaxed);
+  return 0;
+}
+
+int mixq_find_row_scale(const void* x, void* x_scale, void* q_x, int M, int K, int bit, void* stream) {
+  if (x == nullptr || x_scale == nullptr || q_x == nullptr) return fail(MIXQ_EINVAL, "null pointer");
+  RowQuantArgs a{};
+  if (int r = fill_rowquant(&a, const_cast<void*>(x), nullptr, nullptr, 0.f, nullptr, 0, nullptr, 0, q_x, x_scale,
+                            M, K, bit, 0.f, nullptr, nullptr))
+    return r;
+  return launch_rowquant(a, static_cast<cudaStream_t>(stream));
+}
+
+int mixq_extract_outliers_and_set_to_zeros(const int32_t* ind, int n_ind, void* x, void* out, int ld_out, int M,
+                                           int K, void* stream) {
+  if (n_ind == 0) return 0;
+  if (ind == nullptr || x == nullptr || out == nullptr || n_ind < 0 || ld_out < n_ind || M < 1)
+    return fail(MIXQ_EINVAL, "bad extract arguments");
+  DeviceInfo di;
+  if (int r = device_info(&di)) return r;
+  const int grid = grid_for(static_cast<long long>(M) * n_ind, 256, di.sms);
+  extract_outliers_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      ind, n_ind, static_cast<__half*>(x), static_cast<__half*>(out), ld_out, M, K);
+  MIXQ_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int mixq_int8_fused_dequantize(const void* q_x, const void* q_w, const void* x_scale, const void* scale_col,
+                               const void* outl, int ld_outl, void* y, int M, int N, int K, int act,
+                               void* stream) {
+  if (!q_x || !q_w || !x_scale || !scale_col || !y) return fail(MIXQ_EINVAL, "null pointer");
+  GemmCall c{};
+  c.q_x = q_x; c.q_w = q_w; c.bit = 8; c.x_scale = x_scale; c.scale_col = scale_col;
+  c.outl = outl; c.ld_outl = ld_outl; c.y = y; c.M = M; c.N = N; c.K = K; c.act = act;
+  c.epilogue = EPI_DEQUANT_F16;
+  return run_gemm(c, static_cast<cudaStream_t>(stream));
+}
+
+int mixq_int4_fused_dequantize(const void* q_x, const void* q_w_packed, const void* x_scale,
+                               const void* scale_col, const void* outl, int ld_outl, void* y, int M, int N,
+                               int K, int act, void* stream) {
+  if (!q_x || !q_w_packed || !x_scale || !scale_col || !y) return fail(MIXQ_EINVAL, "null pointer");
+  GemmCall c{};
+  c.q_x = q_x; c.q_w = q_w_packed; c.bit = 4; c.x_scale = x_scale; c.scale_col = scale_col;
+  c.outl = outl; c.ld_outl = ld_outl; c.y = y; c.M = M; c.N = N; c.K = K; c.act = act;
+  c.epilogue = EPI_DEQUANT_F16;
+  return run_gemm(c, static_cast<cudaStream_t>(stream));
+}
+
+int mixq_gemm_i8(const void* q_x, const void* q_w, int32_t* y, int M, int N, int K, void* stream) {
+  if (!q_x || !q_w || !y) return fail(MIXQ_EINVAL, "null pointer");
+  GemmCall c{};
+  c.q_x = q_x; c.q_w = q_w; c.bit = 8; c.y_i32 = y; c.M = M; c.N = N; c.K = K;
+  c.epilogue = EPI_RAW_I32;
+  return run_gemm(c, static_cast<cudaStream_t>(stream));
+}
+
+int mixq_dequantize_int8(const int32_t* acc, const void* x_scale, const void* scale_col, const void* outl,
+                         int ld_outl, void* y, int M, int N, int act, void* stream) {
+  if (!acc || !x_scale || !scale_col || !y || M < 1 || N % 8 != 0) return fail(MIXQ_EINVAL, "bad dequantize arguments");
+  DeviceInfo di;
+  if (int r = device_info(&di)) return r;
+  const int grid = grid_for(static_cast<long long>(M) * (N / 8), 256, di.sms);
+  dequant_i32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      acc, static_cast<const __half*>(x_scale), static_cast<const __half*>(scale_col),
+      static_cast<const __half*>(outl), ld_outl, static_cast<__half*>(y), M, N, act);
+  MIXQ_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int mixq_unpack_int4_to_fp16(const void* q_w_packed, const int32_t* ind, int n_ind, void* out, int ld_out, int N,
+                             int K, void* stream) {
+  if (n_ind == 0) return 0;
+  if (!q_w_packed || !ind || !out || ld_out < n_ind) return fail(MIXQ_EINVAL, "bad unpack arguments");
+  DeviceInfo di;
+  if (int r = device_info(&di)) return r;
+  const int grid = grid_for(static_cast<long long>(N) * n_ind, 256, di.sms);
+  unpack_int4_cols_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint8_t*>(q_w_packed), ind, n_ind, static_cast<__half*>(out), ld_out, N, K);
+  MIXQ_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int mixq_rmsnorm(const void* x, const void* w, void* out, float eps, int M, int K, void* stream) {
+  if (!x || !w || !out) return fail(MIXQ_EINVAL, "null pointer");
+  RowQuantArgs a{};
+  if (int r = fill_rowquant(&a, const_cast<void*>(x), w, out, eps, nullptr, 0, nullptr, 0, nullptr, nullptr, M, K,
+                            8, 0.f, nullptr, nullptr))
+    return r;
+  return launch_rowquant(a, static_cast<cudaStream_t>(stream));
+}
+
+int mixq_rmsnorm_extract_outliers(const void* x, const void* w, void* out, float eps, const int32_t* ind,
+                                  int n_ind, void* x_scale, void* act_out, int ld_ao, void* q_x, int M, int K,
+                                  int bit, void* stream) {
+  if (!x || !w || !out || !x_scale || !q_x) return fail(MIXQ_EINVAL, "null pointer");
+  RowQuantArgs a{};
+  if (int r = fill_rowquant(&a, const_cast<void*>(x), w, out, eps, ind, n_ind, act_out, ld_ao, q_x, x_scale, M, K,
+                            bit, 0.f, nullptr, nullptr))
+    return r;
+  return launch_rowquant(a, static_cast<cudaStream_t>(stream));
+}
+
+int mixq_gather_weight_columns(const void* q_w, const void* scale_col, const int32_t* ind, int n_ind, void* wc,
+                               int ld_wc, int col0, int N, int K, int bit, void* stream) {
+  if (n_ind == 0) return 0;
+  if (!q_w || !scale_col || !ind || !wc || col0 < 0 || ld_wc < col0 + n_ind || (bit != 8 && bit != 4))
+    return fail(MIXQ_EINVAL, "bad gather arguments");
+  DeviceInfo di;
+  if (int r = device_info(&di)) return r;
+  const int grid = grid_for(static_cast<long long>(N) * n_ind, 256, di.sms);
+  gather_weight_cols_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      q_w, static_cast<const __half*>(scale_col), ind, n_ind, static_cast<__half*>(wc), ld_wc, col0, N, K, bit);
+  MIXQ_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int mixq_compact_outlier_columns(uint8_t* col_over, int K, int32_t* ind_out, int max_new, int32_t* n_new,
+                                 void* stream) {
+  if (!col_over || !ind_out || !n_new || K < 1 || max_new < 0) return fail(MIXQ_EINVAL, "bad compact arguments");
+  compact_cols_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(col_over, K, ind_out, max_new, n_new);
+  MIXQ_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int mixq_linear_fused(const mixq_linear_args* a, void* stream) {
+  if (a == nullptr) return fail(MIXQ_EINVAL, "null args");
+  if (!a->q_weight || !a->scale_col || !a->q_x || !a->x_scale || !a->y) return fail(MIXQ_EINVAL, "null pointer");
+  if (a->n_ind > 0 && (!a->ind || !a->weight_cache || !a->act_outliers))
+    return fail(MIXQ_EINVAL, "n_ind > 0 needs ind, weight_cache and act_outliers");
+  RowQuantArgs rq{};
+  if (!a->skip_prologue) {
+    if (!a->x || !a->grid_sync) return fail(MIXQ_EINVAL, "prologue needs x and grid_sync");
+    if (a->norm_weight && !a->norm_out) return fail(MIXQ_EINVAL, "norm_weight needs norm_out");
+    if (int r = fill_rowquant(&rq, a->x, a->norm_weight, a->norm_out, a->eps, a->ind, a->n_ind, a->act_outliers,
+                              a->ld_ao, a->q_x, a->x_scale, a->M, a->K, a->bit, a->sigma, a->col_over,
+                              a->over_flag))
+      return r;
+  }
+  GemmCall c{};
+  c.q_x = a->q_x; c.q_w = a->q_weight; c.bit = a->bit; c.x_scale = a->x_scale; c.scale_col = a->scale_col;
+  c.bias = a->bias; c.act_outliers = a->act_outliers; c.ld_ao = a->ld_ao; c.weight_cache = a->weight_cache;
+  c.ld_wc = a->ld_wc; c.n_out = a->n_ind; c.y = a->y; c.M = a->M; c.N = a->N; c.K = a->K; c.act = a->act;
+  c.epilogue = EPI_DEQUANT_F16; c.tile_n = a->tile_n;
+  c.rq = a->skip_prologue ? nullptr : &rq;
+  c.grid_sync = a->grid_sync;
+  return run_gemm(c, static_cast<cudaStream_t>(stream));
+}
+
+int mixq_mul_inplace(void* a, const void* b, long long n, void* stream) {
+  if (!a || !b || n < 0 || (n & 1)) return fail(MIXQ_EINVAL, "bad mul arguments");
+  DeviceInfo di;
+  if (int r = device_info(&di)) return r;
+  const int grid = grid_for(n / 2, 256, di.sms);
+  mul_inplace_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__half2*>(a), static_cast<const __half2*>(b), n / 2);
+  MIXQ_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+}  // extern "C"

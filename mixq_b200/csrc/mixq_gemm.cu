@@ -1,0 +1,321 @@
+// The MixLinear hot-path kernel for sm_100a.
+//
+//   y[M,N] = act( fp16( (int32(q_x . q_w^T) * x_scale[m]) * scale_col[n]          <- tcgen05 kind::i8, TMEM s32
+//                       + act_outliers[M,n_out] . weight_cache[N,n_out]^T            <- tcgen05 kind::f16, TMEM f32
+//                       + outl[m,n] + bias[n] ) )
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer   (cp.async.bulk.tensor, SWIZZLE_128B boxes, mbarrier complete_tx)
+//   warp 1      MMA issuer     (one lane issues tcgen05.mma; tcgen05.commit frees smem stages / publishes TMEM)
+//   warp 2      TMEM allocator (512 columns; double-buffered accumulators when they fit)
+//   warps 4-7   epilogue       (tcgen05.ld 32x32b -> registers -> dequant/bias/SiLU -> 16-byte global stores)
+//   warps 8-11  (W4 only) nibble unpack: packed uint8 tile -> sign-extended int8 tile in the swizzled layout
+// With fused_prologue every warp first runs the activation prologue (rowquant.cuh) on its share of the
+// rows, the grid meets at one barrier, and the producer — which already has the first weight tiles in
+// flight — starts feeding q_x tiles.
+//
+// Reference behaviour this replaces: mixlib.int8FusedDequantize[Silu] / int4FusedDequantize[Silu] / gemm and
+// the torch.mm outlier GEMM in /root/reference/mixquant/modules/linear.py:234-283, :320-366.
+#include "mixq_gemm.cuh"
+
+namespace mixq {
+
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+
+// One 32-column slab of one accumulator row: TMEM -> registers -> dequant (+outliers, +bias, SiLU) -> global.
+// Every lane of the warp must call this (tcgen05.ld is warp-collective); row_ok masks the stores.
+template <bool HAS_O>
+__device__ __forceinline__ void epilogue_chunk(const LinearParams& p, uint32_t t_int, uint32_t t_out, int row,
+                                               bool row_ok, int n, float xs) {
+  uint32_t acc[32];
+  uint32_t oacc[32];
+  tmem_ld_32x32(t_int, acc);
+  if (HAS_O) tmem_ld_32x32(t_out, oacc);
+  tmem_ld_wait();
+  if (!row_ok || n >= p.N) return;
+  if (p.epilogue == EPI_RAW_I32) {
+    int32_t* dst = p.y_i32 + static_cast<size_t>(row) * p.N + n;
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      if (n + g * 4 < p.N)
+        reinterpret_cast<uint4*>(dst)[g] = make_uint4(acc[4 * g], acc[4 * g + 1], acc[4 * g + 2], acc[4 * g + 3]);
+    return;
+  }
+  const bool has_outl = p.outl != nullptr;
+  const bool has_bias = p.bias != nullptr;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {   // 8 columns per 16-byte store
+    const int ng = n + g * 8;
+    if (ng < p.N) {
+      const uint4 wsu = __ldg(reinterpret_cast<const uint4*>(p.scale_col + ng));
+      uint4 olu = make_uint4(0, 0, 0, 0), bsu = make_uint4(0, 0, 0, 0);
+      if (has_outl) olu = *reinterpret_cast<const uint4*>(p.outl + static_cast<size_t>(row) * p.ld_outl + ng);
+      if (has_bias) bsu = __ldg(reinterpret_cast<const uint4*>(p.bias + ng));
+      const uint32_t wsw[4] = {wsu.x, wsu.y, wsu.z, wsu.w};
+      const uint32_t olw[4] = {olu.x, olu.y, olu.z, olu.w};
+      const uint32_t bsw[4] = {bsu.x, bsu.y, bsu.z, bsu.w};
+      uint32_t ow[4];
+#pragma unroll
+      for (int j2 = 0; j2 < 4; ++j2) {
+        const float2 wf = __half22float2(*reinterpret_cast<const __half2*>(&wsw[j2]));
+        const float2 of = __half22float2(*reinterpret_cast<const __half2*>(&olw[j2]));
+        const float2 bf = __half22float2(*reinterpret_cast<const __half2*>(&bsw[j2]));
+        float v[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = g * 8 + j2 * 2 + h;
+          float t = __fmul_rn(__fmul_rn(static_cast<float>(static_cast<int32_t>(acc[c])), xs), h ? wf.y : wf.x);
+          if (HAS_O) t = __fadd_rn(t, __uint_as_float(oacc[c]));
+          if (has_outl) t = __fadd_rn(t, h ? of.y : of.x);
+          if (has_bias) t = __fadd_rn(t, h ? bf.y : bf.x);
+          if (p.act == 1) t = silu_f(t);
+          v[h] = t;
+        }
+        const __half2 o2 = __floats2half2_rn(v[0], v[1]);
+        ow[j2] = *reinterpret_cast<const uint32_t*>(&o2);
+      }
+      *reinterpret_cast<uint4*>(p.y + static_cast<size_t>(row) * p.N + ng) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+  }
+}
+
+template <int BN, bool W4>
+__global__ void __launch_bounds__(GemmCfg<BN, W4>::NUM_THREADS, 1)
+mixq_linear_kernel(const __grid_constant__ LinearParams p) {
+  using Cfg = GemmCfg<BN, W4>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int BM = Cfg::BM;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bar_empty = bar_full + STAGES;
+  uint64_t* bar_ready = bar_empty + STAGES;  // W4: unpacked B tile is ready for the MMA
+  uint64_t* bar_tfull = bar_ready + STAGES;
+  uint64_t* bar_tempty = bar_tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+
+  auto stage_a = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
+  auto stage_b = [&](int s) { return smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
+  auto stage_bp = [&](int s) { return smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES + Cfg::B_BYTES; };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int nk = (p.K + 127) / 128;                 // int8 k-blocks of 128
+  const int nko = (p.n_out + 63) / 64;              // fp16 outlier k-blocks of 64
+  const int nkt = nk + nko;
+  const int MB = (p.M + BM - 1) / BM;
+  const int NB = (p.N + BN - 1) / BN;
+  const int ntiles = MB * NB;
+  const int acc_cols = BN * (nko > 0 ? 2 : 1);      // s32 accumulator [+ f32 outlier accumulator]
+  const int nacc = (2 * acc_cols <= 512) ? 2 : 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tm_a);
+    tma_prefetch_desc(&p.tm_b);
+    if (nko > 0) {
+      tma_prefetch_desc(&p.tm_oa);
+      tma_prefetch_desc(&p.tm_ob);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_empty[s], 1);
+      mbar_init(&bar_ready[s], 128);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar_tfull[s], 1);
+      mbar_init(&bar_tempty[s], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ------------------------------------------------------------------ producer helpers
+  // Work items of this CTA in issue order: (tile i, k-block kb), kb in [0, nkt).
+  // Pre-barrier we may only touch the weight operand; the activation operand exists after phase A.
+  constexpr uint32_t kStageTx = Cfg::A_BYTES + (W4 ? 0 : Cfg::B_BYTES);
+  auto produce = [&](int tile, int kb, int s, bool do_act, bool do_wgt, bool arm) {
+    const int m0 = (tile % MB) * BM;
+    const int n0 = (tile / MB) * BN;
+    if (kb < nk) {
+      if (arm) mbar_arrive_expect_tx(&bar_full[s], Cfg::A_BYTES + (W4 ? Cfg::BP_BYTES : Cfg::B_BYTES));
+      if (do_wgt) {
+        if (W4) tma_load_2d(&p.tm_b, &bar_full[s], stage_bp(s), kb * 64, n0, kEvictFirst);
+        else tma_load_2d(&p.tm_b, &bar_full[s], stage_b(s), kb * 128, n0, kEvictFirst);
+      }
+      if (do_act) tma_load_2d(&p.tm_a, &bar_full[s], stage_a(s), kb * 128, m0, kEvictLast);
+    } else {
+      const int ko = (kb - nk) * 64;
+      if (arm) mbar_arrive_expect_tx(&bar_full[s], Cfg::A_BYTES + Cfg::B_BYTES);
+      if (do_wgt) tma_load_2d(&p.tm_ob, &bar_full[s], stage_b(s), ko, n0, kEvictFirst);
+      if (do_act) tma_load_2d(&p.tm_oa, &bar_full[s], stage_a(s), ko, m0, kEvictLast);
+    }
+    (void)kStageTx;
+  };
+
+  const int my_tiles = (static_cast<int>(blockIdx.x) < ntiles)
+                           ? (ntiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1
+                           : 0;
+  const int my_items = my_tiles * nkt;
+  const int n_pre = (p.fused_prologue && my_items > 0) ? (my_items < STAGES ? my_items : STAGES) : 0;
+
+  // ------------------------------------------------------------------ phase A (fused prologue)
+  if (p.fused_prologue) {
+    if (warp == 0 && lane == 0) {
+      for (int it = 0; it < n_pre; ++it) {
+        const int tile = blockIdx.x + (it / nkt) * gridDim.x;
+        produce(tile, it % nkt, it, /*act*/ false, /*wgt*/ true, /*arm*/ true);
+      }
+    }
+    __syncwarp();
+    const int nwarps = blockDim.x >> 5;
+    for (int m = warp * gridDim.x + blockIdx.x; m < p.M; m += nwarps * gridDim.x) quantize_row_warp(p.rq, m, lane);
+    fence_proxy_async_all();   // q_x / act_outliers were written through the generic proxy; TMA reads them next
+    grid_barrier(p.grid_sync);
+  }
+
+  // ------------------------------------------------------------------ roles
+  if (warp == 0) {
+    if (lane == 0) {
+      fence_proxy_async_all();
+      int it = 0, s = 0;
+      uint32_t ph = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int tile = blockIdx.x + i * gridDim.x;
+        for (int kb = 0; kb < nkt; ++kb, ++it) {
+          if (it < n_pre) {
+            produce(tile, kb, s, true, false, false);
+          } else {
+            mbar_wait(&bar_empty[s], ph ^ 1, 1, s);
+            produce(tile, kb, s, true, true, true);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_i8 = make_idesc_i8(BM, BN);
+      constexpr uint32_t idesc_f16 = make_idesc_f16(BM, BN);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int as = i % nacc;
+        const uint32_t aph = (i / nacc) & 1;
+        mbar_wait(&bar_tempty[as], aph ^ 1, 2, as);
+        tc_fence_after();
+        const uint32_t d_int = tmem_base + as * acc_cols;
+        const uint32_t d_out = d_int + BN;
+        for (int kb = 0; kb < nkt; ++kb) {
+          if (W4) mbar_wait(&bar_ready[s], ph, 3, s);
+          mbar_wait(&bar_full[s], ph, 4, s);
+          tc_fence_after();
+          const uint64_t da = make_sw128_kmajor_desc(smem_u32(stage_a(s)));
+          const uint64_t db = make_sw128_kmajor_desc(smem_u32(stage_b(s)));
+          if (kb < nk) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)   // 4 x (K = 32 int8 = 32 B); +2 in the >>4-encoded start address
+              umma_i8(d_int, da + 2 * k, db + 2 * k, idesc_i8, (kb | k) != 0);
+          } else {
+            const int kbo = kb - nk;
+            int ksteps = (p.n_out - kbo * 64 + 15) / 16;
+            if (ksteps > 4) ksteps = 4;
+            for (int k = 0; k < ksteps; ++k)  // K = 16 fp16 = 32 B
+              umma_f16(d_out, da + 2 * k, db + 2 * k, idesc_f16, (kbo | k) != 0);
+          }
+          umma_commit(&bar_empty[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&bar_tfull[as]);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    for (int i = 0; i < my_tiles; ++i) {
+      const int tile = blockIdx.x + i * gridDim.x;
+      const int m0 = (tile % MB) * BM;
+      const int n0 = (tile / MB) * BN;
+      const int as = i % nacc;
+      const uint32_t aph = (i / nacc) & 1;
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      float xs = 0.f;
+      if (p.epilogue == EPI_DEQUANT_F16 && row_ok) xs = __half2float(p.x_scale[row]);
+
+      mbar_wait(&bar_tfull[as], aph, 5, as);
+      tc_fence_after();
+      const uint32_t t_int = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * acc_cols;
+      const uint32_t t_out = t_int + BN;
+
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (nko > 0) epilogue_chunk<true>(p, t_int + c0, t_out + c0, row, row_ok, n0 + c0, xs);
+        else epilogue_chunk<false>(p, t_int + c0, 0u, row, row_ok, n0 + c0, xs);
+      }
+      tc_fence_before();
+      mbar_arrive(&bar_tempty[as]);
+    }
+  } else if (W4 && warp >= 8) {
+    // Nibble unpack: thread t owns weight rows t, t+128, ... of the tile.  Packed row = 64 B (128 nibbles,
+    // low nibble = even k: linear.py:14-18); unpacked row = 128 B written as 8 x 16-byte chunks at the
+    // SWIZZLE_128B position chunk ^ (row & 7) — the layout the UMMA descriptor expects.
+    const int t = threadIdx.x - 256;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      for (int kb = 0; kb < nkt; ++kb) {
+        mbar_wait(&bar_full[s], ph, 6, s);
+        if (kb < nk) {
+          for (int r = t; r < BN; r += 128) {
+            const uint4* src = reinterpret_cast<const uint4*>(stage_bp(s) + r * 64);
+            uint8_t* drow = stage_b(s) + r * 128;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              const uint4 pk = src[v];
+              const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+              uint32_t o[8];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t lo = __vsub4((w[j] & 0x0F0F0F0Fu) ^ 0x08080808u, 0x08080808u);
+                const uint32_t hi = __vsub4(((w[j] >> 4) & 0x0F0F0F0Fu) ^ 0x08080808u, 0x08080808u);
+                o[2 * j] = __byte_perm(lo, hi, 0x5140);
+                o[2 * j + 1] = __byte_perm(lo, hi, 0x7362);
+              }
+              const int c0 = (2 * v) ^ (r & 7);
+              const int c1 = (2 * v + 1) ^ (r & 7);
+              *reinterpret_cast<uint4*>(drow + c0 * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<uint4*>(drow + c1 * 16) = make_uint4(o[4], o[5], o[6], o[7]);
+            }
+          }
+          fence_proxy_async_smem();   // generic-proxy smem writes -> visible to tcgen05.mma (async proxy)
+        }
+        mbar_arrive(&bar_ready[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template __global__ void mixq_linear_kernel<128, false>(const __grid_constant__ LinearParams);
+template __global__ void mixq_linear_kernel<256, false>(const __grid_constant__ LinearParams);
+template __global__ void mixq_linear_kernel<128, true>(const __grid_constant__ LinearParams);
+template __global__ void mixq_linear_kernel<256, true>(const __grid_constant__ LinearParams);
+
+}  // namespace mixq

@@ -1,0 +1,47 @@
+// Kernel-side parameter block shared between mixq_gemm.cu and mixq_api.cu.
+#pragma once
+#include "ptx.cuh"
+#include "rowquant.cuh"
+
+namespace mixq {
+
+enum EpilogueKind : int { EPI_DEQUANT_F16 = 0, EPI_RAW_I32 = 1 };
+
+struct LinearParams {
+  CUtensorMap tm_a;    // q_x   int8 [M,K]      box 128 B x 128 rows, SWIZZLE_128B
+  CUtensorMap tm_b;    // q_w   int8 [N,K]      box 128 B x BN rows  (W4: uint8 [N,K/2], box 64 B x BN rows)
+  CUtensorMap tm_oa;   // activation outliers fp16 [M,n_ind]  box 64 x 128
+  CUtensorMap tm_ob;   // weight_cache        fp16 [N,n_ind]  box 64 x BN
+  RowQuantArgs rq;     // phase A (fused prologue); rq.q_x == nullptr -> no prologue
+  const __half* x_scale;
+  const __half* scale_col;
+  const __half* bias;
+  const __half* outl;  // optional precomputed fp16 [M,N] addend (mixlib.int8FusedDequantize's 5th argument)
+  int ld_outl;
+  __half* y;
+  int32_t* y_i32;
+  int M, N, K;
+  int n_out;           // outlier columns multiplied on the tensor cores (0 = none)
+  int act;
+  int epilogue;
+  int fused_prologue;
+  uint32_t* grid_sync;
+};
+
+template <int BN, bool W4>
+struct GemmCfg {
+  static constexpr int BM = 128;
+  static constexpr int BK_BYTES = 128;                       // one SWIZZLE_128B row: 128 int8 or 64 fp16
+  static constexpr int A_BYTES = BM * BK_BYTES;              // 16 KB
+  static constexpr int B_BYTES = BN * BK_BYTES;              // 16 / 32 KB
+  static constexpr int BP_BYTES = W4 ? BN * 64 : 0;          // packed-nibble landing buffer
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES + BP_BYTES;
+  static constexpr int STAGES = W4 ? (BN == 128 ? 5 : 3) : (BN == 128 ? 6 : 4);
+  static constexpr int NUM_THREADS = W4 ? 384 : 256;         // W4 adds 4 unpack warps
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool W4>
+__global__ void mixq_linear_kernel(const __grid_constant__ LinearParams p);
+
+}  // namespace mixq

@@ -1,0 +1,128 @@
+// Small HBM-bound kernels around the GEMM: standalone row quantisation / RMSNorm, outlier gather,
+// split-path dequant, nibble unpack, weight-column gather, outlier-column compaction.
+// Each restates one mixlib.* call of the reference (see include/mixq.h for file:line).
+#include "mixq_kernels.cuh"
+
+namespace mixq {
+
+// One warp per row, rows strided over the whole grid.
+__global__ void __launch_bounds__(256) rowquant_kernel(const RowQuantArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  for (int m = gw; m < a.M; m += nw) quantize_row_warp(a, m, lane);
+}
+
+__global__ void extract_outliers_kernel(const int32_t* __restrict__ ind, int n_ind, __half* x, __half* out,
+                                        int ld_out, int M, int K) {
+  const long long total = static_cast<long long>(M) * n_ind;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(i / n_ind);
+    const int j = static_cast<int>(i - static_cast<long long>(m) * n_ind);
+    const int c = ind[j];
+    __half* px = x + static_cast<size_t>(m) * K + c;
+    out[static_cast<size_t>(m) * ld_out + j] = *px;
+    *px = __float2half_rn(0.f);
+  }
+}
+
+// y = act(fp16((float(acc)*xs[m])*ws[n] + outl[m,n])), 8 columns per thread.
+__global__ void dequant_i32_kernel(const int32_t* __restrict__ acc, const __half* __restrict__ x_scale,
+                                   const __half* __restrict__ scale_col, const __half* __restrict__ outl,
+                                   int ld_outl, __half* __restrict__ y, int M, int N, int act) {
+  const int nv = N >> 3;
+  const long long total = static_cast<long long>(M) * nv;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(i / nv);
+    const int n = static_cast<int>(i - static_cast<long long>(m) * nv) * 8;
+    const float xs = __half2float(x_scale[m]);
+    const int4 a0 = *reinterpret_cast<const int4*>(acc + static_cast<size_t>(m) * N + n);
+    const int4 a1 = *reinterpret_cast<const int4*>(acc + static_cast<size_t>(m) * N + n + 4);
+    const int av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    H8 ws, ol, out;
+    ws.u = __ldg(reinterpret_cast<const uint4*>(scale_col + n));
+    if (outl != nullptr) ol.u = *reinterpret_cast<const uint4*>(outl + static_cast<size_t>(m) * ld_outl + n);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = __fmul_rn(__fmul_rn(static_cast<float>(av[j]), xs), __half2float(ws.h[j]));
+      if (outl != nullptr) v = __fadd_rn(v, __half2float(ol.h[j]));
+      if (act == 1) v = __fdividef(v, 1.0f + __expf(-v));
+      out.h[j] = __float2half_rn(v);
+    }
+    *reinterpret_cast<uint4*>(y + static_cast<size_t>(m) * N + n) = out.u;
+  }
+}
+
+__device__ __forceinline__ int nibble_at(const uint8_t* q_w_packed, size_t row, int K, int c) {
+  const uint8_t b = q_w_packed[row * (K >> 1) + (c >> 1)];
+  const int nib = (c & 1) ? (b >> 4) : (b & 0xF);
+  return (nib ^ 8) - 8;  // two's-complement sign extension of 4 bits
+}
+
+__global__ void unpack_int4_cols_kernel(const uint8_t* __restrict__ q_w_packed, const int32_t* __restrict__ ind,
+                                        int n_ind, __half* out, int ld_out, int N, int K) {
+  const long long total = static_cast<long long>(N) * n_ind;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / n_ind);
+    const int j = static_cast<int>(i - static_cast<long long>(n) * n_ind);
+    out[static_cast<size_t>(n) * ld_out + j] = __int2half_rn(nibble_at(q_w_packed, n, K, ind[j]));
+  }
+}
+
+// wc[n, col0+j] = fp16(q_w[n, ind[j]]) * scale_col[n]   (one fp16 multiply, as torch does on fp16 tensors)
+__global__ void gather_weight_cols_kernel(const void* __restrict__ q_w, const __half* __restrict__ scale_col,
+                                          const int32_t* __restrict__ ind, int n_ind, __half* wc, int ld_wc,
+                                          int col0, int N, int K, int bit) {
+  const long long total = static_cast<long long>(N) * n_ind;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / n_ind);
+    const int j = static_cast<int>(i - static_cast<long long>(n) * n_ind);
+    const int c = ind[j];
+    int q;
+    if (bit == 8) q = static_cast<const int8_t*>(q_w)[static_cast<size_t>(n) * K + c];
+    else q = nibble_at(static_cast<const uint8_t*>(q_w), n, K, c);
+    wc[static_cast<size_t>(n) * ld_wc + col0 + j] = __hmul(__int2half_rn(q), scale_col[n]);
+  }
+}
+
+// Single block: ordered compaction of the K flag bytes into ascending column ids.
+__global__ void __launch_bounds__(1024) compact_cols_kernel(uint8_t* col_over, int K, int32_t* ind_out,
+                                                            int max_new, int32_t* n_new) {
+  __shared__ int warp_tot[32];
+  __shared__ int base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < K; c0 += blockDim.x) {
+    const int c = c0 + threadIdx.x;
+    const int f = (c < K && col_over[c] != 0) ? 1 : 0;
+    if (c < K) col_over[c] = 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    const int pre = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int woff = 0, tot = 0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) {
+      if (w < warp) woff += warp_tot[w];
+      tot += warp_tot[w];
+    }
+    const int pos = base + woff + pre;
+    if (f && pos < max_new) ind_out[pos] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) base += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_new = base;
+}
+
+__global__ void mul_inplace_kernel(__half2* a, const __half2* __restrict__ b, long long n2) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n2;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    a[i] = __hmul2(a[i], b[i]);
+}
+
+}  // namespace mixq

@@ -1,0 +1,18 @@
+#pragma once
+#include "rowquant.cuh"
+
+namespace mixq {
+
+__global__ void rowquant_kernel(const RowQuantArgs a);
+__global__ void extract_outliers_kernel(const int32_t* ind, int n_ind, __half* x, __half* out, int ld_out, int M,
+                                        int K);
+__global__ void dequant_i32_kernel(const int32_t* acc, const __half* x_scale, const __half* scale_col,
+                                   const __half* outl, int ld_outl, __half* y, int M, int N, int act);
+__global__ void unpack_int4_cols_kernel(const uint8_t* q_w_packed, const int32_t* ind, int n_ind, __half* out,
+                                        int ld_out, int N, int K);
+__global__ void gather_weight_cols_kernel(const void* q_w, const __half* scale_col, const int32_t* ind, int n_ind,
+                                          __half* wc, int ld_wc, int col0, int N, int K, int bit);
+__global__ void compact_cols_kernel(uint8_t* col_over, int K, int32_t* ind_out, int max_new, int32_t* n_new);
+__global__ void mul_inplace_kernel(__half2* a, const __half2* b, long long n2);
+
+}  // namespace mixq
