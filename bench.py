@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py — the headline metric of BASELINE.json on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl mixq|reference] [--model llama-2-7b] [--batch 512] [--bit 8]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+metric: Llama-2-7B W8A8O16 decode tokens/s at batch 512 (/root/reference/benchflops.py:96-128, :222 — every step is one
+independent [512,1] forward; "decode length 1024" there is the number of timed iterations, not a KV length), random-init
+weights with ~1 % forced outlier channels, synthetic tokens.  A "step" = one pass of the MixLinear hot path over one batch:
+the whole decode step (32 layers x 5 MixLinears + norms + attention glue + fp16 lm_head), replayed from one CUDA graph.
+
+N > 1 shards every Linear column-/row-wise over N ranks (one NCCL all-reduce per row-parallel Linear), total work fixed:
+"scaling": "strong".
+
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for how each field is obtained.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="mixq", choices=["mixq", "reference"])
+    ap.add_argument("--model", default="llama-2-7b")
+    ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--bit", type=int, default=8, choices=[4, 8])
+    ap.add_argument("--layers", type=int, default=None, help="debug: fewer layers (the number is reported, never default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm_gbs=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+# ----------------------------------------------------------------------------------------------- CPU arms
+def cpu_layer_sample(cfg_name, batch, bit, budget_s=12.0, build_only=False):
+    """One decoder layer's five MixLinears + both fused norms, steady state, through the CPU oracle (numpy/BLAS, all host
+    threads).  Returns (seconds per layer, cores, description).  This is bench.py's `cpu_baseline` / `--impl reference`
+    leg — the one place outside tests/ that executes oracle/ (as the thing timed beside the product, never as the product)."""
+    import numpy as np
+    from mixq_b200.llama import CONFIGS
+    from oracle import mixq_oracle as O
+    cfg = CONFIGS[cfg_name]
+    H, I, D = cfg.hidden, cfg.intermediate, cfg.head_dim
+    rng = np.random.default_rng(0)
+    cache = O.MixLibCacheOracle(batch, 6, bit)
+    n_out = max(1, round(0.01 * H))
+
+    def lin(n, k, b):
+        q = rng.integers(-127, 128, (n, k), dtype=np.int8) if b == 8 else rng.integers(0, 256, (n, k // 2), dtype=np.uint8)
+        s = (rng.random((1, n)) * 2e-4 + 1e-4).astype(np.float16)   # keeps the synthetic activations inside fp16
+        m = O.MixLinearOracle(q, s, b, None, cache)
+        m.add_outliers = False
+        m.ind = np.sort(rng.permutation(k)[:max(1, round(0.01 * k))]).astype(np.int32)
+        m.weight_cache = O.weight_cache_columns(q, s, m.ind, b)
+        m.forward_without_precondition_len = len(m.ind)
+        return m
+    qkv_n = (cfg.heads + 2 * cfg.kv_heads) * D
+    W_pack, o_proj = lin(qkv_n, H, bit), lin(H, cfg.heads * D, 8)
+    up, gate, down = lin(I, H, bit), lin(I, H, bit), lin(H, I, 8)
+    gate.ind, gate.weight_cache = up.ind, O.weight_cache_columns(gate.q_weight, gate.scale_col, up.ind, bit)
+    ln = np.ones(H, np.float16)
+    h = rng.standard_normal((batch, H)).astype(np.float16)
+    _ = n_out
+
+    def one_layer(h):
+        out, ao, q_x, xs = O.rmsnorm_extract_outliers(h, ln, cfg.eps, W_pack.ind, bit)
+        cache.activation_outliers, cache.q_xcache = ao, q_x
+        cache.x_scale[:batch] = xs
+        qkv = W_pack.forward(out, cache)
+        attn = qkv[:, -cfg.heads * D:] if cfg.kv_heads == cfg.heads else np.repeat(
+            qkv[:, -cfg.kv_heads * D:].reshape(batch, cfg.kv_heads, D), cfg.heads // cfg.kv_heads, 1).reshape(batch, -1)
+        h = (o_proj.forward(np.ascontiguousarray(attn).copy(), None, True).astype(np.float32) + h).astype(np.float16)
+        out, ao, q_x, xs = O.rmsnorm_extract_outliers(h, ln, cfg.eps, up.ind, bit)
+        cache.activation_outliers, cache.q_xcache = ao, q_x
+        cache.x_scale[:batch] = xs
+        u = up.forward(out, cache)
+        g = gate.forward_without_precondition_fused_silu(out, cache)
+        g = (g.astype(np.float32) * u.astype(np.float32)).astype(np.float16)
+        return (down.forward(g, None, True).astype(np.float32) + h).astype(np.float16)
+
+    desc = f"1 of {cfg.layers} decoder layers (5 MixLinears + 2 fused norms, M={batch}), numpy f64 BLAS"
+    if build_only:
+        return (lambda: one_layer(h)), os.cpu_count(), desc
+    one_layer(h)   # warm BLAS
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        one_layer(h)
+        reps += 1
+        el = time.perf_counter() - t0
+        if (reps >= 3 and el > budget_s / 2) or el > budget_s or reps >= 20:
+            break
+    return el / reps, os.cpu_count(), desc + f", {reps} reps"
+
+
+def torch_cpu_linear_sample(cfg_name, batch):
+    """torch-CPU fp32 F.linear (the un-quantised Linear MixLinear replaces) on the five Linear shapes of one layer."""
+    import torch
+    from mixq_b200.llama import CONFIGS
+    cfg = CONFIGS[cfg_name]
+    H, I, D = cfg.hidden, cfg.intermediate, cfg.head_dim
+    torch.set_num_threads(os.cpu_count())
+    shapes = [((cfg.heads + 2 * cfg.kv_heads) * D, H), (H, H), (I, H), (I, H), (H, I)]
+    tot = 0.0
+    for n, k in shapes:
+        x, w = torch.randn(batch, k), torch.randn(n, k)
+        torch.nn.functional.linear(x, w)
+        best = 1e9
+        for _ in range(3):
+            t0 = time.perf_counter()
+            torch.nn.functional.linear(x, w)
+            best = min(best, time.perf_counter() - t0)
+        tot += best
+    return tot
+
+
+def run_reference(args):
+    """`--impl reference`: the path on the host cores (the reference has no CPU implementation of its CUDA kernels and its
+    mixlib/EETQ sources are not in the tree, so this is the oracle port)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from mixq_b200.llama import CONFIGS
+    cfg = CONFIGS[args.model]
+    times = []
+    # each step = a bounded sample of the workload: ONE decoder layer on all host threads; the step time is that layer
+    # time x the number of layers (every layer does identical work)
+    run_once, cores, desc = cpu_layer_sample(args.model, args.batch, args.bit, build_only=True)
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        run_once()
+        if i >= args.warmup:
+            times.append((time.perf_counter() - t0) * cfg.layers)
+    step_s = sum(times) / len(times)
+    val = args.batch / step_s
+    line = {
+        "impl": "reference", "metric": "llama_decode_tokens_per_s", "value": val, "unit": "tokens/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+        "config": {"workload": f"{args.model} W{args.bit}A{args.bit}O16 decode step, batch {args.batch}, q_len 1, empty KV cache "
+                               "(benchflops.py:96-128)", "parallelism": "cpu", "bit": args.bit},
+        "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": desc + f", x{cfg.layers} layers extrapolated"},
+        "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def run_mixq(args):
+    import torch
+    import torch.distributed as dist
+    from mixq_b200 import _lib
+    from mixq_b200.linear import MixLinear_GEMM
+    from mixq_b200.llama import CONFIGS, LlamaDecoder
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    _lib.load()   # fails loudly when the extension is missing: there is no fallback
+    cfg = CONFIGS[args.model]
+    B = args.batch
+
+    model = LlamaDecoder(cfg, batch=B, bit=args.bit, seed=0, outlier_frac=0.01, rank=rank, world_size=world, layers=args.layers)
+    gen = torch.Generator().manual_seed(0)
+    n_tok_sets = 8
+    host_tokens = [torch.randint(0, cfg.vocab, (B, 1), generator=gen).pin_memory() for _ in range(n_tok_sets)]
+    host_next = torch.empty(B, dtype=torch.int64).pin_memory()
+    tok0 = host_tokens[0].cuda()
+    # the reference's first cache.stop (=2) forwards: online outlier discovery, host-synchronising (linear.py:200-226)
+    ok = model.discover(tok0)
+    assert ok, "outlier discovery did not converge after cache.stop calls"
+    n0 = _lib.launch_count()
+    model.step(tok0)
+    launches_per_step = _lib.launch_count() - n0
+    model.capture(tok0)
+    dev_tokens = [t.cuda() for t in host_tokens]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM, K graph replays, device-timed
+    for i in range(args.warmup):
+        model.replay(dev_tokens[i % n_tok_sets])
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        model.replay(dev_tokens[i % n_tok_sets])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    # ---- e2e: host tokens -> H2D -> step -> argmax -> D2H, every step, through the public call
+    for i in range(2):
+        model.replay(dev_tokens[0])
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        logits = model.replay(host_tokens[i % n_tok_sets])          # pinned host -> static device buffer (H2D)
+        host_next.copy_(torch.argmax(logits, dim=-1), non_blocking=True)   # result D2H
+        torch.cuda.current_stream().synchronize()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+
+    # ---- roofline of the dominant kernel (mixq_linear_kernel): per-launch CUDA-event time over all layers' distinct weights
+    pk = peaks()
+    kinds = ["W_pack", "o_proj", "up_proj", "gate_proj", "down_proj"]
+    h = torch.randn(B, cfg.hidden, device="cuda").half()
+    per_kind = {}
+    tot_t = tot_fl = tot_by = 0.0
+    for kind in kinds:
+        mods = [L[kind] for L in model.layers]
+        K_in = mods[0].in_features
+        xin = torch.randn(B, K_in, device="cuda").half()
+        xw = xin.clone()
+
+        def launch(m):
+            if kind in ("W_pack", "up_proj"):
+                return m.forward_norm_fused(h, model.layers[0]["ln1"], cfg.eps)
+            if kind == "gate_proj":
+                return m.forward_without_preconditionFusedSilu(h, model.cache)
+            return m(xw, None, True)
+        if kind == "gate_proj":   # needs up_proj's q_x in the cache
+            model.layers[0]["up_proj"].forward_norm_fused(h, model.layers[0]["ln2"], cfg.eps)
+        for m in mods[:3]:
+            launch(m)
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        g0.record()
+        for _ in range(reps):
+            for m in mods:
+                launch(m)
+        g1.record()
+        torch.cuda.synchronize()
+        t_launch = g0.elapsed_time(g1) * 1e-3 / (reps * len(mods))
+        m0 = mods[0]
+        N_, n_ = m0.out_features, m0._n_ind
+        fl = 2.0 * B * N_ * K_in
+        by = N_ * K_in * m0.bit / 8 + 2 * B * K_in + 2 * B * N_ + 2 * N_ + 2 * n_ * N_
+        per_kind[kind] = {"N": N_, "K": K_in, "n_outliers": n_, "us": t_launch * 1e6, "tflops": fl / t_launch / 1e12,
+                          "gbs": by / t_launch / 1e9}
+        tot_t += t_launch
+        tot_fl += fl
+        tot_by += by
+    int8_peak = 2.0 * pk["bf16_sustained"]
+    ach_tf, ach_gb = tot_fl / tot_t / 1e12, tot_by / tot_t / 1e9
+    tensor_bound = (tot_fl / (int8_peak * 1e12)) >= (tot_by / (pk["hbm_gbs"] * 1e9))
+    roofline = {
+        "kernel": "mixq_linear_kernel (5 launches per layer: W_pack, o_proj, up_proj, gate_proj, down_proj)",
+        "bound": "tensor" if tensor_bound else "hbm",
+        "achieved": ach_tf if tensor_bound else ach_gb, "peak": int8_peak if tensor_bound else pk["hbm_gbs"],
+        "unit": "TFLOP/s" if tensor_bound else "GB/s",
+        "frac": (ach_tf / int8_peak) if tensor_bound else (ach_gb / pk["hbm_gbs"]),
+        "traffic": None,
+        "peak_source": f"{pk['source']}: int8 tensor pipe taken as 2 x bf16_tflops_sustained ({pk['bf16_sustained']}); hbm_gbs {pk['hbm_gbs']}",
+        "other_bound": {"tflops": ach_tf, "frac_int8": ach_tf / int8_peak, "gbs": ach_gb, "frac_hbm": ach_gb / pk["hbm_gbs"]},
+        "per_linear": per_kind, "linear_share_of_step": tot_t * len(model.layers) / (ms * 1e-3 / args.steps),
+    }
+
+    if rank == 0:
+        step_s = ms * 1e-3 / args.steps
+        fl_step, by_step = model.algorithmic_work()
+        line = {
+            "metric": "llama_decode_tokens_per_s", "value": B / step_s, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "int8" if args.bit == 8 else "int4->int8", "data": "synthetic",
+            "config": {"workload": f"{args.model} W{args.bit}A{args.bit}O16 decode step, batch {B}, q_len 1, empty KV cache "
+                                   "(benchflops.py:96-128), ~1% forced outlier channels",
+                       "layers": len(model.layers), "global_batch": B, "parallelism": f"tp{world}", "bit": args.bit,
+                       "l2": "weights (>= 6 GB per step) exceed the 126 MB L2: inputs larger than L2, no flush",
+                       "outliers_layer0": {k: m._n_ind for k, m in model.layers[0].items() if isinstance(m, MixLinear_GEMM)},
+                       "cuda_graph": True},
+            "e2e": {"value": B / (ms_e2e * 1e-3 / args.steps), "unit": "tokens/s", "h2d_bytes_per_step": B * 8,
+                    "d2h_bytes_per_step": B * 8, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": sampler.result(),
+            "roofline": roofline,
+            "step_work": {"linear_tflop": fl_step / 1e12, "linear_gb": by_step / 1e9,
+                          "tflops_whole_step": fl_step / step_s / 1e12},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            t_layer, cores, desc = cpu_layer_sample(args.model, B, args.bit)
+            t_lin = torch_cpu_linear_sample(args.model, B)
+            line["cpu_baseline"] = {"value": B / (t_layer * cfg.layers), "unit": "tokens/s", "cores": cores, "kind": "port",
+                                    "sample": desc + f", x{cfg.layers} layers extrapolated",
+                                    "torch_fp32_linear_tokens_per_s": B / (t_lin * cfg.layers)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_mixq(args)
+
+
+if __name__ == "__main__":
+    main()

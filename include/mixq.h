@@ -15,7 +15,8 @@
  *     mixq_last_error() returns a human-readable message for the calling thread;
  *   - matrices are row-major and dense unless an explicit leading dimension `ld*` (in elements)
  *     is given; fp16 = IEEE binary16; activations x[M,K], weights q_w[N,K] (K contiguous);
- *   - M >= 1; K % 16 == 0; N % 8 == 0 (TMA / 16-byte vector alignment); base pointers 16-byte aligned.
+ *   - M >= 1; K % 16 == 0; N % 8 == 0 (TMA / 16-byte vector alignment); base pointers 16-byte aligned;
+ *     the activation prologue (FindRowScale, RMSNorm, fused phase A) needs K <= 32768.
  *   - thread-compatible, not thread-safe on the same buffers (the reference shares one
  *     MixLibCache across all layers and relies on single-stream order: Cache.py:5-25).
  */
@@ -48,6 +49,12 @@ int mixq_set_tile_n(int tile_n);
  * q_x is int8 [M,K] for bit 8 AND bit 4 (bit 4: values in [-7,7], one per byte — the packed form is
  * opaque to the reference's Python, and Blackwell has no int4 MMA to feed it to). */
 int mixq_find_row_scale(const void* x, void* x_scale, void* q_x, int M, int K, int bit, void* stream);
+
+/* Same, plus the scan the reference does on the host side of the call (linear.py:201 and FindOutliers,
+ * linear.py:157-161): *over_flag |= 1 when any x_scale[m] > fp16(sigma/qmax); col_over[c] = 1 for every column
+ * with some |x[m,c]| > sigma.  Either output may be NULL. */
+int mixq_find_row_scale_scan(const void* x, void* x_scale, void* q_x, int M, int K, int bit, float sigma,
+                             uint8_t* col_over, uint32_t* over_flag, void* stream);
 
 /* ---- mixlib.ExtractOutliersAndSetToZeros(ind, x) -> out[M,n]   (linear.py:189, :205)
  * out[m,j] = x[m,ind[j]];  x[m,ind[j]] = 0 IN PLACE.  ld_out >= n_ind. */
@@ -110,13 +117,13 @@ typedef struct mixq_linear_args {
   /* activations */
   void* x;                 /* fp16 [M,K]; outlier columns zeroed in place unless norm_weight is set */
   const void* norm_weight; /* optional fp16 [K]: x is un-normed, norm_out receives RMSNorm(x)*w */
-  void* norm_out;          /* fp16 [M,K] (required with norm_weight) */
+  void* norm_out;          /* fp16 [M,K] RMSNorm(x)*w with the ind columns zeroed, or NULL when nobody reads it */
   float eps;
   int M, N, K;
   /* weights */
   const void* q_weight;    /* int8 [N,K] (bit 8) | uint8 [N,K/2] packed nibbles (bit 4) */
   const void* scale_col;   /* fp16 [N] */
-  const void* bias;        /* fp16 [N] or NULL */
+  const void* bias;        /* fp16 [N] or NULL; y = fp16(y + bias) as a second rounding (linear.py:284-285) */
   int bit;                 /* 8 or 4 */
   /* fp16 outlier path */
   const int32_t* ind;      /* [n_ind] */
@@ -133,6 +140,8 @@ typedef struct mixq_linear_args {
   uint8_t* col_over;       /* [K] bytes or NULL */
   uint32_t* over_flag;     /* or NULL; |= 1 when max(x_scale) > fp16(sigma/qmax) (linear.py:201) */
   /* output */
+  const void* residual;    /* fp16 [M, ld_res] or NULL: y = fp16(y + residual) — the decoder layer's residual add */
+  int ld_res;
   void* y;                 /* fp16 [M,N] */
   int act;                 /* MIXQ_ACT_* */
   /* control */
@@ -142,6 +151,12 @@ typedef struct mixq_linear_args {
 } mixq_linear_args;
 
 int mixq_linear_fused(const mixq_linear_args* args /* host */, void* stream);
+
+/* ---- decode-harness glue, outside the quantised path (the reference calls flash-attn: fused/attn.py:239-258).
+ * RoPE(q,k at position past_len, HF rotate_half) + single-query attention over an optional KV cache
+ * [M, Hkv, cache_cap, D] (new k/v appended at past_len) -> out[M, H*D].  qkv row = [H*D | Hkv*D | Hkv*D]. */
+int mixq_rope_attention_decode(const void* qkv, void* k_cache, void* v_cache, int cache_cap, int past_len, void* out,
+                               int M, int H, int Hkv, int D, float theta, void* stream);
 
 /* elementwise gate *= up (mlp.py:64) kept for the decode harness */
 int mixq_mul_inplace(void* a, const void* b, long long n, void* stream);

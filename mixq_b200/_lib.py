@@ -43,6 +43,8 @@ class LinearArgs(C.Structure):
         ("sigma", C.c_float),
         ("col_over", C.c_void_p),
         ("over_flag", C.c_void_p),
+        ("residual", C.c_void_p),
+        ("ld_res", C.c_int),
         ("y", C.c_void_p),
         ("act", C.c_int),
         ("skip_prologue", C.c_int),
@@ -56,6 +58,7 @@ _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 # name -> argtypes; every function returns int unless listed in _RESTYPES
 SIGNATURES = {
     "mixq_find_row_scale": [_vp, _vp, _vp, _i, _i, _i, _vp],
+    "mixq_find_row_scale_scan": [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp],
     "mixq_extract_outliers_and_set_to_zeros": [_vp, _i, _vp, _vp, _i, _i, _i, _vp],
     "mixq_int8_fused_dequantize": [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp],
     "mixq_int4_fused_dequantize": [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp],
@@ -67,6 +70,7 @@ SIGNATURES = {
     "mixq_gather_weight_columns": [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
     "mixq_compact_outlier_columns": [_vp, _i, _vp, _i, _vp, _vp],
     "mixq_linear_fused": [C.POINTER(LinearArgs), _vp],
+    "mixq_rope_attention_decode": [_vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _f, _vp],
     "mixq_mul_inplace": [_vp, _vp, _ll, _vp],
     "mixq_set_tile_n": [_i],
     "mixq_version": [],

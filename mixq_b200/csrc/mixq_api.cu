@@ -140,6 +140,8 @@ int pick_tile_n(int requested, int M, int N, int sms, bool tmem_outliers) {
   return cost(256) < cost(128) ? 256 : 128;
 }
 
+int pick_row_groups(RowQuantArgs* a, int grid, int warps_per_cta);
+
 struct GemmCall {
   const void* q_x;
   const void* q_w;
@@ -149,6 +151,8 @@ struct GemmCall {
   const void* bias;
   const void* outl;
   int ld_outl;
+  const void* residual;
+  int ld_res;
   const void* act_outliers;
   int ld_ao;
   const void* weight_cache;
@@ -197,12 +201,16 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
   if (c.rq != nullptr) {
     p.rq = *c.rq;
     p.fused_prologue = 1;
+    // phase A runs on the persistent grid (one CTA per SM) with every warp of the GEMM CTA
+    if (int r = pick_row_groups(&p.rq, di.sms, w4 ? 12 : 8)) return r;
   }
   p.x_scale = static_cast<const __half*>(c.x_scale);
   p.scale_col = static_cast<const __half*>(c.scale_col);
   p.bias = static_cast<const __half*>(c.bias);
   p.outl = static_cast<const __half*>(c.outl);
   p.ld_outl = c.ld_outl;
+  p.residual = static_cast<const __half*>(c.residual);
+  p.ld_res = c.ld_res;
   p.y = static_cast<__half*>(c.y);
   p.y_i32 = c.y_i32;
   p.M = c.M;
@@ -226,6 +234,22 @@ int grid_for(long long work_items, int threads, int sms, int per_sm = 8) {
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return static_cast<int>(blocks);
+}
+
+// Work split of the activation prologue: G warps per row so that all rows of the batch are in flight at
+// once when possible (latency, not bandwidth, bounds a 4 MB pass), subject to <= 32 vectors per lane.
+int pick_row_groups(RowQuantArgs* a, int grid, int warps_per_cta) {
+  if (a->K > kRowQuantMaxK) return fail(MIXQ_EINVAL, "activation prologue supports K <= 32768");
+  const int nvec = a->K / 8;
+  int g_min = 1;
+  while (g_min < 4 && (nvec + 32 * g_min - 1) / (32 * g_min) > 32) g_min *= 2;
+  const int rows_per_cta = (a->M + grid - 1) / grid;
+  int g = 4;
+  while (g > g_min && warps_per_cta / g < rows_per_cta) g /= 2;
+  const int per_lane = (nvec + 32 * g - 1) / (32 * g);
+  a->group_warps = g;
+  a->nv = per_lane <= 8 ? 8 : (per_lane <= 16 ? 16 : 32);
+  return 0;
 }
 
 int fill_rowquant(RowQuantArgs* a, void* x, const void* norm_w, void* norm_out, float eps, const int32_t* ind,
@@ -257,11 +281,15 @@ int fill_rowquant(RowQuantArgs* a, void* x, const void* norm_w, void* norm_out, 
   return 0;
 }
 
-int launch_rowquant(const RowQuantArgs& a, cudaStream_t st) {
+int launch_rowquant(RowQuantArgs a, cudaStream_t st) {
   DeviceInfo di;
   if (int r = device_info(&di)) return r;
   const int threads = 256;
-  const int grid = grid_for(static_cast<long long>(a.M) * 32, threads, di.sms, 8);
+  // small batches: one row per CTA, 4 warps on it; large batches: up to 4 resident CTAs per SM
+  int grid = a.M < di.sms * 4 ? a.M : di.sms * 4;
+  if (int r = pick_row_groups(&a, grid, threads / 32)) return r;
+  const int groups = (threads / 32) / a.group_warps;
+  if (grid * groups > a.M) grid = (a.M + groups - 1) / groups;
   rowquant_kernel<<<grid, threads, 0, st>>>(a);
   MIXQ_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -286,6 +314,16 @@ int mixq_find_row_scale(const void* x, void* x_scale, void* q_x, int M, int K, i
   RowQuantArgs a{};
   if (int r = fill_rowquant(&a, const_cast<void*>(x), nullptr, nullptr, 0.f, nullptr, 0, nullptr, 0, q_x, x_scale,
                             M, K, bit, 0.f, nullptr, nullptr))
+    return r;
+  return launch_rowquant(a, static_cast<cudaStream_t>(stream));
+}
+
+int mixq_find_row_scale_scan(const void* x, void* x_scale, void* q_x, int M, int K, int bit, float sigma,
+                             uint8_t* col_over, uint32_t* over_flag, void* stream) {
+  if (x == nullptr || x_scale == nullptr || q_x == nullptr) return fail(MIXQ_EINVAL, "null pointer");
+  RowQuantArgs a{};
+  if (int r = fill_rowquant(&a, const_cast<void*>(x), nullptr, nullptr, 0.f, nullptr, 0, nullptr, 0, q_x, x_scale,
+                            M, K, bit, sigma, col_over, over_flag))
     return r;
   return launch_rowquant(a, static_cast<cudaStream_t>(stream));
 }
@@ -415,7 +453,6 @@ int mixq_linear_fused(const mixq_linear_args* a, void* stream) {
   RowQuantArgs rq{};
   if (!a->skip_prologue) {
     if (!a->x || !a->grid_sync) return fail(MIXQ_EINVAL, "prologue needs x and grid_sync");
-    if (a->norm_weight && !a->norm_out) return fail(MIXQ_EINVAL, "norm_weight needs norm_out");
     if (int r = fill_rowquant(&rq, a->x, a->norm_weight, a->norm_out, a->eps, a->ind, a->n_ind, a->act_outliers,
                               a->ld_ao, a->q_x, a->x_scale, a->M, a->K, a->bit, a->sigma, a->col_over,
                               a->over_flag))
@@ -426,9 +463,34 @@ int mixq_linear_fused(const mixq_linear_args* a, void* stream) {
   c.bias = a->bias; c.act_outliers = a->act_outliers; c.ld_ao = a->ld_ao; c.weight_cache = a->weight_cache;
   c.ld_wc = a->ld_wc; c.n_out = a->n_ind; c.y = a->y; c.M = a->M; c.N = a->N; c.K = a->K; c.act = a->act;
   c.epilogue = EPI_DEQUANT_F16; c.tile_n = a->tile_n;
+  c.residual = a->residual; c.ld_res = a->ld_res;
+  if (a->residual && a->ld_res < a->N) return fail(MIXQ_EINVAL, "ld_res < N");
   c.rq = a->skip_prologue ? nullptr : &rq;
   c.grid_sync = a->grid_sync;
   return run_gemm(c, static_cast<cudaStream_t>(stream));
+}
+
+int mixq_rope_attention_decode(const void* qkv, void* k_cache, void* v_cache, int cache_cap, int past_len, void* out,
+                               int M, int H, int Hkv, int D, float theta, void* stream) {
+  if (!qkv || !out || M < 1 || H < 1 || Hkv < 1 || H % Hkv != 0 || (D != 64 && D != 128) || past_len < 0)
+    return fail(MIXQ_EINVAL, "bad attention arguments (head_dim must be 64 or 128)");
+  if (past_len > 0 && (!k_cache || !v_cache || cache_cap <= past_len))
+    return fail(MIXQ_EINVAL, "past_len > 0 needs k/v caches with capacity > past_len");
+  const long long warps = static_cast<long long>(M) * H;
+  const int grid = static_cast<int>((warps + 3) / 4);
+  const float scale = 1.0f / sqrtf(static_cast<float>(D));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (D == 128)
+    rope_attn_decode_kernel<128><<<grid, 128, 0, st>>>(static_cast<const __half*>(qkv), static_cast<__half*>(k_cache),
+                                                       static_cast<__half*>(v_cache), cache_cap, past_len,
+                                                       static_cast<__half*>(out), M, H, Hkv, theta, scale);
+  else
+    rope_attn_decode_kernel<64><<<grid, 128, 0, st>>>(static_cast<const __half*>(qkv), static_cast<__half*>(k_cache),
+                                                      static_cast<__half*>(v_cache), cache_cap, past_len,
+                                                      static_cast<__half*>(out), M, H, Hkv, theta, scale);
+  MIXQ_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
 }
 
 int mixq_mul_inplace(void* a, const void* b, long long n, void* stream) {

@@ -18,6 +18,8 @@ struct LinearParams {
   const __half* bias;
   const __half* outl;  // optional precomputed fp16 [M,N] addend (mixlib.int8FusedDequantize's 5th argument)
   int ld_outl;
+  const __half* residual;  // optional fp16 [M, ld_res]: y = fp16(y + residual) (decoder residual stream)
+  int ld_res;
   __half* y;
   int32_t* y_i32;
   int M, N, K;
@@ -38,7 +40,7 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES + BP_BYTES;
   static constexpr int STAGES = W4 ? (BN == 128 ? 5 : 3) : (BN == 128 ? 6 : 4);
   static constexpr int NUM_THREADS = W4 ? 384 : 256;         // W4 adds 4 unpack warps
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + kRowQuantSmemBytes;
 };
 
 template <int BN, bool W4>

@@ -5,12 +5,10 @@
 
 namespace mixq {
 
-// One warp per row, rows strided over the whole grid.
+// Standalone activation prologue: groups of warps own rows (rowquant.cuh).
 __global__ void __launch_bounds__(256) rowquant_kernel(const RowQuantArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nw = (gridDim.x * blockDim.x) >> 5;
-  for (int m = gw; m < a.M; m += nw) quantize_row_warp(a, m, lane);
+  __shared__ __align__(16) uint8_t smem[kRowQuantSmemBytes];
+  rowquant_cta(a, smem);
 }
 
 __global__ void extract_outliers_kernel(const int32_t* __restrict__ ind, int n_ind, __half* x, __half* out,
@@ -118,6 +116,95 @@ __global__ void __launch_bounds__(1024) compact_cols_kernel(uint8_t* col_over, i
   }
   if (threadIdx.x == 0) *n_new = base;
 }
+
+// RoPE + single-query attention for the decode harness (fused/attn.py:219-263): one warp per (token, head).
+// qkv row = [H*D | Hkv*D | Hkv*D]; the new key/value are appended at position past_len of the optional cache
+// [M, Hkv, cap, D]; out[M, H*D] = softmax(q.K^T * scale) . V.  HF rotate_half convention (pairs i, i + D/2).
+// Outside the quantised hot path (the reference calls flash-attn here); kept simple.
+template <int D>
+__global__ void __launch_bounds__(128) rope_attn_decode_kernel(const __half* __restrict__ qkv, __half* k_cache,
+                                                               __half* v_cache, int cache_cap, int past_len,
+                                                               __half* __restrict__ out, int M, int H, int Hkv,
+                                                               float theta, float scale) {
+  constexpr int E = D / 32;   // elements per lane: lane owns dims lane + 32*e
+  const int lane = threadIdx.x & 31;
+  const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (w >= static_cast<long long>(M) * H) return;
+  const int m = static_cast<int>(w / H), h = static_cast<int>(w % H);
+  const int hk = h / (H / Hkv);
+  const int ld = (H + 2 * Hkv) * D;
+  const __half* qp = qkv + static_cast<size_t>(m) * ld + h * D;
+  const __half* kp = qkv + static_cast<size_t>(m) * ld + (H + hk) * D;
+  const __half* vp = qkv + static_cast<size_t>(m) * ld + (H + Hkv + hk) * D;
+  float q[E], k[E], v[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    q[e] = __half2float(qp[lane + 32 * e]);
+    k[e] = __half2float(kp[lane + 32 * e]);
+    v[e] = __half2float(vp[lane + 32 * e]);
+  }
+  // rotate: dim d pairs with d +- D/2; with 32 lanes x E, the partner of (lane, e) is (lane, e +- E/2)
+  float qr[E], kr[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int d = lane + 32 * e;
+    const int i = d % (D / 2);
+    const float inv_freq = __powf(theta, -2.0f * static_cast<float>(i) / static_cast<float>(D));
+    float sn, cs;
+    sincosf(static_cast<float>(past_len) * inv_freq, &sn, &cs);
+    const int pe = (e + E / 2) % E;
+    const float sgn = (d < D / 2) ? -1.f : 1.f;
+    qr[e] = q[e] * cs + sgn * q[pe] * sn;
+    kr[e] = k[e] * cs + sgn * k[pe] * sn;
+  }
+  // round to fp16 like the reference's fp16 tensors do
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    qr[e] = __half2float(__float2half_rn(qr[e]));
+    kr[e] = __half2float(__float2half_rn(kr[e]));
+  }
+  if (k_cache != nullptr && h % (H / Hkv) == 0) {
+    __half* kc = k_cache + ((static_cast<size_t>(m) * Hkv + hk) * cache_cap + past_len) * D;
+    __half* vc = v_cache + ((static_cast<size_t>(m) * Hkv + hk) * cache_cap + past_len) * D;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      kc[lane + 32 * e] = __float2half_rn(kr[e]);
+      vc[lane + 32 * e] = __float2half_rn(v[e]);
+    }
+  }
+  float mx = -INFINITY, den = 0.f, acc[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) acc[e] = 0.f;
+  for (int t = 0; t <= past_len; ++t) {
+    float kt[E], vt[E];
+    if (t == past_len) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) { kt[e] = kr[e]; vt[e] = v[e]; }
+    } else {
+      const __half* kc = k_cache + ((static_cast<size_t>(m) * Hkv + hk) * cache_cap + t) * D;
+      const __half* vc = v_cache + ((static_cast<size_t>(m) * Hkv + hk) * cache_cap + t) * D;
+#pragma unroll
+      for (int e = 0; e < E; ++e) { kt[e] = __half2float(kc[lane + 32 * e]); vt[e] = __half2float(vc[lane + 32 * e]); }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) s = fmaf(qr[e], kt[e], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    s *= scale;
+    const float mn = fmaxf(mx, s);
+    const float corr = __expf(mx - mn), pw = __expf(s - mn);
+    den = den * corr + pw;
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] = acc[e] * corr + pw * vt[e];
+    mx = mn;
+  }
+  __half* op = out + (static_cast<size_t>(m) * H + h) * D;
+#pragma unroll
+  for (int e = 0; e < E; ++e) op[lane + 32 * e] = __float2half_rn(acc[e] / den);
+}
+template __global__ void rope_attn_decode_kernel<64>(const __half*, __half*, __half*, int, int, __half*, int, int, int, float, float);
+template __global__ void rope_attn_decode_kernel<128>(const __half*, __half*, __half*, int, int, __half*, int, int, int, float, float);
 
 __global__ void mul_inplace_kernel(__half2* a, const __half2* __restrict__ b, long long n2) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n2;

@@ -1,0 +1,267 @@
+"""Llama decode-step harness around MixLinear — the measurement definition of the headline metric.
+
+What it reproduces: one timed iteration of /root/reference/benchflops.py:112-128, i.e. `model(inputs[B,1],
+use_cache=True)` on a `from_quantized(..., fuse_layers=True)` Llama (call sequence: fused/attn.py:206-278,
+fused/mlp.py:57-70, fused/norm.py:14-39, models/llama.py:9-22), with random-init weights of the named
+architecture and synthetic tokens (no checkpoint / dataset is reachable).  benchflops never carries
+past_key_values between iterations (benchflops.py:124), so every step is an independent [B,1] forward with
+an empty KV cache; `past_len > 0` with a real cache is supported for completeness.
+
+Per decoder layer, steady state (after the two outlier-discovery calls), 6 launches:
+    W_pack    = RMSNorm + extract + quantise + int8 GEMM + fp16 outlier GEMM + dequant     (1 launch)
+    attention = RoPE + single-query attention                                              (1 launch)
+    o_proj    = extract + quantise + GEMMs + dequant + residual add                        (1 launch)
+    up_proj   = RMSNorm + ... (1), gate_proj = GEMMs on the shared q_x + SiLU (1), gate *= up (1)
+    down_proj = extract + quantise + GEMMs + dequant + residual add                        (1 launch)
+The whole step is captured into one CUDA graph.
+
+Column-/row-parallel sharding over `world_size` ranks: W_pack / gate / up shard N (by
+heads / intermediate channels), o_proj / down_proj shard K and all-reduce their fp16 output once.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from .cache import MixLibCache
+from .linear import MixLinear_GEMM
+from .tp import all_reduce_sum, pack_qkv_shard, shard_cols, shard_rows
+
+
+@dataclass
+class LlamaConfig:
+    name: str
+    hidden: int
+    intermediate: int
+    layers: int
+    heads: int
+    kv_heads: int
+    vocab: int
+    rope_theta: float = 10000.0
+    eps: float = 1e-5
+
+    @property
+    def head_dim(self):
+        return self.hidden // self.heads
+
+
+CONFIGS = {
+    "llama-2-7b": LlamaConfig("llama-2-7b", 4096, 11008, 32, 32, 32, 32000),
+    "llama-3-8b": LlamaConfig("llama-3-8b", 4096, 14336, 32, 32, 8, 128256, rope_theta=500000.0),
+    "llama-2-70b": LlamaConfig("llama-2-70b", 8192, 28672, 80, 64, 8, 32000),
+    # CPU-oracle-sized configuration for tests / smoke
+    "tiny": LlamaConfig("tiny", 256, 512, 2, 4, 4, 512),
+}
+
+
+class _W:
+    """Minimal stand-in for nn.Linear handed to MixLinear_GEMM.from_linear."""
+
+    def __init__(self, weight):
+        self.weight = weight
+        self.bias = None
+        self.out_features, self.in_features = weight.shape
+
+
+def _forced(n: int, frac: float, gen: torch.Generator) -> torch.Tensor:
+    k = max(1, int(round(frac * n))) if frac > 0 else 0
+    return torch.randperm(n, generator=gen)[:k].sort().values
+
+
+class LlamaDecoder:
+    """Random-init Llama with every decoder-layer Linear replaced by MixLinear_GEMM (base.py:273-347)."""
+
+    def __init__(self, cfg: LlamaConfig, batch: int, bit: int = 8, device="cuda", seed: int = 0,
+                 outlier_frac: float = 0.01, rank: int = 0, world_size: int = 1, group=None, layers: int | None = None):
+        self.cfg, self.batch, self.bit, self.device = cfg, batch, bit, device
+        self.rank, self.world, self.group = rank, world_size, group
+        self.n_layers = cfg.layers if layers is None else layers
+        H, I, D = cfg.hidden, cfg.intermediate, cfg.head_dim
+        if cfg.heads % world_size or cfg.kv_heads % world_size or I % world_size:
+            raise ValueError("heads, kv_heads and intermediate must divide by world_size")
+        self.h_loc, self.kv_loc, self.i_loc = cfg.heads // world_size, cfg.kv_heads // world_size, I // world_size
+        self.cache = MixLibCache(inputdim=batch, sigma=6, bit=bit, device=device)
+        gen = torch.Generator(device="cpu").manual_seed(seed)          # same on every rank
+        dgen = torch.Generator(device=device).manual_seed(seed)        # same on every rank: full weights, then shard
+        f16 = torch.float16
+
+        def rand_w(n, k, row_boost=None):
+            # activations stay O(1): std 0.5/sqrt(k); boosted rows create ~1 % outlier channels downstream
+            w = torch.randn((n, k), generator=dgen, device=device, dtype=torch.float32) * (0.5 / k ** 0.5)
+            if row_boost is not None and row_boost.numel():
+                w[row_boost.to(device)] *= 40.0
+            return w.to(f16)
+
+        self.embed = torch.randn((cfg.vocab, H), generator=dgen, device=device, dtype=torch.float32).to(f16)
+        self.layers = []
+        eight_only = ("o_proj", "down_proj")  # utils/module.py:2: these stay 8-bit in 4-bit models (base.py:308-312)
+        for li in range(self.n_layers):
+            ln1 = torch.ones(H, dtype=f16)
+            ln1[_forced(H, outlier_frac, gen)] = 20.0
+            ln2 = torch.ones(H, dtype=f16)
+            ln2[_forced(H, outlier_frac, gen)] = 20.0
+            v_boost = _forced(cfg.kv_heads * D, outlier_frac, gen)
+            up_boost = _forced(I, outlier_frac, gen)
+            wq = rand_w(cfg.heads * D, H)
+            wk = rand_w(cfg.kv_heads * D, H)
+            wv = rand_w(cfg.kv_heads * D, H, v_boost)
+            wo = rand_w(H, cfg.heads * D)
+            wg = rand_w(I, H)
+            wu = rand_w(I, H, up_boost)
+            wd = rand_w(H, I)
+            r, w_ = rank, world_size
+            w_pack = pack_qkv_shard(wq, wk, wv, r, w_)
+            wo_s = shard_cols(wo, r, w_).contiguous()
+            wd_s = shard_cols(wd, r, w_).contiguous()
+            sl = lambda t, n: shard_rows(t, r, w_)
+            mk = lambda w, nm, b, scales=None: MixLinear_GEMM.from_linear(
+                _W(w), b, cache=self.cache, dev=device, name=f"L{li}.{nm}", layer_scales=scales)
+            if bit == 4:
+                # static outliers need per-input-channel activation scales (mixquant.py:201-208): synthetic ones that
+                # single out the forced channels, padded by the largest-index channels
+                s_h1 = torch.arange(H, dtype=torch.float32) * 1e-6 + (ln1.float() > 1) * 10
+                s_h2 = torch.arange(H, dtype=torch.float32) * 1e-6 + (ln2.float() > 1) * 10
+            layer = {
+                "ln1": ln1.to(device), "ln2": ln2.to(device),
+                "W_pack": mk(w_pack, "W_pack", bit, s_h1 if bit == 4 else None),
+                "o_proj": mk(wo_s, "o_proj", 8),
+                "gate_proj": mk(sl(wg, I).contiguous(), "gate_proj", bit, s_h2 if bit == 4 else None),
+                "up_proj": mk(sl(wu, I).contiguous(), "up_proj", bit, s_h2 if bit == 4 else None),
+                "down_proj": mk(wd_s, "down_proj", 8),
+            }
+            del wq, wk, wv, wo, wg, wu, wd, w_pack, wo_s, wd_s
+            self.layers.append(layer)
+        _ = eight_only
+        self.norm_f = torch.ones(H, dtype=f16, device=device)
+        self.lm_head = rand_w(cfg.vocab, H)   # fp16, never quantised (base.py:285-288 only walks decoder layers)
+        self.discovered = False
+        self.graph = None
+        self._static_tokens = None
+        self._static_logits = None
+        self.kv = None
+        self.lib = _lib.load()
+
+    # ------------------------------------------------------------------ pieces
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _attention(self, qkv, past_len=0, layer_idx=0):
+        cfg = self.cfg
+        M = qkv.shape[0]
+        out = torch.empty((M, self.h_loc * cfg.head_dim), dtype=torch.float16, device=qkv.device)
+        kc = vc = None
+        cap = 0
+        if self.kv is not None:
+            kc, vc = self.kv[layer_idx]
+            cap = kc.shape[2]
+        _lib.check(self.lib.mixq_rope_attention_decode(qkv.data_ptr(), 0 if kc is None else kc.data_ptr(),
+                                                       0 if vc is None else vc.data_ptr(), cap, past_len, out.data_ptr(),
+                                                       M, self.h_loc, self.kv_loc, cfg.head_dim, cfg.rope_theta,
+                                                       self._stream()), "rope_attention_decode")
+        return out
+
+    def _allreduce(self, t):
+        return all_reduce_sum(t, self.group) if self.world > 1 else t
+
+    def alloc_kv(self, capacity: int):
+        cfg = self.cfg
+        self.kv = [(torch.zeros((self.batch, self.kv_loc, capacity, cfg.head_dim), dtype=torch.float16, device=self.device),
+                    torch.zeros((self.batch, self.kv_loc, capacity, cfg.head_dim), dtype=torch.float16, device=self.device))
+                   for _ in range(self.n_layers)]
+
+    # ------------------------------------------------------------------ one decode step
+    @torch.no_grad()
+    def step(self, tokens: torch.Tensor, past_len: int = 0) -> torch.Tensor:
+        """tokens int64 [B,1] (or [B]) on the device -> logits fp16 [B, vocab]."""
+        cfg = self.cfg
+        h = torch.nn.functional.embedding(tokens.reshape(-1), self.embed)   # [B, H] fp16
+        steady = self.discovered
+        tp = self.world > 1
+        for li, L in enumerate(self.layers):
+            if steady:
+                qkv = L["W_pack"].forward_norm_fused(h, L["ln1"], cfg.eps)
+            else:
+                qkv = self._norm_then_linear(h, L["ln1"], L["W_pack"])
+            attn = self._attention(qkv, past_len, li)
+            if tp:
+                h = h + self._allreduce(L["o_proj"](attn, None, True))
+            else:
+                h = L["o_proj"](attn, None, True, residual=h)
+            if steady:
+                up = L["up_proj"].forward_norm_fused(h, L["ln2"], cfg.eps)
+            else:
+                up = self._norm_then_linear(h, L["ln2"], L["up_proj"])
+            gate = L["gate_proj"].forward_without_preconditionFusedSilu(h, self.cache)
+            _lib.check(self.lib.mixq_mul_inplace(gate.data_ptr(), up.data_ptr(), gate.numel(), self._stream()), "mul")
+            if tp:
+                h = h + self._allreduce(L["down_proj"](gate, None, True))
+            else:
+                h = L["down_proj"](gate, None, True, residual=h)
+        hn = torch.empty_like(h)
+        _lib.check(self.lib.mixq_rmsnorm(h.data_ptr(), self.norm_f.data_ptr(), hn.data_ptr(), cfg.eps, h.shape[0],
+                                         cfg.hidden, self._stream()), "final norm")
+        return torch.matmul(hn, self.lm_head.t())
+
+    def _norm_then_linear(self, h, ln_w, lin):
+        """Discovery-phase path: the reference's two-step sequence (norm.py:24-28 then linear.py:165, fused mode)."""
+        from .norm import FasterTransformerRMSNorm
+        norm = FasterTransformerRMSNorm(ln_w, self.cfg.eps, self.cache)
+        norm.next_layer = lin
+        out = norm(h)
+        return lin(out, self.cache)
+
+    @torch.no_grad()
+    def discover(self, tokens: torch.Tensor, calls: int | None = None):
+        """The reference's first `cache.stop` forwards: online outlier discovery with host syncs."""
+        for _ in range(self.cache.stop if calls is None else calls):
+            self.step(tokens)
+        # gate_proj never runs discovery itself: it follows up_proj's outlier set (linear.py:299-315)
+        self.discovered = all(not L[k].add_outliers for L in self.layers for k in ("W_pack", "o_proj", "up_proj", "down_proj"))
+        return self.discovered
+
+    def capture(self, tokens: torch.Tensor):
+        """Capture the steady-state step into a CUDA graph (tokens are copied into a static buffer per replay)."""
+        assert self.discovered, "run discover() first"
+        self._static_tokens = tokens.clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self.step(self._static_tokens)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._static_logits = self.step(self._static_tokens)
+        return self.graph
+
+    def replay(self, tokens: torch.Tensor | None = None) -> torch.Tensor:
+        if tokens is not None:
+            self._static_tokens.copy_(tokens, non_blocking=True)
+        self.graph.replay()
+        return self._static_logits
+
+    # ------------------------------------------------------------------ accounting
+    def linear_shapes(self):
+        """(name, N, K, bit, n_outliers) of the five MixLinears of layer 0 as sharded on this rank."""
+        return [(k, m.out_features, m.in_features, m.bit, m._n_ind) for k, m in self.layers[0].items()
+                if isinstance(m, MixLinear_GEMM)]
+
+    def algorithmic_work(self):
+        """(flops, bytes) of the quantised Linears of one decode step on this rank."""
+        M = self.batch
+        fl = by = 0
+        for L in self.layers:
+            for m in L.values():
+                if not isinstance(m, MixLinear_GEMM):
+                    continue
+                N, K, n = m.out_features, m.in_features, m._n_ind
+                fl += 2 * M * N * K
+                by += N * K * m.bit // 8 + 2 * M * K + 2 * M * N + 2 * N + 2 * n * N
+        return fl, by
+
+    def launches_per_step(self):
+        return 6 * self.n_layers + 1   # + final RMSNorm; embedding / lm_head are library calls

@@ -1,0 +1,446 @@
+"""GPU parity tests: every entry point of the C ABI (called through ctypes, exactly as the reference-side binding
+would) against the CPU oracle on the same seeded inputs, the golden fixtures recorded from the reference's own
+Python, and size-independent properties at the BASELINE.json sizes.
+
+Bars: bit-exact for integer / index / byte outputs (q_x, x_scale bits, outlier index sets, int32 accumulators,
+packed nibbles, gathered columns) and for the fp16 dequant epilogue without SiLU; <= 1e-2 relative (the
+north-star tolerance; observed ~2e-4) wherever the fp16 outlier GEMM's accumulation order or a fast-math
+exp enters.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mixq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-2   # north star: <= 1e-2 relative on the fp16 result
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from mixq_b200 import _lib
+    assert torch.cuda.is_available(), "the gpu-marked tests need a CUDA device"
+    return _lib.load()
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+_KEEP = []
+
+
+def dp(a):
+    """Device copy of a numpy array, kept alive until the end of the test (its pointer goes through ctypes)."""
+    t = dev(a)
+    _KEEP.append(t)
+    return t.data_ptr()
+
+
+@pytest.fixture(autouse=True)
+def _release_kept():
+    yield
+    torch.cuda.synchronize()
+    _KEEP.clear()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def st():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def check(rc, what="call"):
+    from mixq_b200 import _lib
+    _lib.check(rc, what)
+
+
+def bits_equal(a, b, what):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, f"{what}: {a.shape} vs {b.shape}"
+    if a.dtype == np.float16:
+        ua, ub = a.view(np.uint16), np.asarray(b, np.float16).view(np.uint16)
+        bad = (ua != ub) & ~(((ua | ub) & 0x7FFF) == 0)
+    else:
+        bad = a != b
+    assert not bad.any(), f"{what}: {int(bad.sum())} of {a.size} differ; first at {np.argwhere(bad)[:4].tolist()}"
+
+
+def rel_close(a, b, what, tol=REL_TOL):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert a.shape == b.shape, f"{what}: {a.shape} vs {b.shape}"
+    rel = np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+    assert rel <= tol, f"{what}: rel Frobenius error {rel:.3e} > {tol}"
+    assert np.abs(a - b).max() <= tol * max(1.0, np.abs(b).max()), f"{what}: max abs diff {np.abs(a - b).max()}"
+
+
+def make_x(rng, M, K, n_out, scale=20.0):
+    x = rng.standard_normal((M, K)).astype(np.float16)
+    cols = np.sort(rng.permutation(K)[:n_out]).astype(np.int32)
+    if n_out:
+        x[:, cols] = (x[:, cols].astype(np.float32) * scale).astype(np.float16)
+    return x, cols
+
+
+# ----------------------------------------------------------------------------- activation prologue
+@pytest.mark.parametrize("M,K", [(1, 16), (7, 264), (200, 1000), (512, 4096), (33, 11008), (3, 28672)])
+@pytest.mark.parametrize("bit", [8, 4])
+def test_find_row_scale(lib, M, K, bit):
+    rng = np.random.default_rng(M * 131 + K + bit)
+    x, _ = make_x(rng, M, K, 0)
+    if M > 2:
+        x[1] = 0                      # all-zero row: scale 0, q 0 (guarded 0/0)
+        x[2, 0] = np.float16(60000)   # near fp16 max
+    q_ref, xs_ref = O.find_row_scale(x, bit)
+    xd, xs, q = dev(x), torch.zeros(M, 1, dtype=torch.float16, device="cuda"), torch.empty(M, K, dtype=torch.int8, device="cuda")
+    check(lib.mixq_find_row_scale(xd.data_ptr(), xs.data_ptr(), q.data_ptr(), M, K, bit, st()))
+    bits_equal(host(xs), xs_ref, "x_scale")
+    bits_equal(host(q), q_ref, "q_x")
+    bits_equal(host(xd), x, "x must not be modified")
+
+
+@pytest.mark.parametrize("M,K,n", [(5, 64, 3), (128, 4096, 41), (17, 1024, 200)])
+def test_extract_outliers_and_scan(lib, M, K, n):
+    rng = np.random.default_rng(n)
+    x, cols = make_x(rng, M, K, n)
+    xr = x.copy()
+    ao_ref = O.extract_outliers_and_set_to_zeros(cols, xr)
+    xd, ind = dev(x), dev(cols)
+    ao = torch.zeros(M, n + 5, dtype=torch.float16, device="cuda")
+    check(lib.mixq_extract_outliers_and_set_to_zeros(ind.data_ptr(), n, xd.data_ptr(), ao.data_ptr(), n + 5, M, K, st()))
+    bits_equal(host(ao)[:, :n], ao_ref, "activation_outliers")
+    bits_equal(host(xd), xr, "x zeroed in place")
+    # scan on the ORIGINAL x: threshold flag + column flags -> ordered compaction == FindOutliers (linear.py:157-161)
+    xd = dev(x)
+    xs = torch.zeros(M, 1, dtype=torch.float16, device="cuda")
+    q = torch.empty(M, K, dtype=torch.int8, device="cuda")
+    col_over = torch.zeros(K, dtype=torch.uint8, device="cuda")
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    check(lib.mixq_find_row_scale_scan(xd.data_ptr(), xs.data_ptr(), q.data_ptr(), M, K, 8, 6.0, col_over.data_ptr(),
+                                       flag.data_ptr(), st()))
+    out = torch.full((K,), -1, dtype=torch.int32, device="cuda")
+    n_new = torch.zeros(1, dtype=torch.int32, device="cuda")
+    check(lib.mixq_compact_outlier_columns(col_over.data_ptr(), K, out.data_ptr(), K, n_new.data_ptr(), st()))
+    want = O.find_outliers(x, 6)
+    assert int(flag.item()) == int(O.find_row_scale(x, 8)[1].max() > np.float16(np.float32(6) / np.float32(127)))
+    assert int(n_new.item()) == len(want)
+    bits_equal(host(out)[: len(want)], want, "outlier index set")
+    assert int(col_over.sum().item()) == 0, "col_over must be cleared by the compaction"
+
+
+def test_scan_no_outliers_and_threshold_edge(lib):
+    """|x| == sigma exactly is NOT an outlier (strict >, linear.py:159, :201)."""
+    M, K = 4, 64
+    x = np.zeros((M, K), np.float16)
+    x[0, 3] = 6.0
+    x[1, 5] = -6.0
+    xd = dev(x)
+    xs = torch.zeros(M, 1, dtype=torch.float16, device="cuda")
+    q = torch.empty(M, K, dtype=torch.int8, device="cuda")
+    col_over = torch.zeros(K, dtype=torch.uint8, device="cuda")
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    check(lib.mixq_find_row_scale_scan(xd.data_ptr(), xs.data_ptr(), q.data_ptr(), M, K, 8, 6.0, col_over.data_ptr(), flag.data_ptr(), st()))
+    assert int(flag.item()) == 0 and int(col_over.sum().item()) == 0
+    x[2, 7] = np.nextafter(np.float16(6.0), np.float16(7.0))
+    xd = dev(x)
+    check(lib.mixq_find_row_scale_scan(xd.data_ptr(), xs.data_ptr(), q.data_ptr(), M, K, 8, 6.0, col_over.data_ptr(), flag.data_ptr(), st()))
+    assert host(col_over).nonzero()[0].tolist() == [7]
+
+
+# ----------------------------------------------------------------------------- GEMMs
+@pytest.mark.parametrize("M,N,K", [(1, 8, 16), (32, 4096, 4096), (200, 1000, 1008), (130, 264, 144), (512, 512, 4096)])
+def test_gemm_i8_exact(lib, M, N, K):
+    rng = np.random.default_rng(M + N + K)
+    qx = rng.integers(-127, 128, (M, K), dtype=np.int8)
+    qw = rng.integers(-128, 128, (N, K), dtype=np.int8)
+    y = torch.full((M, N), -7, dtype=torch.int32, device="cuda")
+    check(lib.mixq_gemm_i8(dp(qx), dp(qw), y.data_ptr(), M, N, K, st()))
+    bits_equal(host(y), O.gemm_i8(qx, qw), "int32 accumulator")
+
+
+@pytest.mark.parametrize("tile", [128, 256])
+@pytest.mark.parametrize("act", [0, 1])
+@pytest.mark.parametrize("with_outl", [False, True])
+def test_int8_fused_dequantize(lib, tile, act, with_outl):
+    M, N, K = 96, 520, 1040
+    rng = np.random.default_rng(tile + act)
+    qx = rng.integers(-127, 128, (M, K), dtype=np.int8)
+    qw = rng.integers(-127, 128, (N, K), dtype=np.int8)
+    xs = (rng.random((M, 1)) * 0.05 + 0.01).astype(np.float16)
+    ws = (rng.random((1, N)) * 0.01 + 0.001).astype(np.float16)
+    outl = rng.standard_normal((M, N)).astype(np.float16) if with_outl else None
+    y = torch.zeros(M, N, dtype=torch.float16, device="cuda")
+    check(lib.mixq_set_tile_n(tile))
+    try:
+        check(lib.mixq_int8_fused_dequantize(dp(qx), dp(qw), dp(xs), dp(ws),
+                                             dp(outl) if with_outl else 0, N, y.data_ptr(), M, N, K, act, st()))
+    finally:
+        check(lib.mixq_set_tile_n(0))
+    ref = O.int8_fused_dequantize(qx, qw, xs, ws, outl, act)
+    if act == 0:
+        bits_equal(host(y), ref, "y")          # IEEE fp32 epilogue, one rounding
+    else:
+        rel_close(host(y), ref, "y (SiLU, fast exp)", 2e-3)
+
+
+@pytest.mark.parametrize("tile", [128, 256])
+def test_int4_fused_dequantize_and_unpack(lib, tile):
+    M, N, K = 70, 264, 1056
+    rng = np.random.default_rng(tile)
+    q4 = rng.integers(-8, 8, (N, K), dtype=np.int8)
+    qwp = O.pack_to_i4(q4)
+    qx = rng.integers(-7, 8, (M, K), dtype=np.int8)
+    xs = (rng.random((M, 1)) * 0.5 + 0.1).astype(np.float16)
+    ws = (rng.random((1, N)) * 0.01 + 0.001).astype(np.float16)
+    y = torch.zeros(M, N, dtype=torch.float16, device="cuda")
+    check(lib.mixq_set_tile_n(tile))
+    try:
+        check(lib.mixq_int4_fused_dequantize(dp(qx), dp(qwp), dp(xs), dp(ws),
+                                             0, 0, y.data_ptr(), M, N, K, 0, st()))
+    finally:
+        check(lib.mixq_set_tile_n(0))
+    bits_equal(host(y), O.int4_fused_dequantize(qx, qwp, xs, ws), "y (packed-nibble weights)")
+    ind = np.array([0, 1, 5, K - 1, K - 2, 77], np.int32)
+    out = torch.zeros(N, len(ind), dtype=torch.float16, device="cuda")
+    check(lib.mixq_unpack_int4_to_fp16(dp(qwp), dp(ind), len(ind), out.data_ptr(), len(ind), N, K, st()))
+    bits_equal(host(out), O.unpack_int4_to_fp16(qwp, ind), "unpack_int4_to_fp16")
+
+
+def test_dequantize_int8_split_path(lib):
+    M, N = 37, 264
+    rng = np.random.default_rng(5)
+    acc = rng.integers(-2_000_000, 2_000_000, (M, N), dtype=np.int32)
+    xs = (rng.random((M, 1)) * 0.05).astype(np.float16)
+    ws = (rng.random((1, N)) * 0.01).astype(np.float16)
+    outl = rng.standard_normal((M, N)).astype(np.float16)
+    y = torch.zeros(M, N, dtype=torch.float16, device="cuda")
+    check(lib.mixq_dequantize_int8(dp(acc), dp(xs), dp(ws), dp(outl), N,
+                                   y.data_ptr(), M, N, 0, st()))
+    bits_equal(host(y), O.dequantize(acc, xs, ws, outl=outl), "dequantizeInt8")
+
+
+@pytest.mark.parametrize("bit", [8, 4])
+def test_gather_weight_columns(lib, bit):
+    N, K = 200, 512
+    rng = np.random.default_rng(bit)
+    ws = (rng.random((1, N)) * 0.01 + 0.001).astype(np.float16)
+    ind = np.array([3, 500, 17, 18], np.int32)
+    if bit == 8:
+        qw = rng.integers(-127, 128, (N, K), dtype=np.int8)
+    else:
+        qw = O.pack_to_i4(rng.integers(-8, 8, (N, K), dtype=np.int8))
+    wc = torch.zeros(N, 64, dtype=torch.float16, device="cuda")
+    check(lib.mixq_gather_weight_columns(dp(qw), dp(ws), dp(ind), 4, wc.data_ptr(), 64, 2, N,
+                                         K, bit, st()))
+    bits_equal(host(wc)[:, 2:6], O.weight_cache_columns(qw, ws, ind, bit), "weight_cache columns")
+    assert not host(wc)[:, :2].any() and not host(wc)[:, 6:].any()
+
+
+# ----------------------------------------------------------------------------- RMSNorm
+@pytest.mark.parametrize("M,K,n", [(9, 256, 0), (64, 4096, 41), (130, 11008, 7)])
+def test_rmsnorm_and_fused_extract(lib, M, K, n):
+    rng = np.random.default_rng(K + n)
+    x, cols = make_x(rng, M, K, n)
+    w = (1 + 0.1 * rng.standard_normal(K)).astype(np.float16)
+    out = torch.zeros(M, K, dtype=torch.float16, device="cuda")
+    check(lib.mixq_rmsnorm(dp(x), dp(w), out.data_ptr(), 1e-5, M, K, st()))
+    ref = O.rmsnorm(x, w, 1e-5)
+    diff = np.abs(host(out).astype(np.float32) - ref.astype(np.float32))
+    ulp = np.abs(np.spacing(ref)).astype(np.float32)
+    assert (diff <= ulp).all(), "RMSNorm differs by more than 1 fp16 ulp"          # reduction order only
+    assert (diff > 0).mean() < 0.02
+    # fused: norm + extract + quantise; quantisation is checked against the oracle applied to THIS kernel's normed output
+    xs = torch.zeros(M, 1, dtype=torch.float16, device="cuda")
+    ao = torch.zeros(M, max(n, 1) + 3, dtype=torch.float16, device="cuda")
+    q = torch.zeros(M, K, dtype=torch.int8, device="cuda")
+    out2 = torch.zeros(M, K, dtype=torch.float16, device="cuda")
+    xd = dev(x)
+    check(lib.mixq_rmsnorm_extract_outliers(xd.data_ptr(), dp(w), out2.data_ptr(), 1e-5, dp(cols) if n else 0,
+                                            n, xs.data_ptr(), ao.data_ptr(), ao.shape[1], q.data_ptr(), M, K, 8, st()))
+    bits_equal(host(xd), x, "x is read-only in norm mode")
+    normed = host(out).copy()
+    ao_ref = O.extract_outliers_and_set_to_zeros(cols, normed) if n else None
+    bits_equal(host(out2), normed, "normed output with outlier columns zeroed")
+    if n:
+        bits_equal(host(ao)[:, :n], ao_ref, "activation_outliers")
+    q_ref, xs_ref = O.find_row_scale(normed, 8)
+    bits_equal(host(xs), xs_ref, "x_scale")
+    bits_equal(host(q), q_ref, "q_x")
+
+
+# ----------------------------------------------------------------------------- the fused single launch
+def run_fused(lib, x, qw, ws, cols, wc, bit, *, bias=None, act=0, residual=None, norm_w=None, tile=0, skip=None):
+    from mixq_b200 import _lib
+    M, K = x.shape
+    N = qw.shape[0]
+    n = len(cols)
+    cap = max(64, (n + 63) // 64 * 64)
+    t = dict(x=dev(x), qw=dev(qw), ws=dev(ws), ind=dev(np.asarray(cols, np.int32)) if n else None,
+             wc=torch.zeros(N, cap, dtype=torch.float16, device="cuda"),
+             q_x=torch.zeros(M, K, dtype=torch.int8, device="cuda"), xs=torch.zeros(M, dtype=torch.float16, device="cuda"),
+             ao=torch.zeros(M, cap, dtype=torch.float16, device="cuda"), y=torch.zeros(M, N, dtype=torch.float16, device="cuda"),
+             sync=torch.zeros(1, dtype=torch.int32, device="cuda"),
+             bias=None if bias is None else dev(bias), res=None if residual is None else dev(residual),
+             nw=None if norm_w is None else dev(norm_w), nout=torch.zeros(M, K, dtype=torch.float16, device="cuda"))
+    if n:
+        t["wc"][:, :n] = dev(wc)
+    if skip is not None:
+        t["q_x"].copy_(dev(skip[0])); t["xs"].copy_(dev(skip[1].reshape(-1)))
+        if n:
+            t["ao"][:, :n] = dev(skip[2])
+    a = _lib.LinearArgs()
+    a.x = t["x"].data_ptr(); a.M, a.N, a.K = M, N, K
+    a.norm_weight = 0 if norm_w is None else t["nw"].data_ptr(); a.norm_out = t["nout"].data_ptr(); a.eps = 1e-5
+    a.q_weight = t["qw"].data_ptr(); a.scale_col = t["ws"].data_ptr(); a.bit = bit
+    a.bias = 0 if bias is None else t["bias"].data_ptr()
+    a.ind = t["ind"].data_ptr() if n else 0; a.n_ind = n
+    a.weight_cache = t["wc"].data_ptr(); a.ld_wc = cap
+    a.q_x = t["q_x"].data_ptr(); a.x_scale = t["xs"].data_ptr(); a.act_outliers = t["ao"].data_ptr(); a.ld_ao = cap
+    a.sigma = 6.0; a.y = t["y"].data_ptr(); a.act = act; a.grid_sync = t["sync"].data_ptr(); a.tile_n = tile
+    a.residual = 0 if residual is None else t["res"].data_ptr(); a.ld_res = N
+    a.skip_prologue = 0 if skip is None else 1
+    check(lib.mixq_linear_fused(C.byref(a), st()), "mixq_linear_fused")
+    torch.cuda.synchronize()
+    return t
+
+
+def oracle_fused(x, qw, ws, cols, wc, bit, bias=None, act=0, residual=None, norm_w=None):
+    x = x.copy()
+    if norm_w is not None:
+        x = O.rmsnorm(x, norm_w, 1e-5)
+    ao = O.extract_outliers_and_set_to_zeros(cols, x) if len(cols) else None
+    q_x, xs = O.find_row_scale(x, bit)
+    outl = O.outlier_gemm_f32(ao, wc).astype(np.float16) if len(cols) else None
+    qwi = qw if bit == 8 else O.unpack_i4(qw)
+    y = O.dequantize(O.gemm_i8(q_x, qwi), xs, ws, outl=outl, act=act)
+    if bias is not None:
+        y = (y.astype(np.float32) + bias.astype(np.float32)[None]).astype(np.float16)
+    if residual is not None:
+        y = (y.astype(np.float32) + residual.astype(np.float32)).astype(np.float16)
+    return dict(x=x, ao=ao, q_x=q_x, xs=xs, y=y)
+
+
+@pytest.mark.parametrize("M,N,K,n", [(32, 4096, 4096, 41), (1, 8, 16, 0), (130, 264, 1008, 3), (512, 1024, 4096, 129),
+                                     (77, 520, 11008, 64), (16, 136, 144, 144)])
+@pytest.mark.parametrize("tile", [128, 256])
+def test_linear_fused_w8(lib, M, N, K, n, tile):
+    """C1 (M=32, K=N=4096, 41 forced outlier columns) and ragged / edge shapes incl. every column an outlier."""
+    rng = np.random.default_rng(M + N + K + n)
+    x, cols = make_x(rng, M, K, n)
+    W = (rng.standard_normal((N, K)) * 0.02).astype(np.float16)
+    qw, ws = O.quant_weight_w8(W)
+    wc = O.weight_cache_columns(qw, ws, cols, 8)
+    bias = (rng.standard_normal(N) * 0.1).astype(np.float16)
+    res = rng.standard_normal((M, N)).astype(np.float16)
+    t = run_fused(lib, x, qw, ws, cols, wc, 8, bias=bias, residual=res, tile=tile)
+    r = oracle_fused(x, qw, ws, cols, wc, 8, bias=bias, residual=res)
+    bits_equal(host(t["x"]), r["x"], "x zeroed in place")
+    bits_equal(host(t["xs"]), r["xs"].reshape(-1), "x_scale")
+    bits_equal(host(t["q_x"]), r["q_x"], "q_x")
+    if n:
+        bits_equal(host(t["ao"])[:, :n], r["ao"], "activation_outliers")
+        rel_close(host(t["y"]), r["y"], "y")
+    else:
+        bits_equal(host(t["y"]), r["y"], "y (no outliers: bit-exact)")
+
+
+@pytest.mark.parametrize("M,N,K,n", [(64, 264, 1024, 128), (512, 512, 4096, 128)])
+def test_linear_fused_w4(lib, M, N, K, n):
+    rng = np.random.default_rng(N)
+    x, cols = make_x(rng, M, K, 20)
+    W = (rng.standard_normal((N, K)) * 0.02).astype(np.float16)
+    scales = rng.random(K).astype(np.float32)
+    scales[cols] += 10
+    qwp, ws, wc, ind = O.quant_weight_w4(W, scales, n)
+    t = run_fused(lib, x, qwp, ws, ind, wc, 4, act=1)
+    r = oracle_fused(x, qwp, ws, ind, wc, 4, act=1)
+    bits_equal(host(t["q_x"]), r["q_x"], "q_x (int4 range)")
+    assert np.abs(host(t["q_x"])).max() <= 7
+    bits_equal(host(t["xs"]), r["xs"].reshape(-1), "x_scale")
+    bits_equal(host(t["ao"])[:, :n], r["ao"], "activation_outliers")
+    rel_close(host(t["y"]), r["y"], "y")
+
+
+def test_linear_fused_norm_and_skip_prologue(lib):
+    """RMSNorm folded into phase A (norm.py:24-33) and the gate_proj mode that re-uses q_x (linear.py:291-376)."""
+    M, N, K, n = 100, 520, 4096, 41
+    rng = np.random.default_rng(11)
+    x, cols = make_x(rng, M, K, 0)
+    nw = np.ones(K, np.float16)
+    nw[np.sort(rng.permutation(K)[:n])] = 20
+    cols = np.nonzero(nw > 1)[0].astype(np.int32)
+    W = (rng.standard_normal((N, K)) * 0.02).astype(np.float16)
+    qw, ws = O.quant_weight_w8(W)
+    wc = O.weight_cache_columns(qw, ws, cols, 8)
+    t = run_fused(lib, x, qw, ws, cols, wc, 8, norm_w=nw)
+    bits_equal(host(t["x"]), x, "x untouched in norm mode")
+    normed = host(t["nout"])
+    # the oracle's RMSNorm may differ by 1 ulp on a few elements (reduction order): quantisation parity is
+    # asserted on the kernel's own normed output, the norm itself against the oracle within 1 ulp
+    ref_n = O.rmsnorm(x, nw, 1e-5)
+    ref_n[:, cols] = 0
+    assert (np.abs(normed.astype(np.float32) - ref_n.astype(np.float32)) <= np.abs(np.spacing(ref_n)).astype(np.float32)).all()
+    q_ref, xs_ref = O.find_row_scale(normed, 8)
+    bits_equal(host(t["q_x"]), q_ref, "q_x")
+    bits_equal(host(t["xs"]), xs_ref.reshape(-1), "x_scale")
+    ao = host(t["ao"])[:, :n]
+    outl = O.outlier_gemm_f32(ao, wc).astype(np.float16)
+    y_ref = O.dequantize(O.gemm_i8(q_ref, qw), xs_ref, ws, outl=outl)
+    rel_close(host(t["y"]), y_ref, "y")
+    # gate_proj: same q_x / x_scale / outliers, SiLU epilogue, no prologue
+    t2 = run_fused(lib, x, qw, ws, cols, wc, 8, act=1, skip=(q_ref, xs_ref, ao))
+    y2 = O.dequantize(O.gemm_i8(q_ref, qw), xs_ref, ws, outl=outl, act=1)
+    rel_close(host(t2["y"]), y2, "y (skip_prologue + SiLU)")
+
+
+# ----------------------------------------------------------------------------- properties at BASELINE.json sizes
+@pytest.mark.parametrize("N,K", [(12288, 4096), (4096, 4096), (11008, 4096), (4096, 11008)])
+def test_full_size_properties(lib, N, K):
+    """Llama-2-7B shapes at M=512 (C2): (1) q_x / x_scale / outlier gather bit-exact against the same formulas in
+    torch on the device; (2) int32 GEMM exact against a float64 product of the same integers; (3) scaling x by 2
+    scales y by exactly 2 (power-of-two scaling commutes with every rounding in the path); (4) idempotence of the
+    in-place zeroing."""
+    M, n = 512, 41
+    g = torch.Generator(device="cuda").manual_seed(N + K)
+    x = torch.randn(M, K, generator=g, device="cuda", dtype=torch.float32)
+    cols = torch.randperm(K, generator=g, device="cuda")[:n].sort().values
+    x[:, cols] *= 20
+    x = x.half()
+    W = (torch.randn(N, K, generator=g, device="cuda") * 0.02).half()
+    ws = (W.float().abs().amax(1) / 127).half()
+    qw = (W.float() / ws.float()[:, None]).half().float().round().to(torch.int8)
+    wc = (qw[:, cols].half() * ws[:, None])
+    xz = x.clone()
+    ao_ref = xz[:, cols].clone()
+    xz[:, cols] = 0
+    xs_ref = (xz.float().abs().amax(1) / 127).half()
+    q_ref = torch.where(xs_ref[:, None] > 0, (xz.float() / xs_ref.float()[:, None]).round(), torch.zeros((), device="cuda")).clamp(-127, 127).to(torch.int8)
+    acc = (q_ref.double() @ qw.double().T)
+    y_ref = ((acc.float() * xs_ref.float()[:, None]) * ws.float()[None, :] + (ao_ref.double() @ wc.double().T).float().half().float()).half()
+
+    def run(xin):
+        t = run_fused(lib, host(xin), host(qw), host(ws).reshape(1, -1), host(cols).astype(np.int32), host(wc), 8)
+        return t
+    t = run(x)
+    assert torch.equal(t["q_x"], q_ref), "q_x"
+    assert torch.equal(t["xs"].view(torch.int16), xs_ref.view(torch.int16)), "x_scale"
+    assert torch.equal(t["ao"][:, :n], ao_ref), "activation_outliers"
+    assert torch.equal(t["x"], xz), "in-place zeroing"
+    rel = float((t["y"].double() - y_ref.double()).norm() / y_ref.double().norm())
+    assert rel <= REL_TOL, rel
+    yi = torch.zeros(M, N, dtype=torch.int32, device="cuda")
+    check(lib.mixq_gemm_i8(q_ref.data_ptr(), qw.data_ptr(), yi.data_ptr(), M, N, K, st()))
+    assert torch.equal(yi.double(), acc), "int32 accumulator exact"
+    t2 = run(x * 2)
+    assert torch.equal(t2["q_x"], t["q_x"])
+    d = (t2["y"].float() - 2 * t["y"].float()).abs()
+    assert bool((d[t["y"].abs() >= 2 ** -12] == 0).all()), "y(2x) == 2 y(x) exactly (normal range)"
+    assert float(d.max()) <= 2 ** -23, "y(2x) vs 2 y(x) in the fp16 subnormal range"
+    t3 = run(xz)   # already-zeroed input: same q_x, zero outlier contribution
+    assert torch.equal(t3["q_x"], t["q_x"]) and not t3["ao"].any()

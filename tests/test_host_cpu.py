@@ -1,0 +1,153 @@
+"""CPU: host-side logic of the product (no kernels are launched) and the C-ABI surface."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from mixq_b200 import _lib
+from mixq_b200.linear import MixLinear_GEMM, pack_to_i4
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class _Lin:
+    def __init__(self, W, b=None):
+        self.weight = torch.nn.Parameter(torch.from_numpy(W.copy()), requires_grad=False)
+        self.bias = None if b is None else torch.nn.Parameter(torch.from_numpy(b.copy()), requires_grad=False)
+        self.out_features, self.in_features = W.shape
+
+
+class _Cache:
+    sigma = torch.tensor([[6.0]], dtype=torch.float16)
+    stop = 2
+
+
+@pytest.mark.parametrize("case", ["w8_unfused", "w8_unfused_bias", "w4_unfused"])
+def test_from_linear_matches_reference(golden, case):
+    """The product's from_linear (offline torch arithmetic, any device) vs the reference's, bit for bit."""
+    d = golden(case)
+    bit = int(d["bit"])
+    ls = torch.from_numpy(d["layer_scales"]) if bit == 4 else None
+    q = MixLinear_GEMM.from_linear(_Lin(d["W"], d["bias"] if "bias" in d.files else None), bit, cache=_Cache(),
+                                   layer_scales=ls, dev="cpu", fp_features_num=int(d["fp"]))
+    assert np.array_equal(q.q_weight.numpy(), d["q_weight"])
+    assert np.array_equal(q.scale_col.numpy().view(np.uint16), d["scale_col"].view(np.uint16))
+    if bit == 4:
+        assert np.array_equal(q.ind.numpy(), d["ind0"])
+        assert np.array_equal(q.weight_cache.numpy().view(np.uint16), d["weight_cache0"].view(np.uint16))
+        assert q.forward_without_precondition_len == int(d["fp"])
+    else:
+        assert q.ind.shape[0] == 0 and q.weight_cache is None
+    if "bias" in d.files:
+        assert np.array_equal(q.bias.numpy().view(np.uint16), d["bias"].view(np.uint16))
+    # the caller's weights are left intact
+    assert np.array_equal(d["W"].view(np.uint16), np.asarray(_Lin(d["W"]).weight.numpy()).view(np.uint16))
+
+
+def test_pack_to_i4_layout():
+    q = torch.arange(-8, 8, dtype=torch.int8).reshape(2, 8)
+    p = pack_to_i4(q)
+    assert p.dtype == torch.uint8 and tuple(p.shape) == (2, 4)
+    assert int(p[0, 0]) == ((16 - 8) | ((16 - 7) << 4))
+
+
+def test_ind_weight_cache_views_and_setters():
+    q = MixLinear_GEMM(128, 32, False, "cpu", 8, cache=_Cache())
+    assert q.ind.dtype == torch.int32 and q.ind.shape[0] == 0 and q.weight_cache is None
+    q.weight_cache = torch.ones(32, 70, dtype=torch.float16)
+    q.ind = torch.arange(70)
+    assert q.ind.shape[0] == 70 and tuple(q.weight_cache.shape) == (32, 70)
+    assert q._wc_buf.shape[1] % 64 == 0 and q._wc_buf.shape[1] >= 70     # TMA pitch: multiples of 64 fp16
+    assert q._wc_buf.stride(0) * 2 % 16 == 0
+    with pytest.raises(ValueError):
+        q.ind = torch.arange(129)
+    with pytest.raises(NotImplementedError):
+        MixLinear_GEMM(64, 32, False, "cpu", 8, weight_only=True)
+    with pytest.raises(ValueError):
+        MixLinear_GEMM(64, 32, False, "cpu", 3)
+
+
+def test_no_cpu_path():
+    """The product path must fail loudly instead of computing on the CPU."""
+    from mixq_b200.cache import MixLibCache
+    cache = MixLibCache(inputdim=8, device="cpu")
+    q = MixLinear_GEMM(64, 32, False, "cpu", 8, cache=cache)
+    q.add_outliers = False
+    with pytest.raises(_lib.MixqError):
+        q(torch.zeros(4, 64, dtype=torch.float16), None, True)
+    from mixq_b200 import mixlib
+    with pytest.raises(_lib.MixqError):
+        mixlib.FindRowScale(torch.zeros(4, 64, dtype=torch.float16), torch.zeros(4, 1, dtype=torch.float16), 4, 64, 8)
+    from mixq_b200.norm import FasterTransformerRMSNorm
+    with pytest.raises(_lib.MixqError):
+        FasterTransformerRMSNorm(torch.ones(64))(torch.zeros(4, 64, dtype=torch.float16))
+
+
+def test_library_missing_is_loud(monkeypatch, tmp_path):
+    monkeypatch.setenv("MIXQ_LIB", str(tmp_path / "nope.so"))
+    monkeypatch.setattr(_lib, "_lib", None)
+    with pytest.raises(_lib.MixqError, match="no CPU or PyTorch fallback"):
+        _lib.load()
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "mixq.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mixq_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """include/mixq.h <-> libmixq_sm100.so <-> the ctypes table: no drift, no compute call (no GPU here)."""
+    lib = _lib.load()
+    declared = _header_functions()
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/mixq.h but not exported"
+    assert set(_lib.SIGNATURES) == set(declared), set(_lib.SIGNATURES) ^ set(declared)
+    out = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert set(declared) <= exported
+    assert lib.mixq_version() == 100
+    assert lib.mixq_launch_count() == 0
+    # argument validation happens before any CUDA call
+    assert lib.mixq_set_tile_n(100) == -1
+    assert b"tile_n" in lib.mixq_last_error()
+    assert lib.mixq_set_tile_n(0) == 0
+
+
+def test_linear_args_struct_layout_matches_header():
+    """sizeof/field order of mixq_linear_args as the C compiler sees it vs the ctypes mirror."""
+    src = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "mixq.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(mixq_linear_args), offsetof(mixq_linear_args, q_weight),
+         offsetof(mixq_linear_args, ind), offsetof(mixq_linear_args, q_x), offsetof(mixq_linear_args, residual),
+         offsetof(mixq_linear_args, y), offsetof(mixq_linear_args, tile_n));
+  return 0;
+}'''
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "t.c")
+        open(c, "w").write(src)
+        exe = os.path.join(td, "t")
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        got = [int(v) for v in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    A = _lib.LinearArgs
+    want = [ctypes.sizeof(A), A.q_weight.offset, A.ind.offset, A.q_x.offset, A.residual.offset, A.y.offset, A.tile_n.offset]
+    assert got == want
+
+
+def test_llama_accounting_formulas():
+    """per-step algorithmic work of Llama-2-7B at M=512 = 6.63 TFLOP / 8.77 GB."""
+    M, H, I, L = 512, 4096, 11008, 32
+    shapes = [(3 * H, H), (H, H), (I, H), (I, H), (H, I)]
+    fl = sum(2 * M * n * k for n, k in shapes) * L
+    by = sum(n * k + 2 * M * k + 2 * M * n + 2 * n for n, k in shapes) * L
+    assert abs(fl / 1e12 - 6.63) < 0.01
+    assert abs(by / 1e9 - 8.77) < 0.3
