@@ -300,17 +300,29 @@ def run_mixq(args):
             return m(xw, None, True)
         if kind == "gate_proj":   # needs up_proj's q_x in the cache
             model.layers[0]["up_proj"].forward_norm_fused(h, model.layers[0]["ln2"], cfg.eps)
-        for m in mods[:3]:
-            launch(m)
+        # one CUDA graph holding this Linear of every layer (distinct weights: L2-cold, as in the step), so that the
+        # events bracket device time only and not the Python launch path
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for m in mods[:3]:
+                launch(m)
+        torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 3
-        g0.record()
-        for _ in range(reps):
+        gk = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gk):
             for m in mods:
                 launch(m)
+        gk.replay()
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        g0.record()
+        for _ in range(reps):
+            gk.replay()
         g1.record()
         torch.cuda.synchronize()
+        del gk
         t_launch = g0.elapsed_time(g1) * 1e-3 / (reps * len(mods))
         m0 = mods[0]
         N_, n_ = m0.out_features, m0._n_ind

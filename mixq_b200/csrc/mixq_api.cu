@@ -476,18 +476,9 @@ int mixq_rope_attention_decode(const void* qkv, void* k_cache, void* v_cache, in
     return fail(MIXQ_EINVAL, "bad attention arguments (head_dim must be 64 or 128)");
   if (past_len > 0 && (!k_cache || !v_cache || cache_cap <= past_len))
     return fail(MIXQ_EINVAL, "past_len > 0 needs k/v caches with capacity > past_len");
-  const long long warps = static_cast<long long>(M) * H;
-  const int grid = static_cast<int>((warps + 3) / 4);
-  const float scale = 1.0f / sqrtf(static_cast<float>(D));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (D == 128)
-    rope_attn_decode_kernel<128><<<grid, 128, 0, st>>>(static_cast<const __half*>(qkv), static_cast<__half*>(k_cache),
-                                                       static_cast<__half*>(v_cache), cache_cap, past_len,
-                                                       static_cast<__half*>(out), M, H, Hkv, theta, scale);
-  else
-    rope_attn_decode_kernel<64><<<grid, 128, 0, st>>>(static_cast<const __half*>(qkv), static_cast<__half*>(k_cache),
-                                                      static_cast<__half*>(v_cache), cache_cap, past_len,
-                                                      static_cast<__half*>(out), M, H, Hkv, theta, scale);
+  MIXQ_CUDA(launch_rope_attn_decode(static_cast<const __half*>(qkv), static_cast<__half*>(k_cache),
+                                    static_cast<__half*>(v_cache), cache_cap, past_len, static_cast<__half*>(out), M, H,
+                                    Hkv, D, theta, static_cast<cudaStream_t>(stream)));
   MIXQ_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;

@@ -203,8 +203,17 @@ __global__ void __launch_bounds__(128) rope_attn_decode_kernel(const __half* __r
 #pragma unroll
   for (int e = 0; e < E; ++e) op[lane + 32 * e] = __float2half_rn(acc[e] / den);
 }
-template __global__ void rope_attn_decode_kernel<64>(const __half*, __half*, __half*, int, int, __half*, int, int, int, float, float);
-template __global__ void rope_attn_decode_kernel<128>(const __half*, __half*, __half*, int, int, __half*, int, int, int, float, float);
+cudaError_t launch_rope_attn_decode(const __half* qkv, __half* k_cache, __half* v_cache, int cache_cap, int past_len,
+                                    __half* out, int M, int H, int Hkv, int D, float theta, cudaStream_t st) {
+  const long long warps = static_cast<long long>(M) * H;
+  const int grid = static_cast<int>((warps + 3) / 4);
+  const float scale = 1.0f / sqrtf(static_cast<float>(D));
+  if (D == 128)
+    rope_attn_decode_kernel<128><<<grid, 128, 0, st>>>(qkv, k_cache, v_cache, cache_cap, past_len, out, M, H, Hkv, theta, scale);
+  else
+    rope_attn_decode_kernel<64><<<grid, 128, 0, st>>>(qkv, k_cache, v_cache, cache_cap, past_len, out, M, H, Hkv, theta, scale);
+  return cudaGetLastError();
+}
 
 __global__ void mul_inplace_kernel(__half2* a, const __half2* __restrict__ b, long long n2) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n2;

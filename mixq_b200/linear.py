@@ -91,6 +91,7 @@ class MixLinear_GEMM(nn.Module):
         if cache is not None:
             self.sigma = torch.ones((1, 1), dtype=torch.float16, device=dev)
             self.sigma[0] = cache.sigma.reshape(-1)[0]
+        self._sigma_f = float(cache.sigma.reshape(-1)[0]) if cache is not None else 6.0   # host copy: no sync per launch
         self.arch = 10  # sm_100a only; the reference's arch == 9 split path (linear.py:234-241) is never taken
         self.name = name
         self._args = _lib.LinearArgs()
@@ -200,7 +201,7 @@ class MixLinear_GEMM(nn.Module):
         cache.over_flag.zero_()
         lib = _lib.load()
         _lib.check(lib.mixq_find_row_scale_scan(_ptr(inputs), _ptr(cache.x_scale), _ptr(q_x), M, K, self.bit,
-                                                float(self.sigma.reshape(-1)[0]), _ptr(col_over), _ptr(cache.over_flag),
+                                                self._sigma_f, _ptr(col_over), _ptr(cache.over_flag),
                                                 self._stream()), "FindRowScale(scan)")
         cache.q_xcache = q_x
 
@@ -249,7 +250,7 @@ class MixLinear_GEMM(nn.Module):
         a.x_scale = _ptr(cache.x_scale)
         a.act_outliers = _ptr(act_outliers)
         a.ld_ao = ld_ao
-        a.sigma = float(self.sigma.reshape(-1)[0]) if hasattr(self, "sigma") else 6.0
+        a.sigma = self._sigma_f
         a.col_over = 0
         a.over_flag = 0
         a.residual = _ptr(residual)

@@ -7,7 +7,7 @@ architecture and synthetic tokens (no checkpoint / dataset is reachable).  bench
 past_key_values between iterations (benchflops.py:124), so every step is an independent [B,1] forward with
 an empty KV cache; `past_len > 0` with a real cache is supported for completeness.
 
-Per decoder layer, steady state (after the two outlier-discovery calls), 6 launches:
+Per decoder layer, steady state (after the two outlier-discovery calls), 7 launches:
     W_pack    = RMSNorm + extract + quantise + int8 GEMM + fp16 outlier GEMM + dequant     (1 launch)
     attention = RoPE + single-query attention                                              (1 launch)
     o_proj    = extract + quantise + GEMMs + dequant + residual add                        (1 launch)
@@ -88,9 +88,13 @@ class LlamaDecoder:
         dgen = torch.Generator(device=device).manual_seed(seed)        # same on every rank: full weights, then shard
         f16 = torch.float16
 
-        def rand_w(n, k, row_boost=None):
-            # activations stay O(1): std 0.5/sqrt(k); boosted rows create ~1 % outlier channels downstream
-            w = torch.randn((n, k), generator=dgen, device=device, dtype=torch.float32) * (0.5 / k ** 0.5)
+        def rand_w(n, k, row_boost=None, forced_in=0.0):
+            # Synthetic statistics modelled on real LLM activations: inlier activations O(0.35) with ~1 % "massive"
+            # channels.  Linears fed by a normed x whose forced channels carry 20x the inlier magnitude get their
+            # weights scaled down accordingly (forced_in); boosted rows (x40) make ~1 % of the OUTPUT channels massive,
+            # which is what the next unfused Linear (o_proj / down_proj) then discovers as its outlier columns.
+            std = 0.35 / (k * (1.0 + 399.0 * forced_in)) ** 0.5
+            w = torch.randn((n, k), generator=dgen, device=device, dtype=torch.float32) * std
             if row_boost is not None and row_boost.numel():
                 w[row_boost.to(device)] *= 40.0
             return w.to(f16)
@@ -105,12 +109,12 @@ class LlamaDecoder:
             ln2[_forced(H, outlier_frac, gen)] = 20.0
             v_boost = _forced(cfg.kv_heads * D, outlier_frac, gen)
             up_boost = _forced(I, outlier_frac, gen)
-            wq = rand_w(cfg.heads * D, H)
-            wk = rand_w(cfg.kv_heads * D, H)
-            wv = rand_w(cfg.kv_heads * D, H, v_boost)
+            wq = rand_w(cfg.heads * D, H, None, outlier_frac)
+            wk = rand_w(cfg.kv_heads * D, H, None, outlier_frac)
+            wv = rand_w(cfg.kv_heads * D, H, v_boost, outlier_frac)
             wo = rand_w(H, cfg.heads * D)
-            wg = rand_w(I, H)
-            wu = rand_w(I, H, up_boost)
+            wg = rand_w(I, H, None, outlier_frac)
+            wu = rand_w(I, H, up_boost, outlier_frac)
             wd = rand_w(H, I)
             r, w_ = rank, world_size
             w_pack = pack_qkv_shard(wq, wk, wv, r, w_)
@@ -264,4 +268,4 @@ class LlamaDecoder:
         return fl, by
 
     def launches_per_step(self):
-        return 6 * self.n_layers + 1   # + final RMSNorm; embedding / lm_head are library calls
+        return 7 * self.n_layers + 1   # + final RMSNorm; embedding / lm_head are library calls

@@ -201,7 +201,7 @@ def test_llama_decode_step_vs_oracle(bit):
         else:
             n0 = _lib.launch_count()
             logits = m.step(tok)
-            assert _lib.launch_count() - n0 == 6 * cfg.layers + 1, "steady state: 6 launches per layer + final norm"
+            assert _lib.launch_count() - n0 == 7 * cfg.layers + 1, "steady state: 7 launches per layer + final norm"
         ref = oracle_logits()
         for L, lay in zip(m.layers, layers):
             for k, o in (("W_pack", lay.W_pack), ("o_proj", lay.o_proj), ("up_proj", lay.up), ("gate_proj", lay.gate), ("down_proj", lay.down)):
