@@ -44,6 +44,11 @@ unsigned long long mixq_launch_count(void);
  * 0 = heuristic (default), 128 or 256. */
 int mixq_set_tile_n(int tile_n);
 
+/* Tuning aid: device buffer of 148*8 uint64 that every subsequent mixq_linear_fused / GEMM launch fills with
+ * %globaltimer stamps per CTA (start, prologue done, grid barrier passed, first MMA, last MMA, epilogue done).
+ * NULL (default) disables it. */
+int mixq_set_trace_buffer(void* buf);
+
 /* ---- mixlib.FindRowScale(x, x_scale, M, K, bit) -> q_x        (linear.py:190-193, :221)
  * x_scale[m] = fp16(max_k |x[m,k]| / (2^(bit-1)-1));  q_x[m,k] = clamp(rint(x/x_scale)).
  * q_x is int8 [M,K] for bit 8 AND bit 4 (bit 4: values in [-7,7], one per byte — the packed form is

@@ -16,6 +16,7 @@ using namespace mixq;
 thread_local std::string g_err;
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<int> g_tile_n{0};
+std::atomic<unsigned long long*> g_trace{nullptr};
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -140,7 +141,7 @@ int pick_tile_n(int requested, int M, int N, int sms, bool tmem_outliers) {
   return cost(256) < cost(128) ? 256 : 128;
 }
 
-int pick_row_groups(RowQuantArgs* a, int grid, int warps_per_cta);
+int pick_row_groups(RowQuantArgs* a, int grid, int warps_per_cta, long long smem_budget);
 
 struct GemmCall {
   const void* q_x;
@@ -202,7 +203,15 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
     p.rq = *c.rq;
     p.fused_prologue = 1;
     // phase A runs on the persistent grid (one CTA per SM) with every warp of the GEMM CTA
-    if (int r = pick_row_groups(&p.rq, di.sms, w4 ? 12 : 8)) return r;
+    {
+      // row buffers live in the pipeline stages the weight prefetch does not use yet: all but the first stage
+      const long long stage = w4 ? (bn == 256 ? GemmCfg<256, true>::STAGE_BYTES : GemmCfg<128, true>::STAGE_BYTES)
+                                 : (bn == 256 ? GemmCfg<256, false>::STAGE_BYTES : GemmCfg<128, false>::STAGE_BYTES);
+      const int stages = w4 ? (bn == 256 ? GemmCfg<256, true>::STAGES : GemmCfg<128, true>::STAGES)
+                            : (bn == 256 ? GemmCfg<256, false>::STAGES : GemmCfg<128, false>::STAGES);
+      if (int r = pick_row_groups(&p.rq, di.sms, w4 ? 12 : 8, stage * (stages - 1))) return r;
+    }
+    p.rq.trace = g_trace.load(std::memory_order_relaxed);
   }
   p.x_scale = static_cast<const __half*>(c.x_scale);
   p.scale_col = static_cast<const __half*>(c.scale_col);
@@ -220,6 +229,7 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
   p.act = c.act;
   p.epilogue = c.epilogue;
   p.grid_sync = c.grid_sync;
+  p.trace = g_trace.load(std::memory_order_relaxed);
 
   const int tiles = ((c.M + 127) / 128) * ((c.N + bn - 1) / bn);
   const bool coop = p.fused_prologue != 0;
@@ -236,19 +246,20 @@ int grid_for(long long work_items, int threads, int sms, int per_sm = 8) {
   return static_cast<int>(blocks);
 }
 
-// Work split of the activation prologue: G warps per row so that all rows of the batch are in flight at
-// once when possible (latency, not bandwidth, bounds a 4 MB pass), subject to <= 32 vectors per lane.
-int pick_row_groups(RowQuantArgs* a, int grid, int warps_per_cta) {
+// Work split of the activation prologue: `ngroups` rows in flight per CTA (each needs K*2 bytes of shared memory),
+// G = warps / ngroups warps on each.  All rows of the batch in flight at once when possible: a 4 MB pass is bounded
+// by latency, not bandwidth.
+int pick_row_groups(RowQuantArgs* a, int grid, int warps_per_cta, long long smem_budget) {
   if (a->K > kRowQuantMaxK) return fail(MIXQ_EINVAL, "activation prologue supports K <= 32768");
-  const int nvec = a->K / 8;
-  int g_min = 1;
-  while (g_min < 4 && (nvec + 32 * g_min - 1) / (32 * g_min) > 32) g_min *= 2;
+  const long long row_bytes = static_cast<long long>(a->K) * 2;
   const int rows_per_cta = (a->M + grid - 1) / grid;
-  int g = 4;
-  while (g > g_min && warps_per_cta / g < rows_per_cta) g /= 2;
-  const int per_lane = (nvec + 32 * g - 1) / (32 * g);
-  a->group_warps = g;
-  a->nv = per_lane <= 8 ? 8 : (per_lane <= 16 ? 16 : 32);
+  long long ng = rows_per_cta;
+  if (ng > warps_per_cta) ng = warps_per_cta;
+  if (ng > kRowQuantMaxGroups) ng = kRowQuantMaxGroups;
+  if (ng > smem_budget / row_bytes) ng = smem_budget / row_bytes;
+  if (ng < 1) return fail(MIXQ_EINVAL, "activation row does not fit the shared-memory row buffer");
+  a->ngroups = static_cast<int>(ng);
+  a->group_warps = warps_per_cta / a->ngroups;
   return 0;
 }
 
@@ -284,13 +295,34 @@ int fill_rowquant(RowQuantArgs* a, void* x, const void* norm_w, void* norm_out, 
 int launch_rowquant(RowQuantArgs a, cudaStream_t st) {
   DeviceInfo di;
   if (int r = device_info(&di)) return r;
-  const int threads = 256;
-  // small batches: one row per CTA, 4 warps on it; large batches: up to 4 resident CTAs per SM
-  int grid = a.M < di.sms * 4 ? a.M : di.sms * 4;
-  if (int r = pick_row_groups(&a, grid, threads / 32)) return r;
-  const int groups = (threads / 32) / a.group_warps;
-  if (grid * groups > a.M) grid = (a.M + groups - 1) / groups;
-  rowquant_kernel<<<grid, threads, 0, st>>>(a);
+  constexpr int kThreads = 256, kWarps = kThreads / 32;
+  constexpr long long kMaxSmem = 200 * 1024;
+  // G warps per row so that a lane sees ~8 vectors; ngroups = 8 / G rows per CTA
+  const int nvec = a.K / 8;
+  int G = 1;
+  while (G < kWarps && nvec > 256 * G) G *= 2;
+  int ngroups = kWarps / G;
+  while (ngroups > 1 && static_cast<long long>(ngroups) * a.K * 2 > kMaxSmem) ngroups /= 2;
+  if (static_cast<long long>(ngroups) * a.K * 2 > kMaxSmem) return fail(MIXQ_EINVAL, "K too large for the row buffer");
+  a.group_warps = kWarps / ngroups;
+  a.ngroups = ngroups;
+  if (a.K > kRowQuantMaxK) return fail(MIXQ_EINVAL, "activation prologue supports K <= 32768");
+  const size_t smem = static_cast<size_t>(ngroups) * a.K * 2;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(rowquant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxSmem));
+  });
+  static thread_local int last_dev = -1;
+  int dev = 0;
+  MIXQ_CUDA(cudaGetDevice(&dev));
+  if (dev != last_dev) {
+    MIXQ_CUDA(cudaFuncSetAttribute(rowquant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxSmem)));
+    last_dev = dev;
+  }
+  long long grid = (a.M + ngroups - 1) / ngroups;
+  const long long cap = static_cast<long long>(di.sms) * 16;
+  if (grid > cap) grid = cap;
+  rowquant_kernel<<<static_cast<int>(grid), kThreads, smem, st>>>(a);
   MIXQ_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
@@ -306,6 +338,11 @@ unsigned long long mixq_launch_count(void) { return g_launches.load(std::memory_
 int mixq_set_tile_n(int tile_n) {
   if (tile_n != 0 && tile_n != 128 && tile_n != 256) return fail(MIXQ_EINVAL, "tile_n must be 0, 128 or 256");
   g_tile_n.store(tile_n, std::memory_order_relaxed);
+  return 0;
+}
+
+int mixq_set_trace_buffer(void* buf) {
+  g_trace.store(static_cast<unsigned long long*>(buf), std::memory_order_relaxed);
   return 0;
 }
 

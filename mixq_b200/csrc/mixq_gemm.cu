@@ -151,6 +151,8 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  unsigned long long* trace = p.trace ? p.trace + static_cast<size_t>(blockIdx.x) * 8 : nullptr;
+  if (trace && threadIdx.x == 0) trace[0] = globaltimer_ns();
 
   // ------------------------------------------------------------------ producer helpers
   // Work items of this CTA in issue order: (tile i, k-block kb), kb in [0, nkt).
@@ -179,10 +181,18 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
                            ? (ntiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1
                            : 0;
   const int my_items = my_tiles * nkt;
-  const int n_pre = (p.fused_prologue && my_items > 0) ? (my_items < STAGES ? my_items : STAGES) : 0;
+  // phase A parks its activation rows in the LAST pipeline stages; the weight prefetch may use the others
+  const int row_stages = p.fused_prologue
+                             ? static_cast<int>((static_cast<size_t>(p.rq.ngroups) * p.rq.K * 2 + Cfg::STAGE_BYTES - 1) / Cfg::STAGE_BYTES)
+                             : 0;
+  const int free_stages = STAGES - row_stages;
+  const int n_pre = (p.fused_prologue && my_items > 0) ? (my_items < free_stages ? my_items : free_stages) : 0;
 
   // ------------------------------------------------------------------ phase A (fused prologue)
   if (p.fused_prologue) {
+    RowQuantSmem* rq_sm = reinterpret_cast<RowQuantSmem*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
+    uint8_t* rowbuf = smem + static_cast<size_t>(free_stages) * Cfg::STAGE_BYTES;
+    rowquant_begin(p.rq, rq_sm, rowbuf);      // activation rows first: they are on the critical path
     if (warp == 0 && lane == 0) {
       for (int it = 0; it < n_pre; ++it) {
         const int tile = blockIdx.x + (it / nkt) * gridDim.x;
@@ -190,9 +200,11 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
       }
     }
     __syncwarp();
-    rowquant_cta(p.rq, reinterpret_cast<uint8_t*>(tmem_slot + 4));
+    rowquant_run(p.rq, rq_sm, rowbuf);
+    if (trace && threadIdx.x == 0) trace[1] = globaltimer_ns();
     fence_proxy_async_all();   // q_x / act_outliers were written through the generic proxy; TMA reads them next
     grid_barrier(p.grid_sync);
+    if (trace && threadIdx.x == 0) trace[2] = globaltimer_ns();
   }
 
   // ------------------------------------------------------------------ roles
@@ -231,6 +243,7 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
           if (W4) mbar_wait(&bar_ready[s], ph, 3, s);
           mbar_wait(&bar_full[s], ph, 4, s);
           tc_fence_after();
+          if (trace && i == 0 && kb == 0) trace[3] = globaltimer_ns();
           const uint64_t da = make_sw128_kmajor_desc(smem_u32(stage_a(s)));
           const uint64_t db = make_sw128_kmajor_desc(smem_u32(stage_b(s)));
           if (kb < nk) {
@@ -249,6 +262,7 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
         }
         umma_commit(&bar_tfull[as]);
       }
+      if (trace) trace[4] = globaltimer_ns();
     }
   } else if (warp >= 4 && warp < 8) {
     const int q = warp & 3;  // TMEM lane quarter this warp may read
@@ -276,6 +290,7 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
       tc_fence_before();
       mbar_arrive(&bar_tempty[as]);
     }
+    if (trace && warp == 4 && lane == 0) trace[5] = globaltimer_ns();
   } else if (W4 && warp >= 8) {
     // Nibble unpack: thread t owns weight rows t, t+128, ... of the tile.  Packed row = 64 B (128 nibbles,
     // low nibble = even k: linear.py:14-18); unpacked row = 128 B written as 8 x 16-byte chunks at the

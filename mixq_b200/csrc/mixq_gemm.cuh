@@ -28,6 +28,7 @@ struct LinearParams {
   int epilogue;
   int fused_prologue;
   uint32_t* grid_sync;
+  unsigned long long* trace;  // optional [gridDim.x * 8] globaltimer stamps (mixq_set_trace_buffer), debug/tuning only
 };
 
 template <int BN, bool W4>
@@ -40,7 +41,7 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES + BP_BYTES;
   static constexpr int STAGES = W4 ? (BN == 128 ? 5 : 3) : (BN == 128 ? 6 : 4);
   static constexpr int NUM_THREADS = W4 ? 384 : 256;         // W4 adds 4 unpack warps
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + kRowQuantSmemBytes;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 512 /*RowQuantSmem*/;
 };
 
 template <int BN, bool W4>

@@ -5,10 +5,11 @@
 
 namespace mixq {
 
-// Standalone activation prologue: groups of warps own rows (rowquant.cuh).
-__global__ void __launch_bounds__(256) rowquant_kernel(const RowQuantArgs a) {
-  __shared__ __align__(16) uint8_t smem[kRowQuantSmemBytes];
-  rowquant_cta(a, smem);
+// Standalone activation prologue: groups of warps own rows staged in dynamic shared memory (rowquant.cuh).
+__global__ void __launch_bounds__(256, 4) rowquant_kernel(const RowQuantArgs a) {
+  extern __shared__ __align__(128) uint8_t rowbuf[];
+  __shared__ RowQuantSmem sm;
+  rowquant_cta(a, &sm, rowbuf);
 }
 
 __global__ void extract_outliers_kernel(const int32_t* __restrict__ ind, int n_ind, __half* x, __half* out,
