@@ -1,0 +1,80 @@
+// Dequant epilogue shared by the 1-CTA and 2-CTA MixLinear kernels:
+//   y = act( fp16( (f32(acc_int) * x_scale[m]) * scale_col[n] + fp16(acc_outl) [+ outl[m,n]] ) ), then the reference's
+//   separate fp16 adds: + bias (linear.py:284-285), + residual (decoder layer).
+#pragma once
+#include "mixq_gemm.cuh"
+
+namespace mixq {
+
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+// fp16 + fp16 the way torch does it on fp16 tensors: add in fp32, round once to fp16.
+__device__ __forceinline__ __half2 hadd2_via_f32(__half2 a, __half2 b) {
+  const float2 af = __half22float2(a), bf = __half22float2(b);
+  return __floats2half2_rn(__fadd_rn(af.x, bf.x), __fadd_rn(af.y, bf.y));
+}
+
+// One 32-column slab of one accumulator row: TMEM -> registers -> dequant (+outliers, +bias, SiLU) -> global.
+// Every lane of the warp must call this (tcgen05.ld is warp-collective); row_ok masks the stores.
+template <bool HAS_O>
+__device__ __forceinline__ void epilogue_chunk(const LinearParams& p, uint32_t t_int, uint32_t t_out, int row,
+                                               bool row_ok, int n, float xs) {
+  uint32_t acc[32];
+  uint32_t oacc[32];
+  tmem_ld_32x32(t_int, acc);
+  if (HAS_O) tmem_ld_32x32(t_out, oacc);
+  tmem_ld_wait();
+  if (!row_ok || n >= p.N) return;
+  if (p.epilogue == EPI_RAW_I32) {
+    int32_t* dst = p.y_i32 + static_cast<size_t>(row) * p.N + n;
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      if (n + g * 4 < p.N)
+        reinterpret_cast<uint4*>(dst)[g] = make_uint4(acc[4 * g], acc[4 * g + 1], acc[4 * g + 2], acc[4 * g + 3]);
+    return;
+  }
+  const bool has_outl = p.outl != nullptr;
+  const bool has_bias = p.bias != nullptr;
+  const bool has_res = p.residual != nullptr;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {   // 8 columns per 16-byte store
+    const int ng = n + g * 8;
+    if (ng < p.N) {
+      const uint4 wsu = __ldg(reinterpret_cast<const uint4*>(p.scale_col + ng));
+      uint4 olu = make_uint4(0, 0, 0, 0), bsu = make_uint4(0, 0, 0, 0), rsu = make_uint4(0, 0, 0, 0);
+      if (has_outl) olu = *reinterpret_cast<const uint4*>(p.outl + static_cast<size_t>(row) * p.ld_outl + ng);
+      if (has_bias) bsu = __ldg(reinterpret_cast<const uint4*>(p.bias + ng));
+      if (has_res) rsu = *reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(row) * p.ld_res + ng);
+      const uint32_t wsw[4] = {wsu.x, wsu.y, wsu.z, wsu.w};
+      const uint32_t olw[4] = {olu.x, olu.y, olu.z, olu.w};
+      const uint32_t bsw[4] = {bsu.x, bsu.y, bsu.z, bsu.w};
+      const uint32_t rsw[4] = {rsu.x, rsu.y, rsu.z, rsu.w};
+      uint32_t ow[4];
+#pragma unroll
+      for (int j2 = 0; j2 < 4; ++j2) {
+        const float2 wf = __half22float2(*reinterpret_cast<const __half2*>(&wsw[j2]));
+        const float2 of = __half22float2(*reinterpret_cast<const __half2*>(&olw[j2]));
+        float v[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = g * 8 + j2 * 2 + h;
+          float t = __fmul_rn(__fmul_rn(static_cast<float>(static_cast<int32_t>(acc[c])), xs), h ? wf.y : wf.x);
+          // the reference's torch.mm(activation_outliers, weight_cache.T) returns fp16 (linear.py:248):
+          // round the fp32 tensor-core sum to fp16 before it joins the dequantised int part
+          if (HAS_O) t = __fadd_rn(t, __half2float(__float2half_rn(__uint_as_float(oacc[c]))));
+          if (has_outl) t = __fadd_rn(t, h ? of.y : of.x);
+          if (p.act == 1) t = silu_f(t);
+          v[h] = t;
+        }
+        __half2 o2 = __floats2half2_rn(v[0], v[1]);
+        // y1 += bias (linear.py:284-285) and the decoder's residual add are separate fp16 ops in the
+        // reference: each rounds to fp16 again
+        if (has_bias) o2 = hadd2_via_f32(o2, *reinterpret_cast<const __half2*>(&bsw[j2]));
+        if (has_res) o2 = hadd2_via_f32(o2, *reinterpret_cast<const __half2*>(&rsw[j2]));
+        ow[j2] = *reinterpret_cast<const uint32_t*>(&o2);
+      }
+      *reinterpret_cast<uint4*>(p.y + static_cast<size_t>(row) * p.N + ng) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+  }
+}
+
+}  // namespace mixq

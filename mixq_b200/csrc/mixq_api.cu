@@ -123,6 +123,52 @@ int launch_linear(const LinearParams& p, int grid, bool cooperative, cudaStream_
   return 0;
 }
 
+int launch_linear2(const LinearParams& p, int grid, bool cooperative, cudaStream_t st) {
+  using Cfg = Gemm2Cfg;
+  static thread_local int last_dev = -1;
+  int dev = 0;
+  MIXQ_CUDA(cudaGetDevice(&dev));
+  if (dev != last_dev) {
+    MIXQ_CUDA(cudaFuncSetAttribute(mixq_linear2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    last_dev = dev;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(Cfg::NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeCooperative;
+  attrs[0].val.cooperative = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = cooperative ? 1 : 0;
+  MIXQ_CUDA(cudaLaunchKernelEx(&cfg, mixq_linear2_kernel, p));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+// Tile width of the 2-CTA kernel: the multiple of 32 that minimises max(tensor time, L2 -> SM time) + exposed epilogue.
+int pick_bn2(int requested, int M, int N, int K, int n_out, int npairs) {
+  if (requested >= 32 && requested <= 256 && requested % 32 == 0) return requested;
+  const int forced = g_tile_n.load(std::memory_order_relaxed);
+  if (forced >= 32 && forced <= 256 && forced % 32 == 0) return forced;
+  const int mp = (M + 255) / 256;
+  const double nk = (K + 127) / 128 + (n_out + 63) / 64;
+  double best = 1e30;
+  int best_bn = 128;
+  for (int bn = 64; bn <= 256; bn += 32) {
+    const int nt = (N + bn - 1) / bn;
+    const int rounds = (mp * nt + npairs - 1) / npairs;
+    const double t_mma = rounds * nk * 4.0 * (bn / 2.0) / 1.9e3;                                   // us: bn/2 cycles per K=32 step
+    const double t_l2 = (static_cast<double>(nt) * M * K + static_cast<double>(mp) * N * K) / 10e6;   // us at ~10 TB/s L2 -> SM
+    const bool dbl = (2 + (n_out > 0 ? 1 : 0)) * bn <= 512;
+    const double t_epi = (dbl ? 1 : rounds) * bn * 0.010;                                          // us, not overlapped when single-buffered
+    const double t = (t_mma > t_l2 ? t_mma : t_l2) + t_epi;
+    if (t < best) { best = t; best_bn = bn; }
+  }
+  return best_bn;
+}
+
 int pick_tile_n(int requested, int M, int N, int sms, bool tmem_outliers) {
   if (requested == 128 || requested == 256) return requested;
   const int forced = g_tile_n.load(std::memory_order_relaxed);
@@ -176,7 +222,11 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
   if (c.n_out > 0 && (c.ld_ao % 8 != 0 || c.ld_wc % 8 != 0 || c.ld_ao < c.n_out || c.ld_wc < c.n_out))
     return fail(MIXQ_EINVAL, "outlier buffers need ld % 8 == 0 and ld >= n_ind");
   const bool w4 = (c.bit == 4);
-  const int bn = pick_tile_n(c.tile_n, c.M, c.N, di.sms, c.n_out > 0);
+  // M > 128: CTA pairs (cta_group::2) own 256 x bn tiles — half the L2 -> SM bytes per MMA cycle (mixq_gemm2.cu)
+  const bool two_cta = !w4 && c.M > 128 && di.sms >= 2;
+  const int npairs = di.sms / 2;
+  const int bn = two_cta ? pick_bn2(c.tile_n, c.M, c.N, c.K, c.n_out, npairs) : pick_tile_n(c.tile_n, c.M, c.N, di.sms, c.n_out > 0);
+  const int b_rows = two_cta ? bn / 2 : bn;
 
   LinearParams p{};
   if (int r = make_map(&p.tm_a, c.q_x, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, c.K, c.M, c.K, 128, 128,
@@ -187,7 +237,7 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
                          CU_TENSOR_MAP_SWIZZLE_NONE))
       return r;
   } else {
-    if (int r = make_map(&p.tm_b, c.q_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, c.K, c.N, c.K, 128, bn,
+    if (int r = make_map(&p.tm_b, c.q_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, c.K, c.N, c.K, 128, b_rows,
                          CU_TENSOR_MAP_SWIZZLE_128B))
       return r;
   }
@@ -196,7 +246,7 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
                          static_cast<long long>(c.ld_ao) * 2, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B))
       return r;
     if (int r = make_map(&p.tm_ob, c.weight_cache, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c.n_out, c.N,
-                         static_cast<long long>(c.ld_wc) * 2, 64, bn, CU_TENSOR_MAP_SWIZZLE_128B))
+                         static_cast<long long>(c.ld_wc) * 2, 64, b_rows, CU_TENSOR_MAP_SWIZZLE_128B))
       return r;
   }
   if (c.rq != nullptr) {
@@ -209,7 +259,13 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
                                  : (bn == 256 ? GemmCfg<256, false>::STAGE_BYTES : GemmCfg<128, false>::STAGE_BYTES);
       const int stages = w4 ? (bn == 256 ? GemmCfg<256, true>::STAGES : GemmCfg<128, true>::STAGES)
                             : (bn == 256 ? GemmCfg<256, false>::STAGES : GemmCfg<128, false>::STAGES);
-      if (int r = pick_row_groups(&p.rq, di.sms, w4 ? 12 : 8, stage * (stages - 1))) return r;
+      if (two_cta) {
+        if (int r = pick_row_groups(&p.rq, npairs * 2, Gemm2Cfg::NUM_THREADS / 32,
+                                    static_cast<long long>(Gemm2Cfg::STAGE_BYTES) * (Gemm2Cfg::STAGES - 1)))
+          return r;
+      } else if (int r = pick_row_groups(&p.rq, di.sms, w4 ? 12 : 8, stage * (stages - 1))) {
+        return r;
+      }
     }
     p.rq.trace = g_trace.load(std::memory_order_relaxed);
   }
@@ -231,6 +287,13 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
   p.grid_sync = c.grid_sync;
   p.trace = g_trace.load(std::memory_order_relaxed);
 
+  p.bn = bn;
+  if (two_cta) {
+    const int tiles2 = ((c.M + 255) / 256) * ((c.N + bn - 1) / bn);
+    const bool coop2 = p.fused_prologue != 0;
+    const int grid2 = coop2 ? npairs * 2 : 2 * (tiles2 < npairs ? tiles2 : npairs);
+    return launch_linear2(p, grid2, coop2, st);
+  }
   const int tiles = ((c.M + 127) / 128) * ((c.N + bn - 1) / bn);
   const bool coop = p.fused_prologue != 0;
   const int grid = coop ? di.sms : (tiles < di.sms ? tiles : di.sms);
@@ -336,7 +399,8 @@ const char* mixq_last_error(void) { return g_err.c_str(); }
 int mixq_version(void) { return 100; }
 unsigned long long mixq_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 int mixq_set_tile_n(int tile_n) {
-  if (tile_n != 0 && tile_n != 128 && tile_n != 256) return fail(MIXQ_EINVAL, "tile_n must be 0, 128 or 256");
+  if (tile_n != 0 && (tile_n < 32 || tile_n > 256 || tile_n % 32 != 0))
+    return fail(MIXQ_EINVAL, "tile_n must be 0 or a multiple of 32 up to 256 (the 1-CTA kernel honours 128 and 256 only)");
   g_tile_n.store(tile_n, std::memory_order_relaxed);
   return 0;
 }

@@ -28,6 +28,7 @@ struct LinearParams {
   int epilogue;
   int fused_prologue;
   uint32_t* grid_sync;
+  int bn;              // 2-CTA kernel: run-time tile width (multiple of 32, <= 256)
   unsigned long long* trace;  // optional [gridDim.x * 8] globaltimer stamps (mixq_set_trace_buffer), debug/tuning only
 };
 
@@ -46,5 +47,17 @@ struct GemmCfg {
 
 template <int BN, bool W4>
 __global__ void mixq_linear_kernel(const __grid_constant__ LinearParams p);
+
+// 2-CTA (cta_group::2) kernel: a CTA pair owns a 256 x bn tile; each CTA stages 128 activation rows + bn/2 weight rows.
+struct Gemm2Cfg {
+  static constexpr int A_BYTES = 128 * 128;                  // 16 KB
+  static constexpr int B_BYTES = 128 * 128;                  // up to bn/2 = 128 weight rows
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 6;
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;   // TMA, MMA, TMEM-alloc, spare + epilogue warps
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 512 /*RowQuantSmem*/;
+};
+__global__ void mixq_linear2_kernel(const __grid_constant__ LinearParams p);
 
 }  // namespace mixq
