@@ -77,4 +77,73 @@ __device__ __forceinline__ void epilogue_chunk(const LinearParams& p, uint32_t t
   }
 }
 
+
+// A span of `ncols` (multiple of 16) accumulator columns of one row, as a ROLLED loop over 16-column groups: the body is
+// ~200 instructions and stays in the instruction cache (the fully unrolled 32-column form above is paced by
+// instruction fetch when only 1-2 warps per scheduler run it).  Every lane of the warp must call this.
+template <bool HAS_O>
+__device__ __forceinline__ void epilogue_span(const LinearParams& p, uint32_t t_int, uint32_t t_out, int row, bool row_ok,
+                                              int n0, int ncols, float xs) {
+  const bool has_outl = p.outl != nullptr;
+  const bool has_bias = p.bias != nullptr;
+  const bool has_res = p.residual != nullptr;
+  const bool raw = p.epilogue == EPI_RAW_I32;
+  const bool silu = p.act == 1;
+#pragma unroll 1
+  for (int c = 0; c < ncols; c += 16) {
+    uint32_t acc[16];
+    uint32_t oacc[16];
+    tmem_ld_32x16(t_int + c, acc);
+    if (HAS_O) tmem_ld_32x16(t_out + c, oacc);
+    tmem_ld_wait();
+    const int n = n0 + c;
+    if (!row_ok || n >= p.N) continue;
+    if (raw) {
+      int32_t* dst = p.y_i32 + static_cast<size_t>(row) * p.N + n;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (n + g * 4 < p.N)
+          reinterpret_cast<uint4*>(dst)[g] = make_uint4(acc[4 * g], acc[4 * g + 1], acc[4 * g + 2], acc[4 * g + 3]);
+      continue;
+    }
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {   // 8 columns per 16-byte store
+      const int ng = n + g * 8;
+      if (ng < p.N) {
+        const uint4 wsu = __ldg(reinterpret_cast<const uint4*>(p.scale_col + ng));
+        uint4 olu = make_uint4(0, 0, 0, 0), bsu = make_uint4(0, 0, 0, 0), rsu = make_uint4(0, 0, 0, 0);
+        if (has_outl) olu = *reinterpret_cast<const uint4*>(p.outl + static_cast<size_t>(row) * p.ld_outl + ng);
+        if (has_bias) bsu = __ldg(reinterpret_cast<const uint4*>(p.bias + ng));
+        if (has_res) rsu = *reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(row) * p.ld_res + ng);
+        const uint32_t wsw[4] = {wsu.x, wsu.y, wsu.z, wsu.w};
+        const uint32_t olw[4] = {olu.x, olu.y, olu.z, olu.w};
+        const uint32_t bsw[4] = {bsu.x, bsu.y, bsu.z, bsu.w};
+        const uint32_t rsw[4] = {rsu.x, rsu.y, rsu.z, rsu.w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int j2 = 0; j2 < 4; ++j2) {
+          const float2 wf = __half22float2(*reinterpret_cast<const __half2*>(&wsw[j2]));
+          const float2 of = __half22float2(*reinterpret_cast<const __half2*>(&olw[j2]));
+          float v[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int cc = g * 8 + j2 * 2 + h;
+            float t = __fmul_rn(__fmul_rn(static_cast<float>(static_cast<int32_t>(acc[cc])), xs), h ? wf.y : wf.x);
+            // torch.mm(activation_outliers, weight_cache.T) returns fp16 (linear.py:248): round the fp32 tensor-core sum
+            if (HAS_O) t = __fadd_rn(t, __half2float(__float2half_rn(__uint_as_float(oacc[cc]))));
+            if (has_outl) t = __fadd_rn(t, h ? of.y : of.x);
+            if (silu) t = silu_f(t);
+            v[h] = t;
+          }
+          __half2 o2 = __floats2half2_rn(v[0], v[1]);
+          if (has_bias) o2 = hadd2_via_f32(o2, *reinterpret_cast<const __half2*>(&bsw[j2]));
+          if (has_res) o2 = hadd2_via_f32(o2, *reinterpret_cast<const __half2*>(&rsw[j2]));
+          ow[j2] = *reinterpret_cast<const uint32_t*>(&o2);
+        }
+        *reinterpret_cast<uint4*>(p.y + static_cast<size_t>(row) * p.N + ng) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      }
+    }
+  }
+}
+
 }  // namespace mixq

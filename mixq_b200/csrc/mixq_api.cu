@@ -158,12 +158,19 @@ int pick_bn2(int requested, int M, int N, int K, int n_out, int npairs) {
   int best_bn = 128;
   for (int bn = 64; bn <= 256; bn += 32) {
     const int nt = (N + bn - 1) / bn;
-    const int rounds = (mp * nt + npairs - 1) / npairs;
-    const double t_mma = rounds * nk * 4.0 * (bn / 2.0) / 1.9e3;                                   // us: bn/2 cycles per K=32 step
-    const double t_l2 = (static_cast<double>(nt) * M * K + static_cast<double>(mp) * N * K) / 10e6;   // us at ~10 TB/s L2 -> SM
-    const bool dbl = (2 + (n_out > 0 ? 1 : 0)) * bn <= 512;
-    const double t_epi = (dbl ? 1 : rounds) * bn * 0.010;                                          // us, not overlapped when single-buffered
-    const double t = (t_mma > t_l2 ? t_mma : t_l2) + t_epi;
+    const int tiles = mp * nt;
+    const int rounds = (tiles + npairs - 1) / npairs;
+    const double t_mma_tile = nk * 4.0 * (bn / 2.0) / 1.9e3 + 0.5;          // us: bn/2 cycles per K=32 step, + pipeline fill
+    const double tile_bytes = (256.0 + bn) * K;                            // activations + weights one pair pulls per tile
+    double t = 0;
+    for (int r = 0; r < rounds; ++r) {
+      const int active = (tiles - r * npairs) < npairs ? (tiles - r * npairs) : npairs;
+      const double t_l2 = active * tile_bytes / 10e6;                      // us at ~10 TB/s aggregate L2 -> SM
+      t += t_mma_tile > t_l2 ? t_mma_tile : t_l2;
+    }
+    const int slots = (512 - (n_out > 0 ? bn : 0)) / bn;
+    const double t_epi_tile = bn * 0.008;                                  // us per tile epilogue
+    t += t_epi_tile * (rounds > slots ? 1 + (rounds - slots) : 1);         // exposed epilogues
     if (t < best) { best = t; best_bn = bn; }
   }
   return best_bn;
@@ -288,6 +295,8 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
   p.trace = g_trace.load(std::memory_order_relaxed);
 
   p.bn = bn;
+  p.q_w = static_cast<const uint8_t*>(c.q_w);
+  p.q_w_pitch = w4 ? c.K / 2 : c.K;
   if (two_cta) {
     const int tiles2 = ((c.M + 255) / 256) * ((c.N + bn - 1) / bn);
     const bool coop2 = p.fused_prologue != 0;

@@ -5,7 +5,7 @@
 //                       + outl[m,n] + bias[n] ) )
 //
 // One persistent CTA per SM, warp-specialised:
-//   warp 0      TMA producer   (cp.async.bulk.tensor, SWIZZLE_128B boxes, mbarrier complete_tx)
+//   warp 0 / 3  TMA producers: activations / weights (cp.async.bulk.tensor, SWIZZLE_128B boxes, mbarrier complete_tx)
 //   warp 1      MMA issuer     (one lane issues tcgen05.mma; tcgen05.commit frees smem stages / publishes TMEM)
 //   warp 2      TMEM allocator (512 columns; double-buffered accumulators when they fit)
 //   warps 4-7   epilogue       (tcgen05.ld 32x32b -> registers -> dequant/bias/SiLU -> 16-byte global stores)
@@ -122,7 +122,7 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
     RowQuantSmem* rq_sm = reinterpret_cast<RowQuantSmem*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
     uint8_t* rowbuf = smem + static_cast<size_t>(free_stages) * Cfg::STAGE_BYTES;
     rowquant_begin(p.rq, rq_sm, rowbuf);      // activation rows first: they are on the critical path
-    if (warp == 0 && lane == 0) {
+    if (warp == 3 && lane == 0) {
       for (int it = 0; it < n_pre; ++it) {
         const int tile = blockIdx.x + (it / nkt) * gridDim.x;
         produce(tile, it % nkt, it, /*act*/ false, /*wgt*/ true, /*arm*/ true);
@@ -137,19 +137,22 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
   }
 
   // ------------------------------------------------------------------ roles
-  if (warp == 0) {
+  // Two producer threads (one TMA op costs its issuing thread ~300 cycles: tools/tma_bw.cu): warp 3 streams the weights
+  // and arms the stage barrier, warp 0 streams the activations.
+  if (warp == 0 || warp == 3) {
     if (lane == 0) {
+      const bool wgt = warp == 3;
       fence_proxy_async_all();
       int it = 0, s = 0;
       uint32_t ph = 0;
       for (int i = 0; i < my_tiles; ++i) {
         const int tile = blockIdx.x + i * gridDim.x;
         for (int kb = 0; kb < nkt; ++kb, ++it) {
-          if (it < n_pre) {
-            produce(tile, kb, s, true, false, false);
+          if (it >= n_pre) mbar_wait(&bar_empty[s], ph ^ 1, 1, s);
+          if (wgt) {
+            if (it >= n_pre) produce(tile, kb, s, false, true, true);
           } else {
-            mbar_wait(&bar_empty[s], ph ^ 1, 1, s);
-            produce(tile, kb, s, true, true, true);
+            produce(tile, kb, s, true, false, false);
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -211,11 +214,8 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
       const uint32_t t_int = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * acc_cols;
       const uint32_t t_out = t_int + BN;
 
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (nko > 0) epilogue_chunk<true>(p, t_int + c0, t_out + c0, row, row_ok, n0 + c0, xs);
-        else epilogue_chunk<false>(p, t_int + c0, 0u, row, row_ok, n0 + c0, xs);
-      }
+      if (nko > 0) epilogue_span<true>(p, t_int, t_out, row, row_ok, n0, BN, xs);
+      else epilogue_span<false>(p, t_int, 0u, row, row_ok, n0, BN, xs);
       tc_fence_before();
       mbar_arrive(&bar_tempty[as]);
     }

@@ -29,6 +29,8 @@ struct LinearParams {
   int fused_prologue;
   uint32_t* grid_sync;
   int bn;              // 2-CTA kernel: run-time tile width (multiple of 32, <= 256)
+  const uint8_t* q_w;  // raw weight pointer + row pitch in bytes (L2 prefetch of the weight stream)
+  long long q_w_pitch;
   unsigned long long* trace;  // optional [gridDim.x * 8] globaltimer stamps (mixq_set_trace_buffer), debug/tuning only
 };
 

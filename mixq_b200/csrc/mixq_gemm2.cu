@@ -7,10 +7,11 @@
 // tcgen05.mma.cta_group::2 (issued by the pair's leader) reads both halves — half the L2 bytes per MMA cycle.
 // BN is a run-time multiple of 32 (<= 256) chosen on the host so that the tile count fills the 74 pairs evenly.
 //
-//   warp 0      TMA producer (both CTAs; loads land in the local smem, complete_tx on the LEADER's mbarrier)
+//   warp 0 / 3  TMA producers: activations / weights (both CTAs; loads land in the local smem, complete_tx on the
+//               LEADER's mbarrier)
 //   warp 1      MMA issuer   (leader CTA only; tcgen05.commit multicast frees the stage in both CTAs)
 //   warp 2      TMEM allocator (cta_group::2, 512 columns in each CTA)
-//   warps 4-11  epilogue     (2 warps per TMEM lane quarter, alternating 32-column chunks)
+//   warps 4-11  epilogue     (2 warps per TMEM lane quarter, one half of the tile's columns each)
 // Phase A (activation prologue, rowquant.cuh) and the grid barrier are the same as in the 1-CTA kernel.
 //
 // Reference behaviour this replaces: mixlib.int8FusedDequantize[Silu] and the torch.mm outlier GEMM in
@@ -29,8 +30,8 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);   // used in the leader only
   uint64_t* bar_empty = bar_full + STAGES;                                              // per CTA (multicast commit)
   uint64_t* bar_tfull = bar_empty + STAGES;                                             // per CTA (multicast commit)
-  uint64_t* bar_tempty = bar_tfull + 2;                                                 // used in the leader only
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+  uint64_t* bar_tempty = bar_tfull + 4;                                                 // used in the leader only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 4);
 
   auto stage_a = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
   auto stage_b = [&](int s) { return smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
@@ -51,7 +52,9 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
   const int NT = (p.N + bn - 1) / bn;
   const int ntiles = MP * NT;
   const bool has_o = nko > 0;
-  const int nint = ((2 + (has_o ? 1 : 0)) * bn <= 512) ? 2 : 1;   // int32 accumulator slots; the fp32 outlier slot is single
+  // int32 accumulator slots in a ring (a tile's epilogue overlaps the next tiles' MMAs); the fp32 outlier slot is single
+  int nint = (512 - (has_o ? bn : 0)) / bn;
+  if (nint > 4) nint = 4;
   const uint32_t col_outl = static_cast<uint32_t>(nint * bn);
   const uint32_t stage_tx = 2u * (Cfg::A_BYTES + static_cast<uint32_t>(bh) * 128u);   // both CTAs' bytes land on one barrier
 
@@ -68,7 +71,7 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
       mbar_init(&bar_full[s], 1);
       mbar_init(&bar_empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 4; ++s) {
       mbar_init(&bar_tfull[s], 1);
       mbar_init(&bar_tempty[s], 2 * Cfg::EPI_WARPS);   // one arrival per epilogue warp of both CTAs
     }
@@ -115,7 +118,7 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
     RowQuantSmem* rq_sm = reinterpret_cast<RowQuantSmem*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
     uint8_t* rowbuf = smem + static_cast<size_t>(free_stages) * Cfg::STAGE_BYTES;
     rowquant_begin(p.rq, rq_sm, rowbuf);      // activation rows first: they are on the critical path
-    if (warp == 0 && lane == 0) {
+    if (warp == 3 && lane == 0) {
       for (int it = 0; it < n_pre; ++it) {
         const int tile = pair + (it / nkt) * npairs;
         produce(tile, it % nkt, it, /*act*/ false, /*wgt*/ true, /*arm*/ true);
@@ -130,19 +133,25 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
   }
 
   // ------------------------------------------------------------------ roles
-  if (warp == 0) {
+  // Two producer threads: one TMA op costs its issuing thread ~300 cycles (tools/tma_bw.cu: 54 B/clk/SM with one issuer,
+  // 71 with two), and a pair tile needs up to 64 B/clk/SM.  (Tried and dropped: pulling the weight boxes into L2 ahead of
+  // the loads — cp.async.bulk.prefetch.tensor costs a TMA issue slot per box and made the loop 15 % slower; a spare warp
+  // issuing prefetch.global.L2 changed nothing: the loop is bound by bytes landing per SM, not by DRAM latency.)  Warp 3 streams the weights (and arms the stage barrier),
+  // warp 0 the activations.
+  if (warp == 0 || warp == 3) {
     if (lane == 0) {
+      const bool wgt = warp == 3;
       fence_proxy_async_all();
       int it = 0, s = 0;
       uint32_t ph = 0;
       for (int i = 0; i < my_tiles; ++i) {
         const int tile = pair + i * npairs;
         for (int kb = 0; kb < nkt; ++kb, ++it) {
-          if (it < n_pre) {
-            produce(tile, kb, s, true, false, false);
+          if (it >= n_pre) mbar_wait(&bar_empty[s], ph ^ 1, 1, s);
+          if (wgt) {
+            if (it >= n_pre) produce(tile, kb, s, false, true, true);
           } else {
-            mbar_wait(&bar_empty[s], ph ^ 1, 1, s);
-            produce(tile, kb, s, true, true, true);
+            produce(tile, kb, s, true, false, false);
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -162,7 +171,7 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
         const uint32_t d_int = tmem_base + static_cast<uint32_t>(slot * bn);
         const uint32_t d_out = tmem_base + col_outl;
         for (int kb = 0; kb < nkt; ++kb) {
-          if (kb == nk && nint == 2 && i > 0) {
+          if (kb == nk && nint >= 2 && i > 0) {
             // the single fp32 outlier slot is still being read by the previous tile's epilogue
             mbar_wait(&bar_tempty[(i - 1) % nint], static_cast<uint32_t>((i - 1) / nint) & 1, 8, i);
             tc_fence_after();
@@ -192,7 +201,7 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
     }
   } else if (warp >= 4) {
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int half = (warp - 4) >> 2;       // which of the alternating 32-column chunks
+    const int half = (warp - 4) >> 2;       // which half of the tile's columns
     for (int i = 0; i < my_tiles; ++i) {
       const int tile = pair + i * npairs;
       const int m0 = (tile % MP) * 256 + static_cast<int>(rank) * 128;
@@ -208,11 +217,10 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
       tc_fence_after();
       const uint32_t t_int = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(slot * bn);
       const uint32_t t_out = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + col_outl;
-#pragma unroll 1
-      for (int c0 = half * 32; c0 < bn; c0 += 64) {
-        if (has_o) epilogue_chunk<true>(p, t_int + c0, t_out + c0, row, row_ok, n0 + c0, xs);
-        else epilogue_chunk<false>(p, t_int + c0, 0u, row, row_ok, n0 + c0, xs);
-      }
+      const int span = bn >> 1;           // this warp's contiguous half of the tile's columns
+      const int c0 = half * span;
+      if (has_o) epilogue_span<true>(p, t_int + c0, t_out + c0, row, row_ok, n0 + c0, span, xs);
+      else epilogue_span<false>(p, t_int + c0, 0u, row, row_ok, n0 + c0, span, xs);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_tempty[slot]), 0));

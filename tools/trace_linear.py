@@ -1,5 +1,5 @@
 """Per-phase timeline of one mixq_linear_fused launch from in-kernel %globaltimer stamps."""
-import ctypes as C, sys
+import ctypes as C, os, sys
 import torch
 sys.path.insert(0, ".")
 from mixq_b200 import _lib
@@ -8,7 +8,10 @@ M = 512
 dev = "cuda"
 g = torch.Generator(device=dev).manual_seed(0)
 trace = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
-for (N, K) in [(12288, 4096), (4096, 4096), (4096, 11008)]:
+TILE = int(os.environ.get('TILE', '0'))
+MODES = os.environ.get('MODES', 'plain,skip').split(',')
+SHAPES = [tuple(int(v) for v in t.split('x')) for t in os.environ.get('SHAPES', '12288x4096,4096x4096,4096x11008').split(',')]
+for (N, K) in SHAPES:
     n, cap = 41, 64
     cols = torch.randperm(K, generator=g, device=dev)[:n].sort().values.int()
     x0 = torch.randn(M, K, generator=g, device=dev); x0[:, cols.long()] *= 20; x0 = x0.half()
@@ -18,14 +21,14 @@ for (N, K) in [(12288, 4096), (4096, 4096), (4096, 11008)]:
     q_x = torch.zeros(M, K, dtype=torch.int8, device=dev); xs = torch.zeros(M, dtype=torch.float16, device=dev)
     ao = torch.zeros(M, cap, dtype=torch.float16, device=dev); y = torch.zeros(M, N, dtype=torch.float16, device=dev)
     sync = torch.zeros(1, dtype=torch.int32, device=dev); x = x0.clone()
-    for mode in ("plain", "skip"):
+    for mode in MODES:
         for it, (qw, ws, wc) in enumerate(ws_l):
             a = _lib.LinearArgs()
             a.x = x.data_ptr(); a.M, a.N, a.K = M, N, K
             a.q_weight = qw.data_ptr(); a.scale_col = ws.data_ptr(); a.bit = 8
             a.ind = cols.data_ptr(); a.n_ind = n; a.weight_cache = wc.data_ptr(); a.ld_wc = cap
             a.q_x = q_x.data_ptr(); a.x_scale = xs.data_ptr(); a.act_outliers = ao.data_ptr(); a.ld_ao = cap
-            a.sigma = 6.0; a.y = y.data_ptr(); a.grid_sync = sync.data_ptr(); a.skip_prologue = 1 if mode == "skip" else 0
+            a.sigma = 6.0; a.y = y.data_ptr(); a.grid_sync = sync.data_ptr(); a.skip_prologue = 1 if mode == "skip" else 0; a.tile_n = TILE
             lib.mixq_set_trace_buffer(trace.data_ptr() if it == 3 else 0)
             trace.zero_()
             torch.cuda.synchronize()
@@ -36,6 +39,6 @@ for (N, K) in [(12288, 4096), (4096, 4096), (4096, 11008)]:
         def col(i):
             v = t[:, i][t[:, i] > 0]
             return (f"{(v.min()-t0)/1e3:6.2f}..{(v.max()-t0)/1e3:6.2f}" if len(v) else "      -       ")
-        print(f"N={N} K={K} {mode:5s} us since first CTA start: start {col(0)} | mask built {col(6)} | row0 absmax {col(7)} | prologue done {col(1)} | barrier passed {col(2)} | "
+        print(f"N={N} K={K} tile={TILE} {mode:5s} us since first CTA start: start {col(0)} | mask built {col(6)} | row0 absmax {col(7)} | prologue done {col(1)} | barrier passed {col(2)} | "
               f"first MMA {col(3)} | last MMA {col(4)} | epilogue done {col(5)}")
 lib.mixq_set_trace_buffer(0)
