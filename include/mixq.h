@@ -152,7 +152,7 @@ typedef struct mixq_linear_args {
   /* control */
   int skip_prologue;       /* 1: q_x / x_scale / act_outliers already valid (gate_proj, linear.py:291-376) */
   uint32_t* grid_sync;     /* one zero-initialised u32 in device memory, reused across launches */
-  int tile_n;              /* 0 = auto, else 128 or 256 */
+  int tile_n;              /* 0 = auto; else a multiple of 32 up to 512 (the 1-CTA kernel, M <= 128 or W4, honours 128 / 256 only) */
 } mixq_linear_args;
 
 int mixq_linear_fused(const mixq_linear_args* args /* host */, void* stream);

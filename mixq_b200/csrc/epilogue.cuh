@@ -83,8 +83,8 @@ __device__ __forceinline__ void epilogue_chunk(const LinearParams& p, uint32_t t
 // instruction fetch when only 1-2 warps per scheduler run it).  Every lane of the warp must call this.
 template <bool HAS_O>
 __device__ __forceinline__ void epilogue_span(const LinearParams& p, uint32_t t_int, uint32_t t_out, int row, bool row_ok,
-                                              int n0, int ncols, float xs) {
-  const bool has_outl = p.outl != nullptr;
+                                              int n0, int ncols, float xs, const __half* addend, int ld_addend) {
+  const bool has_outl = addend != nullptr;
   const bool has_bias = p.bias != nullptr;
   const bool has_res = p.residual != nullptr;
   const bool raw = p.epilogue == EPI_RAW_I32;
@@ -112,7 +112,7 @@ __device__ __forceinline__ void epilogue_span(const LinearParams& p, uint32_t t_
       if (ng < p.N) {
         const uint4 wsu = __ldg(reinterpret_cast<const uint4*>(p.scale_col + ng));
         uint4 olu = make_uint4(0, 0, 0, 0), bsu = make_uint4(0, 0, 0, 0), rsu = make_uint4(0, 0, 0, 0);
-        if (has_outl) olu = *reinterpret_cast<const uint4*>(p.outl + static_cast<size_t>(row) * p.ld_outl + ng);
+        if (has_outl) olu = *reinterpret_cast<const uint4*>(addend + static_cast<size_t>(row) * ld_addend + ng);
         if (has_bias) bsu = __ldg(reinterpret_cast<const uint4*>(p.bias + ng));
         if (has_res) rsu = *reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(row) * p.ld_res + ng);
         const uint32_t wsw[4] = {wsu.x, wsu.y, wsu.z, wsu.w};
@@ -143,6 +143,118 @@ __device__ __forceinline__ void epilogue_span(const LinearParams& p, uint32_t t_
         *reinterpret_cast<uint4*>(p.y + static_cast<size_t>(row) * p.N + ng) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
       }
     }
+  }
+}
+
+
+}  // namespace mixq
+
+// ================================================================ coalesced epilogue (2-CTA kernel)
+// A thread owns one accumulator ROW (that is how tcgen05.ld hands out TMEM), so direct 16-byte stores from the 32 lanes of
+// a warp touch 32 different rows: 32 memory transactions of 16 bytes per instruction (measured: 12 us to drain a
+// 128 x 352 tile).  Each epilogue warp therefore owns a 4 KB staging tile (32 rows x 64 fp16, 16-byte chunks XOR-swizzled
+// by row so that both the row-wise and the 8-lanes-per-row accesses are conflict free) and moves 64 columns at a time
+// between it and global memory with 8 lanes per row: 4 full 128-byte lines per instruction.
+namespace mixq {
+
+constexpr int kEpiStageBytes = 32 * 128;
+
+__device__ __forceinline__ uint4* epi_slot(uint8_t* stage, int row, int chunk) {
+  return reinterpret_cast<uint4*>(stage + row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+// global [m_base + r][n_blk + 8c] -> stage[r][c]  for r < 32, c < nchunks (rows >= M / columns >= N skipped)
+__device__ __forceinline__ void epi_stage_in(uint8_t* stage, const __half* g, int ld, int m_base, int n_blk, int nchunks, int M,
+                                             int N, int lane) {
+  const int c = lane & 7;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + (lane >> 3);
+    if (c < nchunks && m_base + r < M && n_blk + c * 8 < N)
+      *epi_slot(stage, r, c) = *reinterpret_cast<const uint4*>(g + static_cast<size_t>(m_base + r) * ld + n_blk + c * 8);
+  }
+}
+__device__ __forceinline__ void epi_stage_out(const uint8_t* stage, __half* g, int ld, int m_base, int n_blk, int nchunks, int M,
+                                              int N, int lane) {
+  const int c = lane & 7;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + (lane >> 3);
+    if (c < nchunks && m_base + r < M && n_blk + c * 8 < N)
+      *reinterpret_cast<uint4*>(g + static_cast<size_t>(m_base + r) * ld + n_blk + c * 8) =
+          *epi_slot(const_cast<uint8_t*>(stage), r, c);
+  }
+}
+
+// One contiguous run of `ncols` (multiple of 16) output columns of a tile for the 32 rows of this warp:
+//   y = act(fp16((f32(acc_int) * xs) * ws + fp16(acc_outl) [+ addend])) [+ bias] [+ residual]
+// t_int / t_outl: TMEM addresses (lane quarter included) of the first int32 / fp32-outlier accumulator column of the run
+// (t_outl unused when !HAS_O); s_scale: scale_col of the run's first column, in shared memory.
+// torch.mm(activation_outliers, weight_cache.T) returns fp16 (linear.py:248): the fp32 tensor-core sum is rounded to fp16
+// before it joins the dequantised int part.
+template <bool HAS_O>
+__device__ __forceinline__ void epilogue_run_coalesced(const LinearParams& p, uint8_t* stage, uint32_t t_int, uint32_t t_outl,
+                                                       int m_base, int n0, int ncols, float xs, const __half* s_scale,
+                                                       int lane) {
+  const bool has_add = p.outl != nullptr;
+  const bool has_bias = p.bias != nullptr;
+  const bool has_res = p.residual != nullptr;
+  const bool silu = p.act == 1;
+  const int row = m_base + lane;
+  const bool row_ok = row < p.M;
+#pragma unroll 1
+  for (int b = 0; b < ncols; b += 64) {
+    const int bc = (ncols - b < 64) ? (ncols - b) : 64;
+    if (has_add) {
+      epi_stage_in(stage, p.outl, p.ld_outl, m_base, n0 + b, bc >> 3, p.M, p.N, lane);
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int c = 0; c < bc; c += 16) {
+      uint32_t acc[16];
+      uint32_t oacc[16];
+      tmem_ld_32x16(t_int + b + c, acc);
+      if (HAS_O) tmem_ld_32x16(t_outl + b + c, oacc);
+      tmem_ld_wait();
+      const int n = n0 + b + c;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int ng = n + g * 8;
+        const bool ok = row_ok && ng < p.N;
+        const uint4 wsu = *reinterpret_cast<const uint4*>(s_scale + b + c + g * 8);
+        uint4 olu = make_uint4(0, 0, 0, 0), bsu = make_uint4(0, 0, 0, 0), rsu = make_uint4(0, 0, 0, 0);
+        if (has_add) olu = *epi_slot(stage, lane, (c >> 3) + g);
+        if (has_bias && ng < p.N) bsu = __ldg(reinterpret_cast<const uint4*>(p.bias + ng));
+        if (has_res && ok) rsu = *reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(row) * p.ld_res + ng);
+        const uint32_t wsw[4] = {wsu.x, wsu.y, wsu.z, wsu.w};
+        const uint32_t olw[4] = {olu.x, olu.y, olu.z, olu.w};
+        const uint32_t bsw[4] = {bsu.x, bsu.y, bsu.z, bsu.w};
+        const uint32_t rsw[4] = {rsu.x, rsu.y, rsu.z, rsu.w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int j2 = 0; j2 < 4; ++j2) {
+          const float2 wf = __half22float2(*reinterpret_cast<const __half2*>(&wsw[j2]));
+          const float2 of = __half22float2(*reinterpret_cast<const __half2*>(&olw[j2]));
+          float v[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int cc = g * 8 + j2 * 2 + h;
+            float t = __fmul_rn(__fmul_rn(static_cast<float>(static_cast<int32_t>(acc[cc])), xs), h ? wf.y : wf.x);
+            if (HAS_O) t = __fadd_rn(t, __half2float(__float2half_rn(__uint_as_float(oacc[cc]))));
+            if (has_add) t = __fadd_rn(t, h ? of.y : of.x);
+            if (silu) t = silu_f(t);
+            v[h] = t;
+          }
+          __half2 o2 = __floats2half2_rn(v[0], v[1]);
+          if (has_bias) o2 = hadd2_via_f32(o2, *reinterpret_cast<const __half2*>(&bsw[j2]));
+          if (has_res) o2 = hadd2_via_f32(o2, *reinterpret_cast<const __half2*>(&rsw[j2]));
+          ow[j2] = *reinterpret_cast<const uint32_t*>(&o2);
+        }
+        *epi_slot(stage, lane, (c >> 3) + g) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      }
+    }
+    __syncwarp();
+    epi_stage_out(stage, p.y, p.N, m_base, n0 + b, bc >> 3, p.M, p.N, lane);
+    __syncwarp();
   }
 }
 

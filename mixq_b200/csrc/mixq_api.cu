@@ -1,6 +1,7 @@
 // extern "C" surface of libmixq_sm100 (see include/mixq.h).  Host-side only: argument checks,
 // TMA tensor-map encoding, launch configuration.  No allocation, no synchronisation.
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -147,33 +148,35 @@ int launch_linear2(const LinearParams& p, int grid, bool cooperative, cudaStream
   return 0;
 }
 
-// Tile width of the 2-CTA kernel: the multiple of 32 that minimises max(tensor time, L2 -> SM time) + exposed epilogue.
-int pick_bn2(int requested, int M, int N, int K, int n_out, int npairs) {
-  if (requested >= 32 && requested <= 256 && requested % 32 == 0) return requested;
+// Tile width of the 2-CTA kernel.  The widest strip that still gives every pair one tile: the `npairs / MP` pairs that
+// share a 256-row block split the N columns evenly; if that is more than one TMEM-full (512 columns) they take several
+// tiles each.  Wide tiles minimise the bytes each SM must land per MMA cycle (8192/W + 32).
+int pick_w2(int requested, int M, int N, int n_out, int npairs) {
   const int forced = g_tile_n.load(std::memory_order_relaxed);
-  if (forced >= 32 && forced <= 256 && forced % 32 == 0) return forced;
-  const int mp = (M + 255) / 256;
-  const double nk = (K + 127) / 128 + (n_out + 63) / 64;
-  double best = 1e30;
-  int best_bn = 128;
-  for (int bn = 64; bn <= 256; bn += 32) {
-    const int nt = (N + bn - 1) / bn;
-    const int tiles = mp * nt;
-    const int rounds = (tiles + npairs - 1) / npairs;
-    const double t_mma_tile = nk * 4.0 * (bn / 2.0) / 1.9e3 + 0.5;          // us: bn/2 cycles per K=32 step, + pipeline fill
-    const double tile_bytes = (256.0 + bn) * K;                            // activations + weights one pair pulls per tile
-    double t = 0;
-    for (int r = 0; r < rounds; ++r) {
-      const int active = (tiles - r * npairs) < npairs ? (tiles - r * npairs) : npairs;
-      const double t_l2 = active * tile_bytes / 10e6;                      // us at ~10 TB/s aggregate L2 -> SM
-      t += t_mma_tile > t_l2 ? t_mma_tile : t_l2;
-    }
-    const int slots = (512 - (n_out > 0 ? bn : 0)) / bn;
-    const double t_epi_tile = bn * 0.008;                                  // us per tile epilogue
-    t += t_epi_tile * (rounds > slots ? 1 + (rounds - slots) : 1);         // exposed epilogues
-    if (t < best) { best = t; best_bn = bn; }
+  int fixed = 0;
+  if (requested >= 32 && requested <= 512 && requested % 32 == 0) fixed = requested;
+  else if (forced >= 32 && forced <= 512 && forced % 32 == 0) fixed = forced;
+  if (fixed) {
+    const int nko_f = (n_out + 63) / 64;
+    if (nko_f > 2 && fixed > 256) fixed = 256;
+    if (nko_f > 0 && fixed > 448) fixed = 448;
+    return fixed;
   }
-  return best_bn;
+  const int mp = (M + 255) / 256;
+  int strips = npairs / mp;
+  if (strips < 1) strips = 1;
+  int w = ((N + strips - 1) / strips + 31) / 32 * 32;
+  if (w > 512) {
+    const int t = (w + 511) / 512;
+    w = ((N + strips * t - 1) / (strips * t) + 31) / 32 * 32;
+  }
+  if (w < 128) w = 128;   // an MMA of N <= 128 costs the same 75 cycles (tools/mma_bw.cu): narrower tiles only add traffic
+  // outlier k-blocks stay resident in their stages while the epilogue passes run: at most 2 of them, else the whole
+  // fp32 outlier accumulator must fit beside the int32 one (W <= 256, a single pass, blocks stream normally)
+  const int nko = (n_out + 63) / 64;
+  if (nko > 2 && w > 256) w = 256;
+  if (nko > 0 && w > 448) w = 448;
+  return w;
 }
 
 int pick_tile_n(int requested, int M, int N, int sms, bool tmem_outliers) {
@@ -230,9 +233,19 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
     return fail(MIXQ_EINVAL, "outlier buffers need ld % 8 == 0 and ld >= n_ind");
   const bool w4 = (c.bit == 4);
   // M > 128: CTA pairs (cta_group::2) own 256 x bn tiles — half the L2 -> SM bytes per MMA cycle (mixq_gemm2.cu)
-  const bool two_cta = !w4 && c.M > 128 && di.sms >= 2;
+  bool two_cta = !w4 && c.M > 128 && di.sms >= 2;
   const int npairs = di.sms / 2;
-  const int bn = two_cta ? pick_bn2(c.tile_n, c.M, c.N, c.K, c.n_out, npairs) : pick_tile_n(c.tile_n, c.M, c.N, di.sms, c.n_out > 0);
+  int bn = two_cta ? pick_w2(c.tile_n, c.M, c.N, c.n_out, npairs) : pick_tile_n(c.tile_n, c.M, c.N, di.sms, c.n_out > 0);
+  int stage2 = Gemm2Cfg::A_BYTES + (bn / 2) * 128;
+  if (const char* e = getenv("MIXQ_DEBUG_STAGE_BYTES")) { const int v = atoi(e); if (v >= stage2 && v % 1024 == 0) stage2 = v; }
+  int nstages2 = Gemm2Cfg::PIPE_BYTES / stage2;
+  if (nstages2 > Gemm2Cfg::MAX_STAGES) nstages2 = Gemm2Cfg::MAX_STAGES;
+  if (const char* e = getenv("MIXQ_DEBUG_STAGES")) { const int v = atoi(e); if (v >= 2 && v < nstages2) nstages2 = v; }
+  // the outlier k-blocks of a tile stay resident in the ring during the epilogue passes: they must all fit
+  if (two_cta && (c.n_out + 63) / 64 > nstages2 - 1) {
+    two_cta = false;
+    bn = pick_tile_n(c.tile_n, c.M, c.N, di.sms, c.n_out > 0);
+  }
   const int b_rows = two_cta ? bn / 2 : bn;
 
   LinearParams p{};
@@ -268,7 +281,7 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
                             : (bn == 256 ? GemmCfg<256, false>::STAGES : GemmCfg<128, false>::STAGES);
       if (two_cta) {
         if (int r = pick_row_groups(&p.rq, npairs * 2, Gemm2Cfg::NUM_THREADS / 32,
-                                    static_cast<long long>(Gemm2Cfg::STAGE_BYTES) * (Gemm2Cfg::STAGES - 1)))
+                                    static_cast<long long>(stage2) * (nstages2 - 1)))
           return r;
       } else if (int r = pick_row_groups(&p.rq, di.sms, w4 ? 12 : 8, stage * (stages - 1))) {
         return r;
@@ -295,6 +308,8 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
   p.trace = g_trace.load(std::memory_order_relaxed);
 
   p.bn = bn;
+  p.nstages = nstages2;
+  p.stage_bytes = stage2;
   p.q_w = static_cast<const uint8_t*>(c.q_w);
   p.q_w_pitch = w4 ? c.K / 2 : c.K;
   if (two_cta) {
@@ -408,8 +423,8 @@ const char* mixq_last_error(void) { return g_err.c_str(); }
 int mixq_version(void) { return 100; }
 unsigned long long mixq_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 int mixq_set_tile_n(int tile_n) {
-  if (tile_n != 0 && (tile_n < 32 || tile_n > 256 || tile_n % 32 != 0))
-    return fail(MIXQ_EINVAL, "tile_n must be 0 or a multiple of 32 up to 256 (the 1-CTA kernel honours 128 and 256 only)");
+  if (tile_n != 0 && (tile_n < 32 || tile_n > 512 || tile_n % 32 != 0))
+    return fail(MIXQ_EINVAL, "tile_n must be 0 or a multiple of 32 up to 512 (the 1-CTA kernel honours 128 and 256 only)");
   g_tile_n.store(tile_n, std::memory_order_relaxed);
   return 0;
 }

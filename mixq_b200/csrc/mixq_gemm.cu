@@ -140,44 +140,46 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
   // Two producer threads (one TMA op costs its issuing thread ~300 cycles: tools/tma_bw.cu): warp 3 streams the weights
   // and arms the stage barrier, warp 0 streams the activations.
   if (warp == 0 || warp == 3) {
-    if (lane == 0) {
-      const bool wgt = warp == 3;
-      fence_proxy_async_all();
-      int it = 0, s = 0;
-      uint32_t ph = 0;
-      for (int i = 0; i < my_tiles; ++i) {
-        const int tile = blockIdx.x + i * gridDim.x;
-        for (int kb = 0; kb < nkt; ++kb, ++it) {
-          if (it >= n_pre) mbar_wait(&bar_empty[s], ph ^ 1, 1, s);
+    const bool wgt = warp == 3;
+    fence_proxy_async_all();
+    int it = 0, s = 0;
+    uint32_t ph = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int tile = blockIdx.x + i * gridDim.x;
+      for (int kb = 0; kb < nkt; ++kb, ++it) {
+        if (it >= n_pre) mbar_wait(&bar_empty[s], ph ^ 1, 1, s);
+        if (elect_one()) {
           if (wgt) {
             if (it >= n_pre) produce(tile, kb, s, false, true, true);
           } else {
             produce(tile, kb, s, true, false, false);
           }
-          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_i8 = make_idesc_i8(BM, BN);
-      constexpr uint32_t idesc_f16 = make_idesc_f16(BM, BN);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int i = 0; i < my_tiles; ++i) {
-        const int as = i % nacc;
-        const uint32_t aph = (i / nacc) & 1;
-        mbar_wait(&bar_tempty[as], aph ^ 1, 2, as);
+    // warp-uniform loop, one elected lane issues (see elect_one in ptx.cuh)
+    constexpr uint32_t idesc_i8 = make_idesc_i8(BM, BN);
+    constexpr uint32_t idesc_f16 = make_idesc_f16(BM, BN);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int as = i % nacc;
+      const uint32_t aph = (i / nacc) & 1;
+      mbar_wait(&bar_tempty[as], aph ^ 1, 2, as);
+      tc_fence_after();
+      const uint32_t d_int = tmem_base + as * acc_cols;
+      const uint32_t d_out = d_int + BN;
+      for (int kb = 0; kb < nkt; ++kb) {
+        if (W4) mbar_wait(&bar_ready[s], ph, 3, s);
+        mbar_wait(&bar_full[s], ph, 4, s);
         tc_fence_after();
-        const uint32_t d_int = tmem_base + as * acc_cols;
-        const uint32_t d_out = d_int + BN;
-        for (int kb = 0; kb < nkt; ++kb) {
-          if (W4) mbar_wait(&bar_ready[s], ph, 3, s);
-          mbar_wait(&bar_full[s], ph, 4, s);
-          tc_fence_after();
+        const uint64_t da = make_sw128_kmajor_desc(smem_u32(stage_a(s)));
+        const uint64_t db = make_sw128_kmajor_desc(smem_u32(stage_b(s)));
+        if (elect_one()) {
           if (trace && i == 0 && kb == 0) trace[3] = globaltimer_ns();
-          const uint64_t da = make_sw128_kmajor_desc(smem_u32(stage_a(s)));
-          const uint64_t db = make_sw128_kmajor_desc(smem_u32(stage_b(s)));
           if (kb < nk) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)   // 4 x (K = 32 int8 = 32 B); +2 in the >>4-encoded start address
@@ -190,12 +192,14 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
               umma_f16(d_out, da + 2 * k, db + 2 * k, idesc_f16, (kbo | k) != 0);
           }
           umma_commit(&bar_empty[s]);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&bar_tfull[as]);
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
-      if (trace) trace[4] = globaltimer_ns();
+      if (elect_one()) umma_commit(&bar_tfull[as]);
+      __syncwarp();
     }
+    if (trace && lane == 0) trace[4] = globaltimer_ns();
   } else if (warp >= 4 && warp < 8) {
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     for (int i = 0; i < my_tiles; ++i) {
@@ -209,13 +213,13 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
       float xs = 0.f;
       if (p.epilogue == EPI_DEQUANT_F16 && row_ok) xs = __half2float(p.x_scale[row]);
 
-      mbar_wait(&bar_tfull[as], aph, 5, as);
+      mbar_wait_warp(&bar_tfull[as], aph, 5, as);
       tc_fence_after();
       const uint32_t t_int = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * acc_cols;
       const uint32_t t_out = t_int + BN;
 
-      if (nko > 0) epilogue_span<true>(p, t_int, t_out, row, row_ok, n0, BN, xs);
-      else epilogue_span<false>(p, t_int, 0u, row, row_ok, n0, BN, xs);
+      if (nko > 0) epilogue_span<true>(p, t_int, t_out, row, row_ok, n0, BN, xs, p.outl, p.ld_outl);
+      else epilogue_span<false>(p, t_int, 0u, row, row_ok, n0, BN, xs, p.outl, p.ld_outl);
       tc_fence_before();
       mbar_arrive(&bar_tempty[as]);
     }

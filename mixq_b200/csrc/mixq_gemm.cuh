@@ -28,7 +28,9 @@ struct LinearParams {
   int epilogue;
   int fused_prologue;
   uint32_t* grid_sync;
-  int bn;              // 2-CTA kernel: run-time tile width (multiple of 32, <= 256)
+  int bn;              // 2-CTA kernel: run-time tile width W (multiple of 32, <= 512)
+  int nstages;         // 2-CTA kernel: pipeline stages that fit PIPE_BYTES at this W
+  int stage_bytes;     // 2-CTA kernel: bytes between consecutive stages (>= 16 KB + W/2 * 128, multiple of 1024)
   const uint8_t* q_w;  // raw weight pointer + row pitch in bytes (L2 prefetch of the weight stream)
   long long q_w_pitch;
   unsigned long long* trace;  // optional [gridDim.x * 8] globaltimer stamps (mixq_set_trace_buffer), debug/tuning only
@@ -50,15 +52,16 @@ struct GemmCfg {
 template <int BN, bool W4>
 __global__ void mixq_linear_kernel(const __grid_constant__ LinearParams p);
 
-// 2-CTA (cta_group::2) kernel: a CTA pair owns a 256 x bn tile; each CTA stages 128 activation rows + bn/2 weight rows.
+// 2-CTA (cta_group::2) kernel: a CTA pair owns a 256 x W tile (W <= 512); each CTA stages 128 activation rows + W/2 weight
+// rows per k-block; the number of pipeline stages follows from W (8 at W = 128 ... 4 at W = 512).
 struct Gemm2Cfg {
   static constexpr int A_BYTES = 128 * 128;                  // 16 KB
-  static constexpr int B_BYTES = 128 * 128;                  // up to bn/2 = 128 weight rows
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = 6;
+  static constexpr int PIPE_BYTES = 192 * 1024;              // all stages together
+  static constexpr int MAX_STAGES = 8;
   static constexpr int EPI_WARPS = 8;
-  static constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;   // TMA, MMA, TMEM-alloc, spare + epilogue warps
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 512 /*RowQuantSmem*/;
+  static constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;   // TMA x2, MMA, TMEM-alloc + epilogue warps
+  static constexpr int SMEM_BYTES = PIPE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 512 /*RowQuantSmem*/ +
+                                    EPI_WARPS * 32 * 128 /*epilogue staging*/ + 1024 /*scale_col of the tile*/;
 };
 __global__ void mixq_linear2_kernel(const __grid_constant__ LinearParams p);
 

@@ -1,18 +1,27 @@
-// The MixLinear hot-path kernel, 2-CTA form (tcgen05 cta_group::2) — used for M > 128.
+// The MixLinear hot-path kernel, 2-CTA "strip" form (tcgen05 cta_group::2) — used for M > 128.
 //
-// Why: at M = 512 the 1-CTA kernel (mixq_gemm.cu, 128 x BN tiles) is bound by L2 -> SM traffic, not by the tensor pipe
-// or HBM: every 128-row tile re-reads its weight tile and every BN-column tile re-reads the activations
-// (ncu: l1tex__m_xbar2l1tex_read_bytes = 6x the algorithmic bytes, tensor pipe 21-27 % active).  A CTA PAIR owns a
-// 256 x BN output tile: each CTA stages its own 128 activation rows and only HALF of the BN weight rows, one
-// tcgen05.mma.cta_group::2 (issued by the pair's leader) reads both halves — half the L2 bytes per MMA cycle.
-// BN is a run-time multiple of 32 (<= 256) chosen on the host so that the tile count fills the 74 pairs evenly.
+// What bounds this GEMM on B200 (tools/tma_bw.cu, tools/mma_bw.cu, profiles/): the int8 tensor pipe does 8192 MAC/clk/SM,
+// but one SM cannot LAND more than ~55-70 B/clk through TMA (about 200 KB of smem in flight against >1 us of latency),
+// and at M = 512 there are only a couple of tiles per SM, so pipeline fill, drain and wave quantisation are first-order.
+// Hence:
+//   * a CTA PAIR owns a 256 x W output tile (one tcgen05.mma.cta_group::2 reads the weight halves staged by both CTAs):
+//     bytes landing per MMA cycle = 8192/W + 32 per SM, so W is made as wide as the problem allows — up to 512, i.e. the
+//     WHOLE of TMEM for one int32 accumulator, issued as two MMA column chunks per k-step;
+//   * W is chosen on the host so that every pair gets ONE tile when possible (no second, half-empty wave);
+//   * the int32 accumulator takes W TMEM columns, the fp32 accumulator of the skinny fp16 outlier GEMM only what is left
+//     (R = 512 - W): the outlier k-blocks come LAST in the tile, stay resident in their pipeline stages, and the MMA
+//     warp re-issues the (tiny) outlier MMAs for R columns at a time while the epilogue warps drain the tile pass by
+//     pass.  Nothing leaves the chip, and the reference's rounding (torch.mm -> fp16, linear.py:248) is kept.
 //
-//   warp 0 / 3  TMA producers: activations / weights (both CTAs; loads land in the local smem, complete_tx on the
-//               LEADER's mbarrier)
+//   warp 0 / 3  TMA producers: activations / weights (both CTAs; loads land locally, complete_tx on the LEADER's mbarrier)
 //   warp 1      MMA issuer   (leader CTA only; tcgen05.commit multicast frees the stage in both CTAs)
 //   warp 2      TMEM allocator (cta_group::2, 512 columns in each CTA)
 //   warps 4-11  epilogue     (2 warps per TMEM lane quarter, one half of the tile's columns each)
 // Phase A (activation prologue, rowquant.cuh) and the grid barrier are the same as in the 1-CTA kernel.
+//
+// Column bookkeeping: CTA r of the pair stages weight rows [n0 + r*W/2, +W/2).  MMA chunk c (N_c columns, using rows
+// [o_c, o_c + N_c/2) of each CTA's half) therefore produces accumulator columns [0, N_c/2) = output columns
+// n0 + o_c + j and [N_c/2, N_c) = n0 + W/2 + o_c + j: epilogue warp-half h walks output columns [n0 + h*W/2, +W/2).
 //
 // Reference behaviour this replaces: mixlib.int8FusedDequantize[Silu] and the torch.mm outlier GEMM in
 // /root/reference/mixquant/modules/linear.py:244-283, :329-351.
@@ -23,18 +32,15 @@ namespace mixq {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg::NUM_THREADS, 1)
 mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
   using Cfg = Gemm2Cfg;
-  constexpr int STAGES = Cfg::STAGES;
+  constexpr int MAXS = Cfg::MAX_STAGES;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);   // used in the leader only
-  uint64_t* bar_empty = bar_full + STAGES;                                              // per CTA (multicast commit)
-  uint64_t* bar_tfull = bar_empty + STAGES;                                             // per CTA (multicast commit)
-  uint64_t* bar_tempty = bar_tfull + 4;                                                 // used in the leader only
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 4);
-
-  auto stage_a = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
-  auto stage_b = [&](int s) { return smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + Cfg::PIPE_BYTES);    // used in the leader only
+  uint64_t* bar_empty = bar_full + MAXS;                                       // per CTA (multicast commit)
+  uint64_t* bar_tfull = bar_empty + MAXS;                                      // [0]: one phase per epilogue pass; per CTA
+  uint64_t* bar_tempty = bar_tfull + 2;                                        // [0]: pass consumed by both CTAs' epilogues; leader
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -43,20 +49,27 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
   const int pair = blockIdx.x >> 1;
   const int npairs = gridDim.x >> 1;
 
-  const int bn = p.bn;                               // tile width, multiple of 32
-  const int bh = bn >> 1;                            // weight rows staged by each CTA
+  const int W = p.bn;                                // tile width, multiple of 32, <= 512
+  const int bh = W >> 1;                             // weight rows staged by each CTA
+  const int n1 = (W <= 256) ? W : (((W >> 1) + 31) & ~31);   // MMA column chunks
+  const int n2 = W - n1;
+  const int stage_bytes = p.stage_bytes;
+  const int nstages = p.nstages;
   const int nk = (p.K + 127) / 128;                  // int8 k-blocks of 128
-  const int nko = (p.n_out + 63) / 64;               // fp16 outlier k-blocks of 64
+  const int nko = (p.n_out + 63) / 64;               // fp16 outlier k-blocks of 64 — the LAST items of a tile
   const int nkt = nk + nko;
   const int MP = (p.M + 255) / 256;
-  const int NT = (p.N + bn - 1) / bn;
+  const int NT = (p.N + W - 1) / W;
   const int ntiles = MP * NT;
   const bool has_o = nko > 0;
-  // int32 accumulator slots in a ring (a tile's epilogue overlaps the next tiles' MMAs); the fp32 outlier slot is single
-  int nint = (512 - (has_o ? bn : 0)) / bn;
-  if (nint > 4) nint = 4;
-  const uint32_t col_outl = static_cast<uint32_t>(nint * bn);
-  const uint32_t stage_tx = 2u * (Cfg::A_BYTES + static_cast<uint32_t>(bh) * 128u);   // both CTAs' bytes land on one barrier
+  const uint32_t stage_tx = 2u * static_cast<uint32_t>(Cfg::A_BYTES + bh * 128);   // both CTAs' bytes land on one barrier
+  // outlier passes: R accumulator columns at a time (R = W when everything fits next to the int32 accumulator)
+  const int r_max = has_o ? ((512 - W) < W ? ((512 - W) & ~31) : W) : W;
+  const int P = (W + r_max - 1) / r_max;
+  const int R = ((W + P - 1) / P + 31) & ~31;          // balanced passes (352 -> 128 + 128 + 96, not 160 + 160 + 32)
+
+  auto stage_a = [&](int s) { return smem + static_cast<size_t>(s) * stage_bytes; };
+  auto stage_b = [&](int s) { return smem + static_cast<size_t>(s) * stage_bytes + Cfg::A_BYTES; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tm_a);
@@ -67,11 +80,11 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
     }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < MAXS; ++s) {
       mbar_init(&bar_full[s], 1);
       mbar_init(&bar_empty[s], 1);
     }
-    for (int s = 0; s < 4; ++s) {
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&bar_tfull[s], 1);
       mbar_init(&bar_tempty[s], 2 * Cfg::EPI_WARPS);   // one arrival per epilogue warp of both CTAs
     }
@@ -90,14 +103,16 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
   if (trace && threadIdx.x == 0) trace[0] = globaltimer_ns();
 
   // ------------------------------------------------------------------ producer helper
+  // k-block order within a tile: the nk int8 blocks, then the nko outlier blocks.
   auto produce = [&](int tile, int kb, int s, bool do_act, bool do_wgt, bool arm) {
     const int m0 = (tile % MP) * 256 + static_cast<int>(rank) * 128;
-    const int n0 = (tile / MP) * bn + static_cast<int>(rank) * bh;
+    const int n0 = (tile / MP) * W + static_cast<int>(rank) * bh;
     const uint32_t full_leader = mapa_u32(smem_u32(&bar_full[s]), 0);
     if (arm && leader) mbar_arrive_expect_tx(&bar_full[s], stage_tx);
     if (kb < nk) {
-      if (do_wgt) tma_load_2d_2cta(&p.tm_b, full_leader, stage_b(s), kb * 128, n0, kEvictFirst);
-      if (do_act) tma_load_2d_2cta(&p.tm_a, full_leader, stage_a(s), kb * 128, m0, kEvictLast);
+      const int k0 = kb * 128;
+      if (do_wgt) tma_load_2d_2cta(&p.tm_b, full_leader, stage_b(s), k0, n0, kEvictFirst);
+      if (do_act) tma_load_2d_2cta(&p.tm_a, full_leader, stage_a(s), k0, m0, kEvictLast);
     } else {
       const int ko = (kb - nk) * 64;
       if (do_wgt) tma_load_2d_2cta(&p.tm_ob, full_leader, stage_b(s), ko, n0, kEvictFirst);
@@ -108,15 +123,15 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
   const int my_tiles = (pair < ntiles) ? (ntiles - 1 - pair) / npairs + 1 : 0;
   const int my_items = my_tiles * nkt;
   const int row_stages = p.fused_prologue
-                             ? static_cast<int>((static_cast<size_t>(p.rq.ngroups) * p.rq.K * 2 + Cfg::STAGE_BYTES - 1) / Cfg::STAGE_BYTES)
+                             ? static_cast<int>((static_cast<size_t>(p.rq.ngroups) * p.rq.K * 2 + stage_bytes - 1) / stage_bytes)
                              : 0;
-  const int free_stages = STAGES - row_stages;
+  const int free_stages = nstages - row_stages;
   const int n_pre = (p.fused_prologue && my_items > 0) ? (my_items < free_stages ? my_items : free_stages) : 0;
 
   // ------------------------------------------------------------------ phase A (fused prologue)
   if (p.fused_prologue) {
-    RowQuantSmem* rq_sm = reinterpret_cast<RowQuantSmem*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
-    uint8_t* rowbuf = smem + static_cast<size_t>(free_stages) * Cfg::STAGE_BYTES;
+    RowQuantSmem* rq_sm = reinterpret_cast<RowQuantSmem*>(smem + Cfg::PIPE_BYTES + 256);
+    uint8_t* rowbuf = smem + static_cast<size_t>(free_stages) * stage_bytes;
     rowquant_begin(p.rq, rq_sm, rowbuf);      // activation rows first: they are on the critical path
     if (warp == 3 && lane == 0) {
       for (int it = 0; it < n_pre; ++it) {
@@ -134,96 +149,162 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
 
   // ------------------------------------------------------------------ roles
   // Two producer threads: one TMA op costs its issuing thread ~300 cycles (tools/tma_bw.cu: 54 B/clk/SM with one issuer,
-  // 71 with two), and a pair tile needs up to 64 B/clk/SM.  (Tried and dropped: pulling the weight boxes into L2 ahead of
-  // the loads — cp.async.bulk.prefetch.tensor costs a TMA issue slot per box and made the loop 15 % slower; a spare warp
-  // issuing prefetch.global.L2 changed nothing: the loop is bound by bytes landing per SM, not by DRAM latency.)  Warp 3 streams the weights (and arms the stage barrier),
-  // warp 0 the activations.
+  // 71 with two).  Warp 3 streams the weights (and arms the stage barrier), warp 0 the activations.
+  // (Tried and dropped: pulling the weight boxes into L2 ahead of the loads — cp.async.bulk.prefetch.tensor costs a TMA
+  // issue slot per box and made the loop 15 % slower; a spare warp issuing prefetch.global.L2 changed nothing.)
   if (warp == 0 || warp == 3) {
-    if (lane == 0) {
-      const bool wgt = warp == 3;
-      fence_proxy_async_all();
-      int it = 0, s = 0;
-      uint32_t ph = 0;
-      for (int i = 0; i < my_tiles; ++i) {
-        const int tile = pair + i * npairs;
-        for (int kb = 0; kb < nkt; ++kb, ++it) {
-          if (it >= n_pre) mbar_wait(&bar_empty[s], ph ^ 1, 1, s);
+    const bool wgt = warp == 3;
+    fence_proxy_async_all();
+    int it = 0, s = 0;
+    uint32_t ph = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int tile = pair + i * npairs;
+      for (int kb = 0; kb < nkt; ++kb, ++it) {
+        if (it >= n_pre) mbar_wait(&bar_empty[s], ph ^ 1, 1, s);
+        if (elect_one()) {
           if (wgt) {
             if (it >= n_pre) produce(tile, kb, s, false, true, true);
           } else {
             produce(tile, kb, s, true, false, false);
           }
-          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
+        __syncwarp();
+        if (++s == nstages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (leader && lane == 0) {
-      const uint32_t idesc_i8 = make_idesc_i8_rt(256, bn);
-      const uint32_t idesc_f16 = make_idesc_f16_rt(256, bn);
+    if (leader) {
+      const uint32_t idesc_i8_1 = make_idesc_i8_rt(256, n1), idesc_i8_2 = make_idesc_i8_rt(256, n2 > 0 ? n2 : 32);
+      const uint32_t d1 = tmem_base, d2 = tmem_base + static_cast<uint32_t>(n1);
+      const uint32_t d_outl = tmem_base + static_cast<uint32_t>(W);
+      const uint64_t b2_off = static_cast<uint64_t>((n1 >> 1) * 128) >> 4;   // chunk 2 starts n1/2 rows into the half
+      const bool two = n2 > 0;
       int s = 0;
       uint32_t ph = 0;
+      uint32_t consumed = 0;     // epilogue passes we have waited for so far (phase index of bar_tempty[0])
       for (int i = 0; i < my_tiles; ++i) {
-        const int slot = i % nint;
-        const uint32_t use = static_cast<uint32_t>(i / nint);
-        mbar_wait(&bar_tempty[slot], (use & 1) ^ 1, 2, slot);      // the epilogues of both CTAs drained this slot
-        tc_fence_after();
-        const uint32_t d_int = tmem_base + static_cast<uint32_t>(slot * bn);
-        const uint32_t d_out = tmem_base + col_outl;
-        for (int kb = 0; kb < nkt; ++kb) {
-          if (kb == nk && nint >= 2 && i > 0) {
-            // the single fp32 outlier slot is still being read by the previous tile's epilogue
-            mbar_wait(&bar_tempty[(i - 1) % nint], static_cast<uint32_t>((i - 1) / nint) & 1, 8, i);
-            tc_fence_after();
-          }
+        if (i > 0) {             // the previous tile's last pass has left TMEM (both CTAs)
+          mbar_wait(&bar_tempty[0], (consumed & 1), 2, i);
+          ++consumed;
+          tc_fence_after();
+        }
+        for (int kb = 0; kb < nk; ++kb) {
           mbar_wait(&bar_full[s], ph, 4, s);
           tc_fence_after();
-          if (trace && i == 0 && kb == 0) trace[3] = globaltimer_ns();
           const uint64_t da = make_sw128_kmajor_desc(smem_u32(stage_a(s)));
           const uint64_t db = make_sw128_kmajor_desc(smem_u32(stage_b(s)));
-          if (kb < nk) {
+          if (elect_one()) {
+            if (trace && i == 0 && kb == 0) trace[3] = globaltimer_ns();
+            const uint32_t first = (kb == 0) ? 0u : 1u;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)   // 4 x (K = 32 int8 = 32 B); +2 in the >>4-encoded start address
-              umma_i8_2cta(d_int, da + 2 * k, db + 2 * k, idesc_i8, (kb | k) != 0);
-          } else {
-            const int kbo = kb - nk;
-            int ksteps = (p.n_out - kbo * 64 + 15) / 16;
-            if (ksteps > 4) ksteps = 4;
-            for (int k = 0; k < ksteps; ++k)  // K = 16 fp16 = 32 B
-              umma_f16_2cta(d_out, da + 2 * k, db + 2 * k, idesc_f16, (kbo | k) != 0);
+            for (int k = 0; k < 4; ++k) {   // 4 x (K = 32 int8 = 32 B); +2 in the >>4-encoded start address
+              umma_i8_2cta(d1, da + 2 * k, db + 2 * k, idesc_i8_1, first | k);
+              if (two) umma_i8_2cta(d2, da + 2 * k, db + b2_off + 2 * k, idesc_i8_2, first | k);
+            }
+            umma_commit_2cta(&bar_empty[s], 0x3);
           }
-          umma_commit_2cta(&bar_empty[s], 0x3);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+          __syncwarp();
+          if (++s == nstages) { s = 0; ph ^= 1; }
         }
-        umma_commit_2cta(&bar_tfull[slot], 0x3);
+        if (trace && lane == 0 && i == 0) trace[6] = globaltimer_ns();   // int8 k-blocks of the first tile issued
+        if (!has_o) {
+          if (elect_one()) umma_commit_2cta(&bar_tfull[0], 0x3);
+          __syncwarp();
+        } else {
+          // the nko outlier k-blocks sit in the next nko stages and stay there for all P passes
+          const int s_o = s;
+          const uint32_t ph_o = ph;
+          for (int kbo = 0; kbo < nko; ++kbo) {
+            int so = s_o + kbo;
+            uint32_t pho = ph_o;
+            if (so >= nstages) { so -= nstages; pho ^= 1; }
+            mbar_wait(&bar_full[so], pho, 4, so);
+          }
+          tc_fence_after();
+          for (int c = 0; c < P; ++c) {
+            if (c > 0) {         // region R is free again: pass c-1 was consumed
+              mbar_wait(&bar_tempty[0], (consumed & 1), 8, c);
+              ++consumed;
+              tc_fence_after();
+            }
+            const int nc = (W - c * R) < R ? (W - c * R) : R;
+            const uint32_t idesc_f16 = make_idesc_f16_rt(256, nc);
+            const uint64_t bo = static_cast<uint64_t>(c * (R >> 1) * 128) >> 4;
+            if (elect_one()) {
+              for (int kbo = 0; kbo < nko; ++kbo) {
+                int so = s_o + kbo;
+                if (so >= nstages) so -= nstages;
+                const uint64_t da = make_sw128_kmajor_desc(smem_u32(stage_a(so)));
+                const uint64_t db = make_sw128_kmajor_desc(smem_u32(stage_b(so))) + bo;
+                int ksteps = (p.n_out - kbo * 64 + 15) / 16;
+                if (ksteps > 4) ksteps = 4;
+                for (int k = 0; k < ksteps; ++k)   // K = 16 fp16 = 32 B
+                  umma_f16_2cta(d_outl, da + 2 * k, db + 2 * k, idesc_f16, (kbo | k) != 0);
+              }
+              umma_commit_2cta(&bar_tfull[0], 0x3);
+              if (c == P - 1)
+                for (int kbo = 0; kbo < nko; ++kbo) {
+                  int so = s_o + kbo;
+                  if (so >= nstages) so -= nstages;
+                  umma_commit_2cta(&bar_empty[so], 0x3);
+                }
+            }
+            __syncwarp();
+          }
+          s += nko;
+          if (s >= nstages) { s -= nstages; ph ^= 1; }
+        }
       }
-      if (trace) trace[4] = globaltimer_ns();
+      if (trace && lane == 0) trace[4] = globaltimer_ns();
     }
   } else if (warp >= 4) {
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int half = (warp - 4) >> 2;       // which half of the tile's columns
+    const int half = (warp - 4) >> 2;       // which half of the tile's output columns
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint8_t* epi_stage = smem + Cfg::PIPE_BYTES + 256 + 512 + (warp - 4) * kEpiStageBytes;
+    __half* s_scale = reinterpret_cast<__half*>(smem + Cfg::PIPE_BYTES + 256 + 512 + Cfg::EPI_WARPS * kEpiStageBytes) + half * 256;
+    const uint32_t tempty = mapa_u32(smem_u32(&bar_tempty[0]), 0);
+    const int h1 = n1 >> 1;                 // output columns of this half that live in MMA chunk 1
+    uint32_t pass_idx = 0;                  // phase index of bar_tfull[0]
     for (int i = 0; i < my_tiles; ++i) {
       const int tile = pair + i * npairs;
-      const int m0 = (tile % MP) * 256 + static_cast<int>(rank) * 128;
-      const int n0 = (tile / MP) * bn;
-      const int slot = i % nint;
-      const uint32_t use = static_cast<uint32_t>(i / nint);
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int m0 = (tile % MP) * 256 + static_cast<int>(rank) * 128 + q * 32;   // first row of this warp
+      const int n0 = (tile / MP) * W + half * bh;                                 // first output column of this warp
+      const int row = m0 + lane;
       float xs = 0.f;
-      if (p.epilogue == EPI_DEQUANT_F16 && row_ok) xs = __half2float(p.x_scale[row]);
+      if (p.epilogue == EPI_DEQUANT_F16 && row < p.M) xs = __half2float(p.x_scale[row]);
+      // scale_col of this half -> smem, once per tile, by the first of the four warps that share it
+      named_bar_sync(13 + half, 128);
+      if (q == 0 && p.epilogue == EPI_DEQUANT_F16)
+        for (int j = lane * 8; j < bh; j += 256)
+          *reinterpret_cast<uint4*>(s_scale + j) =
+              (n0 + j < p.N) ? __ldg(reinterpret_cast<const uint4*>(p.scale_col + n0 + j)) : make_uint4(0, 0, 0, 0);
+      named_bar_sync(13 + half, 128);
 
-      mbar_wait(&bar_tfull[slot], use & 1, 5, slot);
-      tc_fence_after();
-      const uint32_t t_int = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(slot * bn);
-      const uint32_t t_out = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + col_outl;
-      const int span = bn >> 1;           // this warp's contiguous half of the tile's columns
-      const int c0 = half * span;
-      if (has_o) epilogue_span<true>(p, t_int + c0, t_out + c0, row, row_ok, n0 + c0, span, xs);
-      else epilogue_span<false>(p, t_int + c0, 0u, row, row_ok, n0 + c0, span, xs);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_tempty[slot]), 0));
+      for (int c = 0; c < P; ++c, ++pass_idx) {
+        mbar_wait_warp(&bar_tfull[0], pass_idx & 1, 5, c);
+        tc_fence_after();
+        const int x0 = c * (R >> 1);                                   // this pass: output columns [x0, x1) of the half
+        const int nc = (W - c * R) < R ? (W - c * R) : R;
+        const int x1 = x0 + (nc >> 1);
+        const uint32_t t_outl = lane_base + static_cast<uint32_t>(W + half * (nc >> 1));
+        // split the run where the int32 accumulator switches from MMA chunk 1 to chunk 2
+        for (int part = 0; part < 2; ++part) {
+          const int a = part == 0 ? x0 : (x0 > h1 ? x0 : h1);
+          const int b = part == 0 ? (x1 < h1 ? x1 : h1) : x1;
+          if (a >= b) continue;
+          const uint32_t t_int = lane_base + static_cast<uint32_t>(part == 0 ? half * h1 + a : n1 + half * (n2 >> 1) + (a - h1));
+          if (p.epilogue == EPI_DEQUANT_F16) {
+            if (has_o) epilogue_run_coalesced<true>(p, epi_stage, t_int, t_outl + (a - x0), m0, n0 + a, b - a, xs, s_scale + a, lane);
+            else epilogue_run_coalesced<false>(p, epi_stage, t_int, 0u, m0, n0 + a, b - a, xs, s_scale + a, lane);
+          } else {   // raw int32 accumulators (mixlib.gemm)
+            epilogue_span<false>(p, t_int, 0u, row, row < p.M, n0 + a, b - a, xs, nullptr, 0);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty);
+      }
     }
     if (trace && warp == 4 && lane == 0) trace[5] = globaltimer_ns();
   }

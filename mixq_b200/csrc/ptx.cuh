@@ -33,6 +33,20 @@ __device__ __forceinline__ uint32_t lane_id() {
   return l;
 }
 
+// One lane of a fully converged warp.  The single-thread roles (TMA issue, tcgen05.mma issue) run their loops
+// WARP-UNIFORMLY and predicate only the issuing instruction with this: inside an `if (lane == 0)` region the compiler
+// cannot keep descriptors / addresses in uniform registers and wraps every UTCIMMA / UTMALDG in an ELECT + R2UR.BROADCAST
+// loop (~120 issue cycles per MMA measured: the whole GEMM was paced by its issuing thread).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -70,6 +84,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int wh
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0xff) == 0 && globaltimer_ns() - t0 > MIXQ_SPIN_TIMEOUT_NS) spin_timeout_trap(what, tag, parity);
   }
+}
+
+// Long waits by whole warps (epilogue warps waiting for a tile): one lane polls, with back-off, so that the spinning
+// does not compete with the tensor core / TMA for the shared-memory and barrier pipes.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int what = 0, int tag = 0) {
+  if ((threadIdx.x & 31) == 0) {
+    if (!mbar_try_wait(bar, parity)) {
+      uint64_t t0 = globaltimer_ns();
+      uint32_t spins = 0;
+      while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(100);
+        if ((++spins & 0xff) == 0 && globaltimer_ns() - t0 > MIXQ_SPIN_TIMEOUT_NS) spin_timeout_trap(what, tag, parity);
+      }
+    }
+  }
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------- proxies

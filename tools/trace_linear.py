@@ -7,7 +7,7 @@ lib = _lib.load()
 M = 512
 dev = "cuda"
 g = torch.Generator(device=dev).manual_seed(0)
-trace = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
+trace = torch.zeros(4096, dtype=torch.int64, device=dev)
 TILE = int(os.environ.get('TILE', '0'))
 MODES = os.environ.get('MODES', 'plain,skip').split(',')
 SHAPES = [tuple(int(v) for v in t.split('x')) for t in os.environ.get('SHAPES', '12288x4096,4096x4096,4096x11008').split(',')]
@@ -34,11 +34,18 @@ for (N, K) in SHAPES:
             torch.cuda.synchronize()
             _lib.check(lib.mixq_linear_fused(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "fused")
             torch.cuda.synchronize()
-        t = trace.view(148, 8).cpu().double()
+        full = trace.cpu().double()
+        t = full[:148 * 8].view(148, 8)
         t0 = t[:, 0][t[:, 0] > 0].min()
         def col(i):
             v = t[:, i][t[:, i] > 0]
             return (f"{(v.min()-t0)/1e3:6.2f}..{(v.max()-t0)/1e3:6.2f}" if len(v) else "      -       ")
         print(f"N={N} K={K} tile={TILE} {mode:5s} us since first CTA start: start {col(0)} | mask built {col(6)} | row0 absmax {col(7)} | prologue done {col(1)} | barrier passed {col(2)} | "
-              f"first MMA {col(3)} | last MMA {col(4)} | epilogue done {col(5)}")
+              f"first MMA {col(3)} | int MMAs issued {col(6)} | last MMA {col(4)} | epilogue done {col(5)}")
+        if os.environ.get("CADENCE"):
+            base = t[0, 0]
+            for name, off in (("mma", 2048), ("wgt-tma", 2048 + 256), ("act-tma", 2048 + 512)):
+                v = full[off:off + 40]
+                v = v[v > 0]
+                print("   ", name, " ".join(f"{(x - base) / 1e3:.2f}" for x in v.tolist()))
 lib.mixq_set_trace_buffer(0)
