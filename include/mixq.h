@@ -130,6 +130,12 @@ typedef struct mixq_linear_args {
   const void* scale_col;   /* fp16 [N] */
   const void* bias;        /* fp16 [N] or NULL; y = fp16(y + bias) as a second rounding (linear.py:284-285) */
   int bit;                 /* 8 or 4 */
+  /* SwiGLU pair (fused/mlp.py:61-64): when q_weight_up is set, q_weight / scale_col / weight_cache are gate_proj's and
+   * these are up_proj's (same N, K, ind, ld_wc; bit 8, M > 128, no bias); y[M,N] = fp16( fp16(silu(gate)) * fp16(up) ),
+   * i.e. up_proj(x), gate_proj.forward_without_preconditionFusedSilu(x) and `gate *= up` in ONE launch. */
+  const void* q_weight_up;
+  const void* scale_col_up;
+  const void* weight_cache_up;
   /* fp16 outlier path */
   const int32_t* ind;      /* [n_ind] */
   int n_ind;

@@ -32,6 +32,9 @@ class LinearArgs(C.Structure):
         ("scale_col", C.c_void_p),
         ("bias", C.c_void_p),
         ("bit", C.c_int),
+        ("q_weight_up", C.c_void_p),
+        ("scale_col_up", C.c_void_p),
+        ("weight_cache_up", C.c_void_p),
         ("ind", C.c_void_p),
         ("n_ind", C.c_int),
         ("weight_cache", C.c_void_p),

@@ -259,3 +259,78 @@ __device__ __forceinline__ void epilogue_run_coalesced(const LinearParams& p, ui
 }
 
 }  // namespace mixq
+
+// ================================================================ SwiGLU pair epilogue (2-CTA kernel, pair mode)
+// In pair mode CTA 0 of the pair stages gate_proj's weight rows and CTA 1 up_proj's rows for the SAME output columns, so
+// in every CTA the accumulator's first column half is gate and the second half is up: epilogue warp (q, 0) holds gate,
+// warp (q, 1) holds up for the same 32 rows.  The reference (fused/mlp.py:61-64) does
+//     up = up_proj(x);  gate = gate_proj.forward_without_preconditionFusedSilu(x);  gate *= up        (all fp16 tensors)
+// so y = fp16( fp16(silu(v_gate)) * fp16(v_up) ).  The gate warp publishes its fp16 values through its staging tile,
+// the up warp multiplies and stores; the two warps meet at a 64-thread named barrier twice per 64-column block.
+namespace mixq {
+
+template <bool HAS_O, int ROLE>   // ROLE 0 = gate warp, 1 = up warp
+__device__ __forceinline__ void epilogue_run_swiglu(const LinearParams& p, uint8_t* my_stage, uint8_t* gate_stage, int bar_id,
+                                                    uint32_t t_int, uint32_t t_outl, int m_base, int n0, int ncols, float xs,
+                                                    const __half* s_scale, int lane) {
+#pragma unroll 1
+  for (int b = 0; b < ncols; b += 64) {
+    const int bc = (ncols - b < 64) ? (ncols - b) : 64;
+#pragma unroll 1
+    for (int c = 0; c < bc; c += 16) {
+      uint32_t acc[16];
+      uint32_t oacc[16];
+      tmem_ld_32x16(t_int + b + c, acc);
+      if (HAS_O) tmem_ld_32x16(t_outl + b + c, oacc);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const uint4 wsu = *reinterpret_cast<const uint4*>(s_scale + b + c + g * 8);
+        const uint32_t wsw[4] = {wsu.x, wsu.y, wsu.z, wsu.w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int j2 = 0; j2 < 4; ++j2) {
+          const float2 wf = __half22float2(*reinterpret_cast<const __half2*>(&wsw[j2]));
+          float v[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int cc = g * 8 + j2 * 2 + h;
+            float t = __fmul_rn(__fmul_rn(static_cast<float>(static_cast<int32_t>(acc[cc])), xs), h ? wf.y : wf.x);
+            if (HAS_O) t = __fadd_rn(t, __half2float(__float2half_rn(__uint_as_float(oacc[cc]))));
+            if (ROLE == 0) t = silu_f(t);
+            v[h] = t;
+          }
+          const __half2 o2 = __floats2half2_rn(v[0], v[1]);
+          ow[j2] = *reinterpret_cast<const uint32_t*>(&o2);
+        }
+        *epi_slot(my_stage, lane, (c >> 3) + g) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      }
+    }
+    named_bar_sync(bar_id, 64);            // gate tile published
+    if (ROLE == 1) {
+#pragma unroll 1
+      for (int ch = 0; ch < (bc >> 3); ++ch) {
+        const uint4 gu = *epi_slot(gate_stage, lane, ch);
+        uint4* mine = epi_slot(my_stage, lane, ch);
+        const uint4 uu = *mine;
+        const uint32_t gw[4] = {gu.x, gu.y, gu.z, gu.w};
+        const uint32_t uw[4] = {uu.x, uu.y, uu.z, uu.w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __half2 pr = __hmul2(*reinterpret_cast<const __half2*>(&gw[j]), *reinterpret_cast<const __half2*>(&uw[j]));
+          ow[j] = *reinterpret_cast<const uint32_t*>(&pr);
+        }
+        *mine = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      }
+    }
+    named_bar_sync(bar_id, 64);            // gate tile consumed: its warp may overwrite it
+    if (ROLE == 1) {
+      __syncwarp();
+      epi_stage_out(my_stage, p.y, p.N, m_base, n0 + b, bc >> 3, p.M, p.N, lane);
+      __syncwarp();
+    }
+  }
+}
+
+}  // namespace mixq

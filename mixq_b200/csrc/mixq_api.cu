@@ -202,6 +202,9 @@ int pick_row_groups(RowQuantArgs* a, int grid, int warps_per_cta, long long smem
 struct GemmCall {
   const void* q_x;
   const void* q_w;
+  const void* q_w_up = nullptr;        // SwiGLU pair
+  const void* scale_col_up = nullptr;
+  const void* weight_cache_up = nullptr;
   int bit;
   const void* x_scale;
   const void* scale_col;
@@ -235,7 +238,12 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
   // M > 128: CTA pairs (cta_group::2) own 256 x bn tiles — half the L2 -> SM bytes per MMA cycle (mixq_gemm2.cu)
   bool two_cta = !w4 && c.M > 128 && di.sms >= 2;
   const int npairs = di.sms / 2;
-  int bn = two_cta ? pick_w2(c.tile_n, c.M, c.N, c.n_out, npairs) : pick_tile_n(c.tile_n, c.M, c.N, di.sms, c.n_out > 0);
+  const bool pair = c.q_w_up != nullptr;
+  if (pair && (!two_cta || c.bias != nullptr || !c.scale_col_up || (c.n_out > 0 && !c.weight_cache_up) || c.epilogue != EPI_DEQUANT_F16 ||
+               c.outl != nullptr || c.residual != nullptr || c.N % 16 != 0))
+    return fail(MIXQ_EINVAL, "SwiGLU pair needs bit 8, M > 128, N % 16 == 0, both scale/weight_cache sets, no bias/residual/addend");
+  // pair: a tile of width W holds W/2 gate columns (staged by CTA 0) and the SAME W/2 up columns (staged by CTA 1)
+  int bn = two_cta ? pick_w2(c.tile_n, c.M, pair ? 2 * c.N : c.N, c.n_out, npairs) : pick_tile_n(c.tile_n, c.M, c.N, di.sms, c.n_out > 0);
   int stage2 = Gemm2Cfg::A_BYTES + (bn / 2) * 128;
   if (const char* e = getenv("MIXQ_DEBUG_STAGE_BYTES")) { const int v = atoi(e); if (v >= stage2 && v % 1024 == 0) stage2 = v; }
   int nstages2 = Gemm2Cfg::PIPE_BYTES / stage2;
@@ -243,6 +251,7 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
   if (const char* e = getenv("MIXQ_DEBUG_STAGES")) { const int v = atoi(e); if (v >= 2 && v < nstages2) nstages2 = v; }
   // the outlier k-blocks of a tile stay resident in the ring during the epilogue passes: they must all fit
   if (two_cta && (c.n_out + 63) / 64 > nstages2 - 1) {
+    if (pair) return fail(MIXQ_EINVAL, "SwiGLU pair: too many outlier columns for the resident outlier stages");
     two_cta = false;
     bn = pick_tile_n(c.tile_n, c.M, c.N, di.sms, c.n_out > 0);
   }
@@ -268,6 +277,16 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
     if (int r = make_map(&p.tm_ob, c.weight_cache, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c.n_out, c.N,
                          static_cast<long long>(c.ld_wc) * 2, 64, b_rows, CU_TENSOR_MAP_SWIZZLE_128B))
       return r;
+  }
+  if (pair) {
+    if (int r = make_map(&p.tm_b2, c.q_w_up, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, c.K, c.N, c.K, 128, b_rows, CU_TENSOR_MAP_SWIZZLE_128B))
+      return r;
+    if (c.n_out > 0)
+      if (int r = make_map(&p.tm_ob2, c.weight_cache_up, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c.n_out, c.N,
+                           static_cast<long long>(c.ld_wc) * 2, 64, b_rows, CU_TENSOR_MAP_SWIZZLE_128B))
+        return r;
+    p.scale_col2 = static_cast<const __half*>(c.scale_col_up);
+    p.pair_swiglu = 1;
   }
   if (c.rq != nullptr) {
     p.rq = *c.rq;
@@ -313,7 +332,7 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
   p.q_w = static_cast<const uint8_t*>(c.q_w);
   p.q_w_pitch = w4 ? c.K / 2 : c.K;
   if (two_cta) {
-    const int tiles2 = ((c.M + 255) / 256) * ((c.N + bn - 1) / bn);
+    const int tiles2 = ((c.M + 255) / 256) * (((pair ? 2 * c.N : c.N) + bn - 1) / bn);
     const bool coop2 = p.fused_prologue != 0;
     const int grid2 = coop2 ? npairs * 2 : 2 * (tiles2 < npairs ? tiles2 : npairs);
     return launch_linear2(p, grid2, coop2, st);
@@ -589,6 +608,7 @@ int mixq_linear_fused(const mixq_linear_args* a, void* stream) {
   c.ld_wc = a->ld_wc; c.n_out = a->n_ind; c.y = a->y; c.M = a->M; c.N = a->N; c.K = a->K; c.act = a->act;
   c.epilogue = EPI_DEQUANT_F16; c.tile_n = a->tile_n;
   c.residual = a->residual; c.ld_res = a->ld_res;
+  c.q_w_up = a->q_weight_up; c.scale_col_up = a->scale_col_up; c.weight_cache_up = a->weight_cache_up;
   if (a->residual && a->ld_res < a->N) return fail(MIXQ_EINVAL, "ld_res < N");
   c.rq = a->skip_prologue ? nullptr : &rq;
   c.grid_sync = a->grid_sync;

@@ -12,6 +12,10 @@ struct LinearParams {
   CUtensorMap tm_b;    // q_w   int8 [N,K]      box 128 B x BN rows  (W4: uint8 [N,K/2], box 64 B x BN rows)
   CUtensorMap tm_oa;   // activation outliers fp16 [M,n_ind]  box 64 x 128
   CUtensorMap tm_ob;   // weight_cache        fp16 [N,n_ind]  box 64 x BN
+  CUtensorMap tm_b2;   // SwiGLU pair: up_proj q_w (rank 1 of the CTA pair stages these rows instead)
+  CUtensorMap tm_ob2;  // SwiGLU pair: up_proj weight_cache
+  const __half* scale_col2;   // SwiGLU pair: up_proj scale_col
+  int pair_swiglu;
   RowQuantArgs rq;     // phase A (fused prologue); rq.q_x == nullptr -> no prologue
   const __half* x_scale;
   const __half* scale_col;

@@ -59,7 +59,9 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
   const int nko = (p.n_out + 63) / 64;               // fp16 outlier k-blocks of 64 — the LAST items of a tile
   const int nkt = nk + nko;
   const int MP = (p.M + 255) / 256;
-  const int NT = (p.N + W - 1) / W;
+  const bool pairm = p.pair_swiglu != 0;             // SwiGLU pair: CTA 0 stages gate rows, CTA 1 the same up rows
+  const int wout = pairm ? bh : W;                   // output columns per tile
+  const int NT = (p.N + wout - 1) / wout;
   const int ntiles = MP * NT;
   const bool has_o = nko > 0;
   const uint32_t stage_tx = 2u * static_cast<uint32_t>(Cfg::A_BYTES + bh * 128);   // both CTAs' bytes land on one barrier
@@ -74,6 +76,7 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tm_a);
     tma_prefetch_desc(&p.tm_b);
+    if (pairm) tma_prefetch_desc(&p.tm_b2);
     if (has_o) {
       tma_prefetch_desc(&p.tm_oa);
       tma_prefetch_desc(&p.tm_ob);
@@ -106,16 +109,18 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
   // k-block order within a tile: the nk int8 blocks, then the nko outlier blocks.
   auto produce = [&](int tile, int kb, int s, bool do_act, bool do_wgt, bool arm) {
     const int m0 = (tile % MP) * 256 + static_cast<int>(rank) * 128;
-    const int n0 = (tile / MP) * W + static_cast<int>(rank) * bh;
+    const int n0 = pairm ? (tile / MP) * bh : (tile / MP) * W + static_cast<int>(rank) * bh;
+    const CUtensorMap* tmb = (pairm && rank == 1) ? &p.tm_b2 : &p.tm_b;
+    const CUtensorMap* tmob = (pairm && rank == 1) ? &p.tm_ob2 : &p.tm_ob;
     const uint32_t full_leader = mapa_u32(smem_u32(&bar_full[s]), 0);
     if (arm && leader) mbar_arrive_expect_tx(&bar_full[s], stage_tx);
     if (kb < nk) {
       const int k0 = kb * 128;
-      if (do_wgt) tma_load_2d_2cta(&p.tm_b, full_leader, stage_b(s), k0, n0, kEvictFirst);
+      if (do_wgt) tma_load_2d_2cta(tmb, full_leader, stage_b(s), k0, n0, kEvictFirst);
       if (do_act) tma_load_2d_2cta(&p.tm_a, full_leader, stage_a(s), k0, m0, kEvictLast);
     } else {
       const int ko = (kb - nk) * 64;
-      if (do_wgt) tma_load_2d_2cta(&p.tm_ob, full_leader, stage_b(s), ko, n0, kEvictFirst);
+      if (do_wgt) tma_load_2d_2cta(tmob, full_leader, stage_b(s), ko, n0, kEvictFirst);
       if (do_act) tma_load_2d_2cta(&p.tm_oa, full_leader, stage_a(s), ko, m0, kEvictLast);
     }
   };
@@ -269,7 +274,7 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
     for (int i = 0; i < my_tiles; ++i) {
       const int tile = pair + i * npairs;
       const int m0 = (tile % MP) * 256 + static_cast<int>(rank) * 128 + q * 32;   // first row of this warp
-      const int n0 = (tile / MP) * W + half * bh;                                 // first output column of this warp
+      const int n0 = pairm ? (tile / MP) * bh : (tile / MP) * W + half * bh;     // first output column of this warp
       const int row = m0 + lane;
       float xs = 0.f;
       if (p.epilogue == EPI_DEQUANT_F16 && row < p.M) xs = __half2float(p.x_scale[row]);
@@ -278,7 +283,8 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
       if (q == 0 && p.epilogue == EPI_DEQUANT_F16)
         for (int j = lane * 8; j < bh; j += 256)
           *reinterpret_cast<uint4*>(s_scale + j) =
-              (n0 + j < p.N) ? __ldg(reinterpret_cast<const uint4*>(p.scale_col + n0 + j)) : make_uint4(0, 0, 0, 0);
+              (n0 + j < p.N) ? __ldg(reinterpret_cast<const uint4*>(((pairm && half == 1) ? p.scale_col2 : p.scale_col) + n0 + j))
+                             : make_uint4(0, 0, 0, 0);
       named_bar_sync(13 + half, 128);
 
       for (int c = 0; c < P; ++c, ++pass_idx) {
@@ -294,7 +300,16 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
           const int b = part == 0 ? (x1 < h1 ? x1 : h1) : x1;
           if (a >= b) continue;
           const uint32_t t_int = lane_base + static_cast<uint32_t>(part == 0 ? half * h1 + a : n1 + half * (n2 >> 1) + (a - h1));
-          if (p.epilogue == EPI_DEQUANT_F16) {
+          if (pairm) {
+            uint8_t* gate_stage = smem + Cfg::PIPE_BYTES + 256 + 512 + q * kEpiStageBytes;   // staging tile of warp (q, half 0)
+            if (half == 0) {
+              if (has_o) epilogue_run_swiglu<true, 0>(p, epi_stage, gate_stage, 1 + q, t_int, t_outl + (a - x0), m0, n0 + a, b - a, xs, s_scale + a, lane);
+              else epilogue_run_swiglu<false, 0>(p, epi_stage, gate_stage, 1 + q, t_int, 0u, m0, n0 + a, b - a, xs, s_scale + a, lane);
+            } else {
+              if (has_o) epilogue_run_swiglu<true, 1>(p, epi_stage, gate_stage, 1 + q, t_int, t_outl + (a - x0), m0, n0 + a, b - a, xs, s_scale + a, lane);
+              else epilogue_run_swiglu<false, 1>(p, epi_stage, gate_stage, 1 + q, t_int, 0u, m0, n0 + a, b - a, xs, s_scale + a, lane);
+            }
+          } else if (p.epilogue == EPI_DEQUANT_F16) {
             if (has_o) epilogue_run_coalesced<true>(p, epi_stage, t_int, t_outl + (a - x0), m0, n0 + a, b - a, xs, s_scale + a, lane);
             else epilogue_run_coalesced<false>(p, epi_stage, t_int, 0u, m0, n0 + a, b - a, xs, s_scale + a, lane);
           } else {   // raw int32 accumulators (mixlib.gemm)

@@ -121,57 +121,63 @@ __global__ void __launch_bounds__(1024) compact_cols_kernel(uint8_t* col_over, i
 // RoPE + single-query attention for the decode harness (fused/attn.py:219-263): one warp per (token, head).
 // qkv row = [H*D | Hkv*D | Hkv*D]; the new key/value are appended at position past_len of the optional cache
 // [M, Hkv, cap, D]; out[M, H*D] = softmax(q.K^T * scale) . V.  HF rotate_half convention (pairs i, i + D/2).
-// Outside the quantised hot path (the reference calls flash-attn here); kept simple.
+// Lane l owns the D/32 consecutive dims [l*E, l*E + E) (8-byte vector accesses); its rotation partner dims live in
+// lane l ^ 16.  Outside the quantised hot path (the reference calls flash-attn here); kept simple.
 template <int D>
-__global__ void __launch_bounds__(128) rope_attn_decode_kernel(const __half* __restrict__ qkv, __half* k_cache,
+__global__ void __launch_bounds__(256) rope_attn_decode_kernel(const __half* __restrict__ qkv, __half* k_cache,
                                                                __half* v_cache, int cache_cap, int past_len,
                                                                __half* __restrict__ out, int M, int H, int Hkv,
                                                                float theta, float scale) {
-  constexpr int E = D / 32;   // elements per lane: lane owns dims lane + 32*e
+  constexpr int E = D / 32;   // 2 (D = 64) or 4 (D = 128) halves per lane
   const int lane = threadIdx.x & 31;
   const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (w >= static_cast<long long>(M) * H) return;
   const int m = static_cast<int>(w / H), h = static_cast<int>(w % H);
   const int hk = h / (H / Hkv);
   const int ld = (H + 2 * Hkv) * D;
-  const __half* qp = qkv + static_cast<size_t>(m) * ld + h * D;
-  const __half* kp = qkv + static_cast<size_t>(m) * ld + (H + hk) * D;
-  const __half* vp = qkv + static_cast<size_t>(m) * ld + (H + Hkv + hk) * D;
-  float q[E], k[E], v[E];
+  const __half* qp = qkv + static_cast<size_t>(m) * ld + h * D + lane * E;
+  const __half* kp = qkv + static_cast<size_t>(m) * ld + (H + hk) * D + lane * E;
+  const __half* vp = qkv + static_cast<size_t>(m) * ld + (H + Hkv + hk) * D + lane * E;
+  auto ldv = [](const __half* p_, float (&f)[E]) {
+    if (E == 4) {
+      const uint2 u = *reinterpret_cast<const uint2*>(p_);
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+      f[0] = a.x; f[1] = a.y; f[E - 2] = b.x; f[E - 1] = b.y;
+    } else {
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(p_));
+      f[0] = a.x; f[1] = a.y;
+    }
+  };
+  auto stv = [](__half* p_, const float (&f)[E]) {
+    if (E == 4) {
+      const __half2 a = __floats2half2_rn(f[0], f[1]), b = __floats2half2_rn(f[E - 2], f[E - 1]);
+      *reinterpret_cast<uint2*>(p_) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+    } else {
+      const __half2 a = __floats2half2_rn(f[0], f[1]);
+      *reinterpret_cast<uint32_t*>(p_) = *reinterpret_cast<const uint32_t*>(&a);
+    }
+  };
+  float q[E], k[E], v[E], qr[E], kr[E];
+  ldv(qp, q);
+  ldv(kp, k);
+  ldv(vp, v);
+  const float sgn = (lane < 16) ? -1.f : 1.f;      // dims < D/2 take -x[d + D/2], the others +x[d - D/2]
 #pragma unroll
   for (int e = 0; e < E; ++e) {
-    q[e] = __half2float(qp[lane + 32 * e]);
-    k[e] = __half2float(kp[lane + 32 * e]);
-    v[e] = __half2float(vp[lane + 32 * e]);
-  }
-  // rotate: dim d pairs with d +- D/2; with 32 lanes x E, the partner of (lane, e) is (lane, e +- E/2)
-  float qr[E], kr[E];
-#pragma unroll
-  for (int e = 0; e < E; ++e) {
-    const int d = lane + 32 * e;
-    const int i = d % (D / 2);
-    const float inv_freq = __powf(theta, -2.0f * static_cast<float>(i) / static_cast<float>(D));
-    float sn, cs;
-    sincosf(static_cast<float>(past_len) * inv_freq, &sn, &cs);
-    const int pe = (e + E / 2) % E;
-    const float sgn = (d < D / 2) ? -1.f : 1.f;
-    qr[e] = q[e] * cs + sgn * q[pe] * sn;
-    kr[e] = k[e] * cs + sgn * k[pe] * sn;
-  }
-  // round to fp16 like the reference's fp16 tensors do
-#pragma unroll
-  for (int e = 0; e < E; ++e) {
-    qr[e] = __half2float(__float2half_rn(qr[e]));
-    kr[e] = __half2float(__float2half_rn(kr[e]));
+    const float qo = __shfl_xor_sync(0xffffffffu, q[e], 16), ko = __shfl_xor_sync(0xffffffffu, k[e], 16);
+    float sn = 0.f, cs = 1.f;
+    if (past_len > 0) {
+      const int i = (lane * E + e) % (D / 2);
+      const float inv_freq = powf(theta, -2.0f * static_cast<float>(i) / static_cast<float>(D));
+      sincosf(static_cast<float>(past_len) * inv_freq, &sn, &cs);
+    }
+    // round to fp16 like the reference's fp16 tensors do
+    qr[e] = __half2float(__float2half_rn(q[e] * cs + sgn * qo * sn));
+    kr[e] = __half2float(__float2half_rn(k[e] * cs + sgn * ko * sn));
   }
   if (k_cache != nullptr && h % (H / Hkv) == 0) {
-    __half* kc = k_cache + ((static_cast<size_t>(m) * Hkv + hk) * cache_cap + past_len) * D;
-    __half* vc = v_cache + ((static_cast<size_t>(m) * Hkv + hk) * cache_cap + past_len) * D;
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-      kc[lane + 32 * e] = __float2half_rn(kr[e]);
-      vc[lane + 32 * e] = __float2half_rn(v[e]);
-    }
+    stv(k_cache + ((static_cast<size_t>(m) * Hkv + hk) * cache_cap + past_len) * D + lane * E, kr);
+    stv(v_cache + ((static_cast<size_t>(m) * Hkv + hk) * cache_cap + past_len) * D + lane * E, v);
   }
   float mx = -INFINITY, den = 0.f, acc[E];
 #pragma unroll
@@ -182,10 +188,8 @@ __global__ void __launch_bounds__(128) rope_attn_decode_kernel(const __half* __r
 #pragma unroll
       for (int e = 0; e < E; ++e) { kt[e] = kr[e]; vt[e] = v[e]; }
     } else {
-      const __half* kc = k_cache + ((static_cast<size_t>(m) * Hkv + hk) * cache_cap + t) * D;
-      const __half* vc = v_cache + ((static_cast<size_t>(m) * Hkv + hk) * cache_cap + t) * D;
-#pragma unroll
-      for (int e = 0; e < E; ++e) { kt[e] = __half2float(kc[lane + 32 * e]); vt[e] = __half2float(vc[lane + 32 * e]); }
+      ldv(k_cache + ((static_cast<size_t>(m) * Hkv + hk) * cache_cap + t) * D + lane * E, kt);
+      ldv(v_cache + ((static_cast<size_t>(m) * Hkv + hk) * cache_cap + t) * D + lane * E, vt);
     }
     float s = 0.f;
 #pragma unroll
@@ -200,19 +204,20 @@ __global__ void __launch_bounds__(128) rope_attn_decode_kernel(const __half* __r
     for (int e = 0; e < E; ++e) acc[e] = acc[e] * corr + pw * vt[e];
     mx = mn;
   }
-  __half* op = out + (static_cast<size_t>(m) * H + h) * D;
 #pragma unroll
-  for (int e = 0; e < E; ++e) op[lane + 32 * e] = __float2half_rn(acc[e] / den);
+  for (int e = 0; e < E; ++e) acc[e] = acc[e] / den;
+  stv(out + (static_cast<size_t>(m) * H + h) * D + lane * E, acc);
 }
+
 cudaError_t launch_rope_attn_decode(const __half* qkv, __half* k_cache, __half* v_cache, int cache_cap, int past_len,
                                     __half* out, int M, int H, int Hkv, int D, float theta, cudaStream_t st) {
   const long long warps = static_cast<long long>(M) * H;
-  const int grid = static_cast<int>((warps + 3) / 4);
+  const int grid = static_cast<int>((warps + 7) / 8);
   const float scale = 1.0f / sqrtf(static_cast<float>(D));
   if (D == 128)
-    rope_attn_decode_kernel<128><<<grid, 128, 0, st>>>(qkv, k_cache, v_cache, cache_cap, past_len, out, M, H, Hkv, theta, scale);
+    rope_attn_decode_kernel<128><<<grid, 256, 0, st>>>(qkv, k_cache, v_cache, cache_cap, past_len, out, M, H, Hkv, theta, scale);
   else
-    rope_attn_decode_kernel<64><<<grid, 128, 0, st>>>(qkv, k_cache, v_cache, cache_cap, past_len, out, M, H, Hkv, theta, scale);
+    rope_attn_decode_kernel<64><<<grid, 256, 0, st>>>(qkv, k_cache, v_cache, cache_cap, past_len, out, M, H, Hkv, theta, scale);
   return cudaGetLastError();
 }
 

@@ -224,7 +224,7 @@ class MixLinear_GEMM(nn.Module):
                                                   self.in_features, self.bit, self._stream()), "gather_weight_columns")
 
     def _launch(self, cache, M, y, *, x=None, skip_prologue=False, act=ACT_NONE, norm_weight=None, eps=0.0,
-                norm_out=None, residual=None, q_x=None, act_outliers=None, ld_ao=None):
+                norm_out=None, residual=None, q_x=None, act_outliers=None, ld_ao=None, up=None):
         """One mixq_linear_fused launch."""
         a = self._args
         n = self._n_ind
@@ -242,6 +242,10 @@ class MixLinear_GEMM(nn.Module):
         a.scale_col = _ptr(self.scale_col)
         a.bias = _ptr(self.bias)
         a.bit = self.bit
+        # SwiGLU pair: self is gate_proj, `up` is up_proj (same outlier set)
+        a.q_weight_up = _ptr(None if up is None else up.q_weight)
+        a.scale_col_up = _ptr(None if up is None else up.scale_col)
+        a.weight_cache_up = _ptr(None if up is None else up._wc_buf)
         a.ind = _ptr(self._ind_buf)
         a.n_ind = n
         a.weight_cache = _ptr(self._wc_buf)
@@ -377,6 +381,33 @@ class MixLinear_GEMM(nn.Module):
         y = torch.empty((M, self.out_features), dtype=torch.float16, device=inputs.device)
         self._launch(cache, M, y, x=inputs, norm_weight=norm_weight, eps=eps, norm_out=norm_out,
                      residual=None if residual is None else residual.reshape(M, self.out_features))
+        cache.ind = self.ind
+        cache.q_xcache = cache.q_x_buffer(M, self.in_features)
+        cache.activation_outliers = cache.ao_buffer(self._n_ind)[:M, : self._n_ind]
+        return y.reshape(cache.shape)
+
+    @torch.no_grad()
+    def forward_swiglu_fused(self, up, x, norm_weight=None, eps=0.0, cache=None):
+        """B200 extension: self is gate_proj, `up` is up_proj.  [RMSNorm ->] quantise once -> both GEMMs -> fp16(silu(gate)) *
+        fp16(up) in ONE launch: fused/norm.py:24-33 + fused/mlp.py:61-64 (up_proj, gate_proj.forward_without_precondition-
+        FusedSilu, gate *= up).  Steady state only; needs M > 128 and bit 8 (MixqError otherwise: callers fall back to the
+        three-launch sequence)."""
+        if cache is None:
+            cache = self.cache
+        if self.add_outliers and up.add_outliers:
+            raise _lib.MixqError("forward_swiglu_fused is a steady-state path: run the discovery calls first")
+        if self._n_ind != up._n_ind or self.in_features != up.in_features or self.out_features != up.out_features:
+            raise _lib.MixqError("gate_proj and up_proj must share shape and outlier set")
+        if self._wc_buf.shape[1] != up._wc_buf.shape[1]:
+            n = max(self._wc_buf.shape[1], up._wc_buf.shape[1])
+            self._reserve_wc(n)
+            up._reserve_wc(n)
+        cache.shape = x.shape[:-1] + (self.out_features,)
+        inputs = x.reshape(-1, x.shape[-1])
+        self._require_cuda(inputs, self.q_weight)
+        M = inputs.shape[0]
+        y = torch.empty((M, self.out_features), dtype=torch.float16, device=inputs.device)
+        self._launch(cache, M, y, x=inputs, norm_weight=norm_weight, eps=eps, up=up)
         cache.ind = self.ind
         cache.q_xcache = cache.q_x_buffer(M, self.in_features)
         cache.activation_outliers = cache.ao_buffer(self._n_ind)[:M, : self._n_ind]

@@ -7,7 +7,7 @@ architecture and synthetic tokens (no checkpoint / dataset is reachable).  bench
 past_key_values between iterations (benchflops.py:124), so every step is an independent [B,1] forward with
 an empty KV cache; `past_len > 0` with a real cache is supported for completeness.
 
-Per decoder layer, steady state (after the two outlier-discovery calls), 7 launches:
+Per decoder layer, steady state (after the two outlier-discovery calls), 7 launches (5 with the SwiGLU pair fused):
     W_pack    = RMSNorm + extract + quantise + int8 GEMM + fp16 outlier GEMM + dequant     (1 launch)
     attention = RoPE + single-query attention                                              (1 launch)
     o_proj    = extract + quantise + GEMMs + dequant + residual add                        (1 launch)
@@ -142,6 +142,8 @@ class LlamaDecoder:
         self.norm_f = torch.ones(H, dtype=f16, device=device)
         self.lm_head = rand_w(cfg.vocab, H)   # fp16, never quantised (base.py:285-288 only walks decoder layers)
         self.discovered = False
+        # one launch for up_proj + gate_proj + SiLU + gate*up (needs the 2-CTA kernel: M > 128, bit 8)
+        self.fuse_swiglu = (bit == 8 and batch > 128)
         self.graph = None
         self._static_tokens = None
         self._static_logits = None
@@ -194,12 +196,15 @@ class LlamaDecoder:
                 h = h + self._allreduce(L["o_proj"](attn, None, True))
             else:
                 h = L["o_proj"](attn, None, True, residual=h)
-            if steady:
-                up = L["up_proj"].forward_norm_fused(h, L["ln2"], cfg.eps)
+            if steady and self.fuse_swiglu:
+                gate = L["gate_proj"].forward_swiglu_fused(L["up_proj"], h, L["ln2"], cfg.eps)
             else:
-                up = self._norm_then_linear(h, L["ln2"], L["up_proj"])
-            gate = L["gate_proj"].forward_without_preconditionFusedSilu(h, self.cache)
-            _lib.check(self.lib.mixq_mul_inplace(gate.data_ptr(), up.data_ptr(), gate.numel(), self._stream()), "mul")
+                if steady:
+                    up = L["up_proj"].forward_norm_fused(h, L["ln2"], cfg.eps)
+                else:
+                    up = self._norm_then_linear(h, L["ln2"], L["up_proj"])
+                gate = L["gate_proj"].forward_without_preconditionFusedSilu(h, self.cache)
+                _lib.check(self.lib.mixq_mul_inplace(gate.data_ptr(), up.data_ptr(), gate.numel(), self._stream()), "mul")
             if tp:
                 h = h + self._allreduce(L["down_proj"](gate, None, True))
             else:
@@ -268,4 +273,4 @@ class LlamaDecoder:
         return fl, by
 
     def launches_per_step(self):
-        return 7 * self.n_layers + 1   # + final RMSNorm; embedding / lm_head are library calls
+        return (5 if self.fuse_swiglu else 7) * self.n_layers + 1   # + final RMSNorm; embedding / lm_head are library calls

@@ -214,6 +214,27 @@ def test_llama_decode_step_vs_oracle(bit):
     assert torch.equal(out, logits), "graph replay == eager steady-state step"
 
 
+def test_llama_swiglu_fused_step_matches_unfused():
+    """M > 128: the decode step with the SwiGLU pair in one launch (5 launches per layer) vs the reference's
+    up_proj / gate_proj / gate*=up sequence (7 launches per layer) on the same model: same logits."""
+    from mixq_b200 import _lib
+    from mixq_b200.llama import CONFIGS, LlamaDecoder
+    cfg = CONFIGS["tiny"]
+    B = 160
+    m = LlamaDecoder(cfg, batch=B, bit=8, seed=5, outlier_frac=0.02)
+    assert m.fuse_swiglu
+    tok = torch.randint(0, cfg.vocab, (B, 1), generator=torch.Generator().manual_seed(1)).cuda()
+    assert m.discover(tok)
+    n0 = _lib.launch_count()
+    fused = m.step(tok).clone()
+    assert _lib.launch_count() - n0 == 5 * cfg.layers + 1
+    m.fuse_swiglu = False
+    n0 = _lib.launch_count()
+    plain = m.step(tok).clone()
+    assert _lib.launch_count() - n0 == 7 * cfg.layers + 1
+    rel_close(host(fused), host(plain), "logits fused vs unfused", 2e-3)
+
+
 def test_attention_decode_with_kv_cache():
     """RoPE + single-query attention kernel against the numpy restatement, with a non-empty KV cache and GQA."""
     from mixq_b200 import _lib

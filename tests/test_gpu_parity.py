@@ -275,7 +275,7 @@ def test_rmsnorm_and_fused_extract(lib, M, K, n):
 
 
 # ----------------------------------------------------------------------------- the fused single launch
-def run_fused(lib, x, qw, ws, cols, wc, bit, *, bias=None, act=0, residual=None, norm_w=None, tile=0, skip=None):
+def run_fused(lib, x, qw, ws, cols, wc, bit, *, bias=None, act=0, residual=None, norm_w=None, tile=0, skip=None, up=None):
     from mixq_b200 import _lib
     M, K = x.shape
     N = qw.shape[0]
@@ -290,6 +290,11 @@ def run_fused(lib, x, qw, ws, cols, wc, bit, *, bias=None, act=0, residual=None,
              nw=None if norm_w is None else dev(norm_w), nout=torch.zeros(M, K, dtype=torch.float16, device="cuda"))
     if n:
         t["wc"][:, :n] = dev(wc)
+    if up is not None:   # SwiGLU pair: (q_weight_up, scale_col_up, weight_cache_up)
+        t["qw_up"], t["ws_up"] = dev(up[0]), dev(up[1])
+        t["wc_up"] = torch.zeros(N, cap, dtype=torch.float16, device="cuda")
+        if n:
+            t["wc_up"][:, :n] = dev(up[2])
     if skip is not None:
         t["q_x"].copy_(dev(skip[0])); t["xs"].copy_(dev(skip[1].reshape(-1)))
         if n:
@@ -305,6 +310,8 @@ def run_fused(lib, x, qw, ws, cols, wc, bit, *, bias=None, act=0, residual=None,
     a.sigma = 6.0; a.y = t["y"].data_ptr(); a.act = act; a.grid_sync = t["sync"].data_ptr(); a.tile_n = tile
     a.residual = 0 if residual is None else t["res"].data_ptr(); a.ld_res = N
     a.skip_prologue = 0 if skip is None else 1
+    if up is not None:
+        a.q_weight_up = t["qw_up"].data_ptr(); a.scale_col_up = t["ws_up"].data_ptr(); a.weight_cache_up = t["wc_up"].data_ptr()
     check(lib.mixq_linear_fused(C.byref(a), st()), "mixq_linear_fused")
     torch.cuda.synchronize()
     return t
@@ -397,6 +404,39 @@ def test_linear_fused_norm_and_skip_prologue(lib):
     t2 = run_fused(lib, x, qw, ws, cols, wc, 8, act=1, skip=(q_ref, xs_ref, ao))
     y2 = O.dequantize(O.gemm_i8(q_ref, qw), xs_ref, ws, outl=outl, act=1)
     rel_close(host(t2["y"]), y2, "y (skip_prologue + SiLU)")
+
+
+@pytest.mark.parametrize("M,N,K,n,norm", [(300, 528, 1040, 41, False), (512, 1024, 4096, 0, True), (512, 11008, 4096, 41, True),
+                                          (129, 16, 144, 70, False)])
+def test_linear_fused_swiglu_pair(lib, M, N, K, n, norm):
+    """up_proj + gate_proj (SiLU) + gate *= up in one launch (fused/mlp.py:61-64) vs the three reference steps in the oracle."""
+    rng = np.random.default_rng(M + N + n)
+    x, cols = make_x(rng, M, K, 0 if norm else n)
+    nw = None
+    if norm:
+        nw = np.ones(K, np.float16)
+        if n:
+            nw[np.sort(rng.permutation(K)[:n])] = 20
+        cols = np.nonzero(nw > 1)[0].astype(np.int32)
+    Wg = (rng.standard_normal((N, K)) * 0.02).astype(np.float16)
+    Wu = (rng.standard_normal((N, K)) * 0.02).astype(np.float16)
+    qg, sg = O.quant_weight_w8(Wg)
+    qu, su = O.quant_weight_w8(Wu)
+    wcg, wcu = O.weight_cache_columns(qg, sg, cols, 8), O.weight_cache_columns(qu, su, cols, 8)
+    t = run_fused(lib, x, qg, sg, cols, wcg, 8, norm_w=nw, up=(qu, su, wcu))
+    # oracle on THIS kernel's quantised activations (the RMSNorm reduction order may move single ulps)
+    q_x, xs = host(t["q_x"]), host(t["xs"]).reshape(-1, 1)
+    ao = host(t["ao"])[:, :len(cols)]
+    if not norm:
+        r = oracle_fused(x, qg, sg, cols, wcg, 8)
+        bits_equal(q_x, r["q_x"], "q_x")
+        bits_equal(xs, r["xs"], "x_scale")
+    og = O.outlier_gemm_f32(ao, wcg).astype(np.float16) if len(cols) else None
+    ou = O.outlier_gemm_f32(ao, wcu).astype(np.float16) if len(cols) else None
+    gate = O.dequantize(O.gemm_i8(q_x, qg), xs, sg, outl=og, act=1)
+    upv = O.dequantize(O.gemm_i8(q_x, qu), xs, su, outl=ou, act=0)
+    ref = (gate.astype(np.float32) * upv.astype(np.float32)).astype(np.float16)
+    rel_close(host(t["y"]), ref, "silu(gate) * up", 2e-3 if n == 0 else REL_TOL)
 
 
 # ----------------------------------------------------------------------------- properties at BASELINE.json sizes
