@@ -377,8 +377,15 @@ def run_mixq(args):
                                     "torch_fp32_linear_tokens_per_s": B / (t_lin * cfg.layers)}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # NCCL communicators that CUDA graphs still reference can hang in destroy_process_group (seen at N=2: the line was
+        # printed, then the ranks never exited).  No collective follows the max-over-ranks reduction above, so every rank
+        # drops its graphs and leaves on its own, without the NCCL teardown.
+        model.graph = None
+        del model
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -43,6 +43,11 @@ unsigned long long mixq_launch_count(void);
 /* Tuning/testing override of the GEMM tile width for calls that do not carry their own tile_n:
  * 0 = heuristic (default), 128 or 256. */
 int mixq_set_tile_n(int tile_n);
+/* Programmatic dependent launch (default on; MIXQ_PDL=0 in the environment or on = 0 turns it off): every kernel of the
+ * library is launched so that its CTAs may take an SM as soon as the previous kernel's CTA there has exited, set up, and
+ * prefetch constants (the quantised weights) while the previous kernel drains; each kernel waits for its predecessors
+ * (griddepcontrol.wait) before touching any activation tensor.  Results are identical either way. */
+int mixq_set_pdl(int on);
 
 /* Tuning aid: device buffer of 148*8 uint64 that every subsequent mixq_linear_fused / GEMM launch fills with
  * %globaltimer stamps per CTA (start, prologue done, grid barrier passed, first MMA, last MMA, epilogue done).

@@ -76,6 +76,7 @@ SIGNATURES = {
     "mixq_rope_attention_decode": [_vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _f, _vp],
     "mixq_mul_inplace": [_vp, _vp, _ll, _vp],
     "mixq_set_tile_n": [_i],
+    "mixq_set_pdl": [_i],
     "mixq_set_trace_buffer": [_vp],
     "mixq_version": [],
     "mixq_launch_count": [],

@@ -201,6 +201,12 @@ __device__ __forceinline__ void epilogue_run_coalesced(const LinearParams& p, ui
   const bool silu = p.act == 1;
   const int row = m_base + lane;
   const bool row_ok = row < p.M;
+#ifdef MIXQ_EPI_PROFILE
+  long long t_ld = 0, t_math = 0, t_out = 0, t_a, t_b;
+#define EPI_T(x) x = clock64()
+#else
+#define EPI_T(x)
+#endif
 #pragma unroll 1
   for (int b = 0; b < ncols; b += 64) {
     const int bc = (ncols - b < 64) ? (ncols - b) : 64;
@@ -212,9 +218,13 @@ __device__ __forceinline__ void epilogue_run_coalesced(const LinearParams& p, ui
     for (int c = 0; c < bc; c += 16) {
       uint32_t acc[16];
       uint32_t oacc[16];
+      EPI_T(t_a);
       tmem_ld_32x16(t_int + b + c, acc);
       if (HAS_O) tmem_ld_32x16(t_outl + b + c, oacc);
       tmem_ld_wait();
+#ifdef MIXQ_EPI_PROFILE
+      EPI_T(t_b); t_ld += t_b - t_a;
+#endif
       const int n = n0 + b + c;
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
@@ -251,11 +261,27 @@ __device__ __forceinline__ void epilogue_run_coalesced(const LinearParams& p, ui
         }
         *epi_slot(stage, lane, (c >> 3) + g) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
       }
+#ifdef MIXQ_EPI_PROFILE
+      EPI_T(t_a); t_math += t_a - t_b;
+#endif
     }
     __syncwarp();
+    EPI_T(t_a);
     epi_stage_out(stage, p.y, p.N, m_base, n0 + b, bc >> 3, p.M, p.N, lane);
     __syncwarp();
+#ifdef MIXQ_EPI_PROFILE
+    EPI_T(t_b); t_out += t_b - t_a;
+#endif
   }
+#ifdef MIXQ_EPI_PROFILE
+  if (p.trace && lane == 0) {
+    unsigned long long* t = p.trace + 2048 + (static_cast<size_t>(blockIdx.x) * 8 + ((threadIdx.x >> 5) - 4)) * 4;
+    atomicAdd(t + 0, static_cast<unsigned long long>(t_ld));
+    atomicAdd(t + 1, static_cast<unsigned long long>(t_math));
+    atomicAdd(t + 2, static_cast<unsigned long long>(t_out));
+    atomicAdd(t + 3, 1ull);
+  }
+#endif
 }
 
 }  // namespace mixq

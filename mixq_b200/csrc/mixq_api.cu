@@ -18,6 +18,40 @@ thread_local std::string g_err;
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<int> g_tile_n{0};
 std::atomic<unsigned long long*> g_trace{nullptr};
+// Programmatic dependent launch (ptx.cuh: pdl_wait / pdl_launch_dependents): on unless MIXQ_PDL=0 or mixq_set_pdl(0).
+std::atomic<int> g_pdl{[] { const char* e = getenv("MIXQ_PDL"); return (e && e[0] == '0') ? 0 : 1; }()};
+bool pdl_on() { return g_pdl.load(std::memory_order_relaxed) != 0; }
+
+// Launch attributes shared by every kernel of the library.  A kernel with a grid barrier needs all of its CTAs
+// co-resident: a cooperative launch guarantees it; under PDL the grid is exactly one CTA per SM and the CTAs of the
+// previous kernel leave without waiting for anybody, so ours all become resident as those exit.
+struct LaunchAttrs {
+  cudaLaunchAttribute a[2];
+  int n = 0;
+  LaunchAttrs(bool cooperative, bool pdl) {
+    if (pdl) {
+      a[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      a[n].val.programmaticStreamSerializationAllowed = 1;
+      ++n;
+    } else if (cooperative) {
+      a[n].id = cudaLaunchAttributeCooperative;
+      a[n].val.cooperative = 1;
+      ++n;
+    }
+  }
+};
+template <typename... KArgs, typename... Args>
+cudaError_t launch_small(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  LaunchAttrs la(false, pdl_on());
+  cfg.attrs = la.a;
+  cfg.numAttrs = la.n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -114,11 +148,9 @@ int launch_linear(const LinearParams& p, int grid, bool cooperative, cudaStream_
   cfg.blockDim = dim3(Cfg::NUM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attrs[1];
-  attrs[0].id = cudaLaunchAttributeCooperative;
-  attrs[0].val.cooperative = 1;
-  cfg.attrs = attrs;
-  cfg.numAttrs = cooperative ? 1 : 0;
+  LaunchAttrs la(cooperative, pdl_on());
+  cfg.attrs = la.a;
+  cfg.numAttrs = la.n;
   MIXQ_CUDA(cudaLaunchKernelEx(&cfg, mixq_linear_kernel<BN, W4>, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
@@ -138,11 +170,9 @@ int launch_linear2(const LinearParams& p, int grid, bool cooperative, cudaStream
   cfg.blockDim = dim3(Cfg::NUM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attrs[1];
-  attrs[0].id = cudaLaunchAttributeCooperative;
-  attrs[0].val.cooperative = 1;
-  cfg.attrs = attrs;
-  cfg.numAttrs = cooperative ? 1 : 0;
+  LaunchAttrs la(cooperative, pdl_on());
+  cfg.attrs = la.a;
+  cfg.numAttrs = la.n;
   MIXQ_CUDA(cudaLaunchKernelEx(&cfg, mixq_linear2_kernel, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
@@ -428,8 +458,7 @@ int launch_rowquant(RowQuantArgs a, cudaStream_t st) {
   long long grid = (a.M + ngroups - 1) / ngroups;
   const long long cap = static_cast<long long>(di.sms) * 16;
   if (grid > cap) grid = cap;
-  rowquant_kernel<<<static_cast<int>(grid), kThreads, smem, st>>>(a);
-  MIXQ_CUDA(cudaGetLastError());
+  MIXQ_CUDA(launch_small(rowquant_kernel, static_cast<int>(grid), kThreads, smem, st, a));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
@@ -445,6 +474,11 @@ int mixq_set_tile_n(int tile_n) {
   if (tile_n != 0 && (tile_n < 32 || tile_n > 512 || tile_n % 32 != 0))
     return fail(MIXQ_EINVAL, "tile_n must be 0 or a multiple of 32 up to 512 (the 1-CTA kernel honours 128 and 256 only)");
   g_tile_n.store(tile_n, std::memory_order_relaxed);
+  return 0;
+}
+
+int mixq_set_pdl(int on) {
+  g_pdl.store(on ? 1 : 0, std::memory_order_relaxed);
   return 0;
 }
 
@@ -480,9 +514,8 @@ int mixq_extract_outliers_and_set_to_zeros(const int32_t* ind, int n_ind, void* 
   DeviceInfo di;
   if (int r = device_info(&di)) return r;
   const int grid = grid_for(static_cast<long long>(M) * n_ind, 256, di.sms);
-  extract_outliers_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      ind, n_ind, static_cast<__half*>(x), static_cast<__half*>(out), ld_out, M, K);
-  MIXQ_CUDA(cudaGetLastError());
+  MIXQ_CUDA(launch_small(extract_outliers_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), ind, n_ind,
+                         static_cast<__half*>(x), static_cast<__half*>(out), ld_out, M, K));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
@@ -523,10 +556,9 @@ int mixq_dequantize_int8(const int32_t* acc, const void* x_scale, const void* sc
   DeviceInfo di;
   if (int r = device_info(&di)) return r;
   const int grid = grid_for(static_cast<long long>(M) * (N / 8), 256, di.sms);
-  dequant_i32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      acc, static_cast<const __half*>(x_scale), static_cast<const __half*>(scale_col),
-      static_cast<const __half*>(outl), ld_outl, static_cast<__half*>(y), M, N, act);
-  MIXQ_CUDA(cudaGetLastError());
+  MIXQ_CUDA(launch_small(dequant_i32_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), acc,
+                         static_cast<const __half*>(x_scale), static_cast<const __half*>(scale_col),
+                         static_cast<const __half*>(outl), ld_outl, static_cast<__half*>(y), M, N, act));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
@@ -623,8 +655,7 @@ int mixq_rope_attention_decode(const void* qkv, void* k_cache, void* v_cache, in
     return fail(MIXQ_EINVAL, "past_len > 0 needs k/v caches with capacity > past_len");
   MIXQ_CUDA(launch_rope_attn_decode(static_cast<const __half*>(qkv), static_cast<__half*>(k_cache),
                                     static_cast<__half*>(v_cache), cache_cap, past_len, static_cast<__half*>(out), M, H,
-                                    Hkv, D, theta, static_cast<cudaStream_t>(stream)));
-  MIXQ_CUDA(cudaGetLastError());
+                                    Hkv, D, theta, pdl_on(), static_cast<cudaStream_t>(stream)));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
@@ -634,9 +665,8 @@ int mixq_mul_inplace(void* a, const void* b, long long n, void* stream) {
   DeviceInfo di;
   if (int r = device_info(&di)) return r;
   const int grid = grid_for(n / 2, 256, di.sms);
-  mul_inplace_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<__half2*>(a), static_cast<const __half2*>(b), n / 2);
-  MIXQ_CUDA(cudaGetLastError());
+  MIXQ_CUDA(launch_small(mul_inplace_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), static_cast<__half2*>(a),
+                         static_cast<const __half2*>(b), n / 2));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }

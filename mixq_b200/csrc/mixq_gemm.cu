@@ -76,9 +76,12 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  RowQuantSmem* rq_sm = reinterpret_cast<RowQuantSmem*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
+  if (p.fused_prologue) rowquant_init(p.rq, rq_sm);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents(); // the next kernel's CTAs may queue up behind this grid
   const uint32_t tmem_base = *tmem_slot;
   unsigned long long* trace = p.trace ? p.trace + static_cast<size_t>(blockIdx.x) * 8 : nullptr;
   if (trace && threadIdx.x == 0) trace[0] = globaltimer_ns();
@@ -115,20 +118,23 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
                              ? static_cast<int>((static_cast<size_t>(p.rq.ngroups) * p.rq.K * 2 + Cfg::STAGE_BYTES - 1) / Cfg::STAGE_BYTES)
                              : 0;
   const int free_stages = STAGES - row_stages;
-  const int n_pre = (p.fused_prologue && my_items > 0) ? (my_items < free_stages ? my_items : free_stages) : 0;
+  const int n_pre = my_items < free_stages ? my_items : free_stages;
+
+  // The quantised weights are constants: fill every free pipeline stage with them BEFORE waiting for the kernels ahead
+  // of us in the stream (programmatic dependent launch) — and, with the fused prologue, before phase A.
+  if (warp == 3 && lane == 0) {
+    for (int it = 0; it < n_pre; ++it) {
+      const int tile = blockIdx.x + (it / nkt) * gridDim.x;
+      produce(tile, it % nkt, it, /*act*/ false, /*wgt*/ true, /*arm*/ true);
+    }
+  }
+  __syncwarp();
+  pdl_wait();              // everything below reads or writes tensors that earlier kernels touch
 
   // ------------------------------------------------------------------ phase A (fused prologue)
   if (p.fused_prologue) {
-    RowQuantSmem* rq_sm = reinterpret_cast<RowQuantSmem*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
     uint8_t* rowbuf = smem + static_cast<size_t>(free_stages) * Cfg::STAGE_BYTES;
-    rowquant_begin(p.rq, rq_sm, rowbuf);      // activation rows first: they are on the critical path
-    if (warp == 3 && lane == 0) {
-      for (int it = 0; it < n_pre; ++it) {
-        const int tile = blockIdx.x + (it / nkt) * gridDim.x;
-        produce(tile, it % nkt, it, /*act*/ false, /*wgt*/ true, /*arm*/ true);
-      }
-    }
-    __syncwarp();
+    rowquant_begin(p.rq, rq_sm, rowbuf);
     rowquant_run(p.rq, rq_sm, rowbuf);
     if (trace && threadIdx.x == 0) trace[1] = globaltimer_ns();
     fence_proxy_async_all();   // q_x / act_outliers were written through the generic proxy; TMA reads them next

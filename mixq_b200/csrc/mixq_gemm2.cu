@@ -97,10 +97,13 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
     tmem_alloc_2cta(tmem_slot, 512);
     tmem_relinquish_2cta();
   }
+  RowQuantSmem* rq_sm = reinterpret_cast<RowQuantSmem*>(smem + Cfg::PIPE_BYTES + 256);
+  if (p.fused_prologue) rowquant_init(p.rq, rq_sm);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();      // the peer's barriers exist before anything remote touches them
   tc_fence_after();
+  pdl_launch_dependents(); // the next kernel's CTAs may queue up behind this grid (they take an SM as soon as ours exits)
   const uint32_t tmem_base = *tmem_slot;
   unsigned long long* trace = p.trace ? p.trace + static_cast<size_t>(blockIdx.x) * 8 : nullptr;
   if (trace && threadIdx.x == 0) trace[0] = globaltimer_ns();
@@ -131,20 +134,23 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
                              ? static_cast<int>((static_cast<size_t>(p.rq.ngroups) * p.rq.K * 2 + stage_bytes - 1) / stage_bytes)
                              : 0;
   const int free_stages = nstages - row_stages;
-  const int n_pre = (p.fused_prologue && my_items > 0) ? (my_items < free_stages ? my_items : free_stages) : 0;
+  const int n_pre = my_items < free_stages ? my_items : free_stages;
+
+  // The quantised weights are constants: fill every free pipeline stage with them BEFORE waiting for the kernels ahead
+  // of us in the stream (programmatic dependent launch) — and, with the fused prologue, before phase A.
+  if (warp == 3 && lane == 0) {
+    for (int it = 0; it < n_pre; ++it) {
+      const int tile = pair + (it / nkt) * npairs;
+      produce(tile, it % nkt, it, /*act*/ false, /*wgt*/ true, /*arm*/ true);
+    }
+  }
+  __syncwarp();
+  pdl_wait();              // everything below reads or writes tensors that earlier kernels touch
 
   // ------------------------------------------------------------------ phase A (fused prologue)
   if (p.fused_prologue) {
-    RowQuantSmem* rq_sm = reinterpret_cast<RowQuantSmem*>(smem + Cfg::PIPE_BYTES + 256);
     uint8_t* rowbuf = smem + static_cast<size_t>(free_stages) * stage_bytes;
-    rowquant_begin(p.rq, rq_sm, rowbuf);      // activation rows first: they are on the critical path
-    if (warp == 3 && lane == 0) {
-      for (int it = 0; it < n_pre; ++it) {
-        const int tile = pair + (it / nkt) * npairs;
-        produce(tile, it % nkt, it, /*act*/ false, /*wgt*/ true, /*arm*/ true);
-      }
-    }
-    __syncwarp();
+    rowquant_begin(p.rq, rq_sm, rowbuf);
     rowquant_run(p.rq, rq_sm, rowbuf);
     if (trace && threadIdx.x == 0) trace[1] = globaltimer_ns();
     fence_proxy_async_all();   // q_x / act_outliers were written through the generic proxy; TMA reads them next
@@ -290,6 +296,7 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
       for (int c = 0; c < P; ++c, ++pass_idx) {
         mbar_wait_warp(&bar_tfull[0], pass_idx & 1, 5, c);
         tc_fence_after();
+        if (trace && !p.fused_prologue && warp == 4 && lane == 0 && pass_idx == 0) trace[7] = globaltimer_ns();
         const int x0 = c * (R >> 1);                                   // this pass: output columns [x0, x1) of the half
         const int nc = (W - c * R) < R ? (W - c * R) : R;
         const int x1 = x0 + (nc >> 1);

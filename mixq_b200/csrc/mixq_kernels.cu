@@ -14,6 +14,8 @@ __global__ void __launch_bounds__(256, 4) rowquant_kernel(const RowQuantArgs a) 
 
 __global__ void extract_outliers_kernel(const int32_t* __restrict__ ind, int n_ind, __half* x, __half* out,
                                         int ld_out, int M, int K) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = static_cast<long long>(M) * n_ind;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -30,6 +32,8 @@ __global__ void extract_outliers_kernel(const int32_t* __restrict__ ind, int n_i
 __global__ void dequant_i32_kernel(const int32_t* __restrict__ acc, const __half* __restrict__ x_scale,
                                    const __half* __restrict__ scale_col, const __half* __restrict__ outl,
                                    int ld_outl, __half* __restrict__ y, int M, int N, int act) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int nv = N >> 3;
   const long long total = static_cast<long long>(M) * nv;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -129,6 +133,8 @@ __global__ void __launch_bounds__(256) rope_attn_decode_kernel(const __half* __r
                                                                __half* __restrict__ out, int M, int H, int Hkv,
                                                                float theta, float scale) {
   constexpr int E = D / 32;   // 2 (D = 64) or 4 (D = 128) halves per lane
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (w >= static_cast<long long>(M) * H) return;
@@ -210,18 +216,27 @@ __global__ void __launch_bounds__(256) rope_attn_decode_kernel(const __half* __r
 }
 
 cudaError_t launch_rope_attn_decode(const __half* qkv, __half* k_cache, __half* v_cache, int cache_cap, int past_len,
-                                    __half* out, int M, int H, int Hkv, int D, float theta, cudaStream_t st) {
+                                    __half* out, int M, int H, int Hkv, int D, float theta, bool pdl, cudaStream_t st) {
   const long long warps = static_cast<long long>(M) * H;
   const int grid = static_cast<int>((warps + 7) / 8);
   const float scale = 1.0f / sqrtf(static_cast<float>(D));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
   if (D == 128)
-    rope_attn_decode_kernel<128><<<grid, 256, 0, st>>>(qkv, k_cache, v_cache, cache_cap, past_len, out, M, H, Hkv, theta, scale);
-  else
-    rope_attn_decode_kernel<64><<<grid, 256, 0, st>>>(qkv, k_cache, v_cache, cache_cap, past_len, out, M, H, Hkv, theta, scale);
-  return cudaGetLastError();
+    return cudaLaunchKernelEx(&cfg, rope_attn_decode_kernel<128>, qkv, k_cache, v_cache, cache_cap, past_len, out, M, H, Hkv, theta, scale);
+  return cudaLaunchKernelEx(&cfg, rope_attn_decode_kernel<64>, qkv, k_cache, v_cache, cache_cap, past_len, out, M, H, Hkv, theta, scale);
 }
 
 __global__ void mul_inplace_kernel(__half2* a, const __half2* __restrict__ b, long long n2) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n2;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     a[i] = __hmul2(a[i], b[i]);

@@ -14,7 +14,7 @@ __global__ void gather_weight_cols_kernel(const void* q_w, const __half* scale_c
                                           __half* wc, int ld_wc, int col0, int N, int K, int bit);
 __global__ void compact_cols_kernel(uint8_t* col_over, int K, int32_t* ind_out, int max_new, int32_t* n_new);
 cudaError_t launch_rope_attn_decode(const __half* qkv, __half* k_cache, __half* v_cache, int cache_cap, int past_len,
-                                    __half* out, int M, int H, int Hkv, int D, float theta, cudaStream_t st);
+                                    __half* out, int M, int H, int Hkv, int D, float theta, bool pdl, cudaStream_t st);
 __global__ void mul_inplace_kernel(__half2* a, const __half2* b, long long n2);
 
 }  // namespace mixq

@@ -47,6 +47,15 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of this library is launched with cudaLaunchAttributeProgrammaticStreamSerialization (mixq_api.cu), so its
+// CTAs may start while the previous kernel of the stream is still draining.  pdl_launch_dependents() lets the NEXT kernel's
+// CTAs queue up behind ours as early as possible; pdl_wait() returns once every earlier kernel has completed and its
+// memory is visible — nothing before it may touch a tensor another kernel writes or reads (constants such as the
+// quantised weights may be fetched earlier: that is the point).  Both are no-ops for a plain launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -253,15 +253,17 @@ __device__ __forceinline__ void process_row(const RowQuantArgs& a, int m, int gr
 
 // Row loop of one CTA: rows are dealt round-robin over (CTA, group) so that every CTA gets ceil(M / gridDim) rows
 // at most.  rowbuf: ngroups * K * 2 bytes of 16-byte aligned shared memory.
-// rowquant_begin: every thread of the CTA (contains __syncthreads); starts the bulk copy of each group's first row.
+// rowquant_init: threads [0, ngroups) initialise the per-group mbarriers; a __syncthreads (the caller's) must follow.
+// rowquant_begin: every thread, after that barrier (and after pdl_wait: it reads x); starts each group's first row copy.
+__device__ __forceinline__ void rowquant_init(const RowQuantArgs& a, RowQuantSmem* sm) {
+  if (threadIdx.x < a.ngroups) mbar_init(&sm->bars[threadIdx.x], 1);
+  fence_mbar_init();
+}
 __device__ __forceinline__ void rowquant_begin(const RowQuantArgs& a, RowQuantSmem* sm, uint8_t* rowbuf) {
   const int G = a.group_warps;
   const int group = (threadIdx.x >> 5) / G;
   const int gl = threadIdx.x - group * G * 32;
   const uint32_t row_bytes = static_cast<uint32_t>(a.K) * 2u;
-  if (threadIdx.x < a.ngroups) mbar_init(&sm->bars[threadIdx.x], 1);
-  fence_mbar_init();
-  __syncthreads();
   const int m = blockIdx.x + gridDim.x * group;
   if (group < a.ngroups && m < a.M && gl == 0) {
     mbar_arrive_expect_tx(&sm->bars[group], row_bytes);
@@ -298,6 +300,10 @@ __device__ __forceinline__ void rowquant_run(const RowQuantArgs& a, RowQuantSmem
   }
 }
 __device__ __forceinline__ void rowquant_cta(const RowQuantArgs& a, RowQuantSmem* sm, uint8_t* rowbuf) {
+  rowquant_init(a, sm);
+  __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();
   rowquant_begin(a, sm, rowbuf);
   rowquant_run(a, sm, rowbuf);
 }

@@ -10,7 +10,7 @@ cat gpurun_out/${TAG}_bench_linear.jsonl
 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file gpurun_out/${TAG}_launches.csv python tools/profile_step.py > gpurun_out/${TAG}_launches.log 2>&1
 tail -2 gpurun_out/${TAG}_launches.log
-timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:mixq_linear_kernel -c 5 \
+timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:mixq_linear -c 4 \
     -f -o gpurun_out/${TAG}_prof_linear python tools/profile_step.py --layers 1 > gpurun_out/${TAG}_prof.log 2>&1
 tail -2 gpurun_out/${TAG}_prof.log
 ls -la gpurun_out

@@ -7,13 +7,14 @@ lib = _lib.load()
 M = 512
 dev = "cuda"
 g = torch.Generator(device=dev).manual_seed(0)
-trace = torch.zeros(4096, dtype=torch.int64, device=dev)
+trace = torch.zeros(16384, dtype=torch.int64, device=dev)
+NOUT = int(os.environ.get('NOUT', '41'))
 TILE = int(os.environ.get('TILE', '0'))
 MODES = os.environ.get('MODES', 'plain,skip').split(',')
 SHAPES = [tuple(int(v) for v in t.split('x')) for t in os.environ.get('SHAPES', '12288x4096,4096x4096,4096x11008').split(',')]
 for (N, K) in SHAPES:
-    n, cap = 41, 64
-    cols = torch.randperm(K, generator=g, device=dev)[:n].sort().values.int()
+    n, cap = NOUT, max(64, (NOUT + 63) // 64 * 64)
+    cols = torch.randperm(K, generator=g, device=dev)[:max(n, 1)].sort().values.int()
     x0 = torch.randn(M, K, generator=g, device=dev); x0[:, cols.long()] *= 20; x0 = x0.half()
     ws_l = [(torch.randint(-127, 128, (N, K), generator=g, device=dev, dtype=torch.int8),
              (torch.rand(N, generator=g, device=dev) * 1e-3 + 1e-4).half(),
@@ -42,6 +43,11 @@ for (N, K) in SHAPES:
             return (f"{(v.min()-t0)/1e3:6.2f}..{(v.max()-t0)/1e3:6.2f}" if len(v) else "      -       ")
         print(f"N={N} K={K} tile={TILE} {mode:5s} us since first CTA start: start {col(0)} | mask built {col(6)} | row0 absmax {col(7)} | prologue done {col(1)} | barrier passed {col(2)} | "
               f"first MMA {col(3)} | int MMAs issued {col(6)} | last MMA {col(4)} | epilogue done {col(5)}")
+        ep = full[2048:2048 + 148 * 8 * 4].view(148 * 8, 4)
+        if ep[:, 3].sum() > 0:   # built with EXTRA=-DMIXQ_EPI_PROFILE: clock64 sums per epilogue warp
+            ok = ep[:, 3] > 0
+            print(f"    epilogue clocks per warp (mean over {int(ok.sum())} warps): tmem ld+wait {ep[ok, 0].mean():8.0f} | math+smem {ep[ok, 1].mean():8.0f} | "
+                  f"stage-out {ep[ok, 2].mean():8.0f} | calls {ep[ok, 3].mean():.1f}")
         if os.environ.get("CADENCE"):
             base = t[0, 0]
             for name, off in (("mma", 2048), ("wgt-tma", 2048 + 256), ("act-tma", 2048 + 512)):
