@@ -155,52 +155,98 @@ __device__ __forceinline__ void epilogue_span(const LinearParams& p, uint32_t t_
 // 128 x 352 tile).  Each epilogue warp therefore owns a 4 KB staging tile (32 rows x 64 fp16, 16-byte chunks XOR-swizzled
 // by row so that both the row-wise and the 8-lanes-per-row accesses are conflict free) and moves 64 columns at a time
 // between it and global memory with 8 lanes per row: 4 full 128-byte lines per instruction.
+//
+// The epilogue is bound by INSTRUCTION ISSUE (ncu + clock64 profile, profiles/r01_ncu_summary.md: tcgen05.ld+wait is 3 %
+// of it; two epilogue warps per scheduler at ~260 SASS instructions per 16 columns): the variants below are templated on
+// what the call actually needs, address shared memory through 32-bit shared-window addresses (ld/st.shared, no generic
+// 64-bit pointer arithmetic), and bring residual / addend tiles in through the same coalesced staging path.
 namespace mixq {
 
 constexpr int kEpiStageBytes = 32 * 128;
 
-__device__ __forceinline__ uint4* epi_slot(uint8_t* stage, int row, int chunk) {
-  return reinterpret_cast<uint4*>(stage + row * 128 + ((chunk ^ (row & 7)) << 4));
+__device__ __forceinline__ uint4 lds128(uint32_t sa) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sa) : "memory");
+  return v;
 }
-// global [m_base + r][n_blk + 8c] -> stage[r][c]  for r < 32, c < nchunks (rows >= M / columns >= N skipped)
-__device__ __forceinline__ void epi_stage_in(uint8_t* stage, const __half* g, int ld, int m_base, int n_blk, int nchunks, int M,
+__device__ __forceinline__ void sts128(uint32_t sa, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// stage[r][c] (r < 32 rows, c < 8 chunks of 16 bytes) lives at stage_sa + r * 128 + ((c ^ (r & 7)) << 4)
+__device__ __forceinline__ uint32_t epi_slot_sa(uint32_t stage_sa, int row, int chunk) {
+  return stage_sa + row * 128 + ((chunk ^ (row & 7)) << 4);
+}
+// global [m_base + r][n_blk + 8c] -> stage[r][c]  for r < 32, c < nchunks (rows >= M / columns >= N skipped).
+// Lane l moves chunk c = l & 7 of rows (l >> 3) + 4 it: slot address = (base0 + 512 it) ^ ((it & 1) << 6).
+__device__ __forceinline__ void epi_stage_in(uint32_t stage_sa, const __half* g, int ld, int m_base, int n_blk, int nchunks, int M,
                                              int N, int lane) {
-  const int c = lane & 7;
+  const int c = lane & 7, r0 = lane >> 3;
+  if (c >= nchunks || n_blk + c * 8 >= N) return;
+  const __half* src = g + static_cast<size_t>(m_base + r0) * ld + n_blk + c * 8;
+  const size_t step = static_cast<size_t>(4) * ld;
+  const uint32_t base0 = stage_sa + r0 * 128 + ((c ^ r0) << 4);
+  if (m_base + 32 <= M) {
+    uint4 v[8];
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int r = it * 4 + (lane >> 3);
-    if (c < nchunks && m_base + r < M && n_blk + c * 8 < N)
-      *epi_slot(stage, r, c) = *reinterpret_cast<const uint4*>(g + static_cast<size_t>(m_base + r) * ld + n_blk + c * 8);
+    for (int it = 0; it < 8; ++it) v[it] = *reinterpret_cast<const uint4*>(src + it * step);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) sts128((base0 + it * 512) ^ ((it & 1) << 6), v[it]);
+  } else {
+#pragma unroll
+    for (int it = 0; it < 8; ++it)
+      if (m_base + it * 4 + r0 < M) sts128((base0 + it * 512) ^ ((it & 1) << 6), *reinterpret_cast<const uint4*>(src + it * step));
   }
 }
-__device__ __forceinline__ void epi_stage_out(const uint8_t* stage, __half* g, int ld, int m_base, int n_blk, int nchunks, int M,
+__device__ __forceinline__ void epi_stage_out(uint32_t stage_sa, __half* g, int ld, int m_base, int n_blk, int nchunks, int M,
                                               int N, int lane) {
-  const int c = lane & 7;
+  const int c = lane & 7, r0 = lane >> 3;
+  if (c >= nchunks || n_blk + c * 8 >= N) return;
+  __half* dst = g + static_cast<size_t>(m_base + r0) * ld + n_blk + c * 8;
+  const size_t step = static_cast<size_t>(4) * ld;
+  const uint32_t base0 = stage_sa + r0 * 128 + ((c ^ r0) << 4);
+  if (m_base + 32 <= M) {
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int r = it * 4 + (lane >> 3);
-    if (c < nchunks && m_base + r < M && n_blk + c * 8 < N)
-      *reinterpret_cast<uint4*>(g + static_cast<size_t>(m_base + r) * ld + n_blk + c * 8) =
-          *epi_slot(const_cast<uint8_t*>(stage), r, c);
+    for (int it = 0; it < 8; ++it) *reinterpret_cast<uint4*>(dst + it * step) = lds128((base0 + it * 512) ^ ((it & 1) << 6));
+  } else {
+#pragma unroll
+    for (int it = 0; it < 8; ++it)
+      if (m_base + it * 4 + r0 < M) *reinterpret_cast<uint4*>(dst + it * step) = lds128((base0 + it * 512) ^ ((it & 1) << 6));
   }
+}
+
+// v = (f32(acc) * xs) * ws [+ fp16(f32 outlier sum)] for the two accumulator columns that share one 32-bit scale word.
+// torch.mm(activation_outliers, weight_cache.T) returns fp16 (linear.py:248): the fp32 tensor-core sum is rounded to fp16
+// before it joins the dequantised int part.
+template <bool HAS_O>
+__device__ __forceinline__ float2 dequant2(uint32_t a0, uint32_t a1, uint32_t o0, uint32_t o1, float xs, uint32_t ws2) {
+  const float2 wf = __half22float2(*reinterpret_cast<const __half2*>(&ws2));
+  float2 v;
+  v.x = __fmul_rn(__fmul_rn(static_cast<float>(static_cast<int32_t>(a0)), xs), wf.x);
+  v.y = __fmul_rn(__fmul_rn(static_cast<float>(static_cast<int32_t>(a1)), xs), wf.y);
+  if (HAS_O) {
+    const float2 of = __half22float2(__floats2half2_rn(__uint_as_float(o0), __uint_as_float(o1)));
+    v.x = __fadd_rn(v.x, of.x);
+    v.y = __fadd_rn(v.y, of.y);
+  }
+  return v;
 }
 
 // One contiguous run of `ncols` (multiple of 16) output columns of a tile for the 32 rows of this warp:
 //   y = act(fp16((f32(acc_int) * xs) * ws + fp16(acc_outl) [+ addend])) [+ bias] [+ residual]
 // t_int / t_outl: TMEM addresses (lane quarter included) of the first int32 / fp32-outlier accumulator column of the run
-// (t_outl unused when !HAS_O); s_scale: scale_col of the run's first column, in shared memory.
-// torch.mm(activation_outliers, weight_cache.T) returns fp16 (linear.py:248): the fp32 tensor-core sum is rounded to fp16
-// before it joins the dequantised int part.
-template <bool HAS_O>
-__device__ __forceinline__ void epilogue_run_coalesced(const LinearParams& p, uint8_t* stage, uint32_t t_int, uint32_t t_outl,
-                                                       int m_base, int n0, int ncols, float xs, const __half* s_scale,
-                                                       int lane) {
-  const bool has_add = p.outl != nullptr;
-  const bool has_bias = p.bias != nullptr;
-  const bool has_res = p.residual != nullptr;
-  const bool silu = p.act == 1;
+// (t_outl unused when !HAS_O); scale_sa: shared-window address of scale_col (fp16) of the run's first column.
+// MODE 0: nothing else.  MODE 1: + residual (staged in through the tile).  MODE 2: any of addend / bias / residual / SiLU.
+template <bool HAS_O, int MODE>
+__device__ __forceinline__ void epilogue_run_coalesced(const LinearParams& p, uint32_t stage_sa, uint32_t t_int, uint32_t t_outl,
+                                                       int m_base, int n0, int ncols, float xs, uint32_t scale_sa, int lane) {
+  const bool has_add = MODE == 2 && p.outl != nullptr;
+  const bool has_bias = MODE == 2 && p.bias != nullptr;
+  const bool has_res = MODE == 2 && p.residual != nullptr;
+  const bool silu = MODE == 2 && p.act == 1;
   const int row = m_base + lane;
   const bool row_ok = row < p.M;
+  const uint32_t row_sa = stage_sa + lane * 128;
+  const uint32_t sw = lane & 7;
 #ifdef MIXQ_EPI_PROFILE
   long long t_ld = 0, t_math = 0, t_out = 0, t_a, t_b;
 #define EPI_T(x) x = clock64()
@@ -210,8 +256,11 @@ __device__ __forceinline__ void epilogue_run_coalesced(const LinearParams& p, ui
 #pragma unroll 1
   for (int b = 0; b < ncols; b += 64) {
     const int bc = (ncols - b < 64) ? (ncols - b) : 64;
-    if (has_add) {
-      epi_stage_in(stage, p.outl, p.ld_outl, m_base, n0 + b, bc >> 3, p.M, p.N, lane);
+    if (MODE == 1) {
+      epi_stage_in(stage_sa, p.residual, p.ld_res, m_base, n0 + b, bc >> 3, p.M, p.N, lane);
+      __syncwarp();
+    } else if (has_add) {
+      epi_stage_in(stage_sa, p.outl, p.ld_outl, m_base, n0 + b, bc >> 3, p.M, p.N, lane);
       __syncwarp();
     }
 #pragma unroll 1
@@ -225,41 +274,62 @@ __device__ __forceinline__ void epilogue_run_coalesced(const LinearParams& p, ui
 #ifdef MIXQ_EPI_PROFILE
       EPI_T(t_b); t_ld += t_b - t_a;
 #endif
-      const int n = n0 + b + c;
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
-        const int ng = n + g * 8;
-        const bool ok = row_ok && ng < p.N;
-        const uint4 wsu = *reinterpret_cast<const uint4*>(s_scale + b + c + g * 8);
-        uint4 olu = make_uint4(0, 0, 0, 0), bsu = make_uint4(0, 0, 0, 0), rsu = make_uint4(0, 0, 0, 0);
-        if (has_add) olu = *epi_slot(stage, lane, (c >> 3) + g);
-        if (has_bias && ng < p.N) bsu = __ldg(reinterpret_cast<const uint4*>(p.bias + ng));
-        if (has_res && ok) rsu = *reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(row) * p.ld_res + ng);
+        const uint4 wsu = lds128(scale_sa + (b + c + g * 8) * 2);
+        const uint32_t slot = row_sa + ((((c >> 3) + g) ^ sw) << 4);
         const uint32_t wsw[4] = {wsu.x, wsu.y, wsu.z, wsu.w};
-        const uint32_t olw[4] = {olu.x, olu.y, olu.z, olu.w};
-        const uint32_t bsw[4] = {bsu.x, bsu.y, bsu.z, bsu.w};
-        const uint32_t rsw[4] = {rsu.x, rsu.y, rsu.z, rsu.w};
         uint32_t ow[4];
+        if (MODE == 0) {
 #pragma unroll
-        for (int j2 = 0; j2 < 4; ++j2) {
-          const float2 wf = __half22float2(*reinterpret_cast<const __half2*>(&wsw[j2]));
-          const float2 of = __half22float2(*reinterpret_cast<const __half2*>(&olw[j2]));
-          float v[2];
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int cc = g * 8 + j2 * 2 + h;
-            float t = __fmul_rn(__fmul_rn(static_cast<float>(static_cast<int32_t>(acc[cc])), xs), h ? wf.y : wf.x);
-            if (HAS_O) t = __fadd_rn(t, __half2float(__float2half_rn(__uint_as_float(oacc[cc]))));
-            if (has_add) t = __fadd_rn(t, h ? of.y : of.x);
-            if (silu) t = silu_f(t);
-            v[h] = t;
+          for (int j2 = 0; j2 < 4; ++j2) {
+            const int cc = g * 8 + j2 * 2;
+            const float2 v = dequant2<HAS_O>(acc[cc], acc[cc + 1], oacc[cc], oacc[cc + 1], xs, wsw[j2]);
+            const __half2 o2 = __floats2half2_rn(v.x, v.y);
+            ow[j2] = *reinterpret_cast<const uint32_t*>(&o2);
           }
-          __half2 o2 = __floats2half2_rn(v[0], v[1]);
-          if (has_bias) o2 = hadd2_via_f32(o2, *reinterpret_cast<const __half2*>(&bsw[j2]));
-          if (has_res) o2 = hadd2_via_f32(o2, *reinterpret_cast<const __half2*>(&rsw[j2]));
-          ow[j2] = *reinterpret_cast<const uint32_t*>(&o2);
+        } else if (MODE == 1) {
+          const uint4 rsu = lds128(slot);
+          const uint32_t rsw[4] = {rsu.x, rsu.y, rsu.z, rsu.w};
+#pragma unroll
+          for (int j2 = 0; j2 < 4; ++j2) {
+            const int cc = g * 8 + j2 * 2;
+            const float2 v = dequant2<HAS_O>(acc[cc], acc[cc + 1], oacc[cc], oacc[cc + 1], xs, wsw[j2]);
+            // the decoder's residual add is a separate fp16 op in the reference: round, then add in fp32, round again
+            const __half2 o2 = hadd2_via_f32(__floats2half2_rn(v.x, v.y), *reinterpret_cast<const __half2*>(&rsw[j2]));
+            ow[j2] = *reinterpret_cast<const uint32_t*>(&o2);
+          }
+        } else {
+          const int ng = n0 + b + c + g * 8;
+          const bool ok = row_ok && ng < p.N;
+          uint4 olu = make_uint4(0, 0, 0, 0), bsu = make_uint4(0, 0, 0, 0), rsu = make_uint4(0, 0, 0, 0);
+          if (has_add) olu = lds128(slot);
+          if (has_bias && ng < p.N) bsu = __ldg(reinterpret_cast<const uint4*>(p.bias + ng));
+          if (has_res && ok) rsu = *reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(row) * p.ld_res + ng);
+          const uint32_t olw[4] = {olu.x, olu.y, olu.z, olu.w};
+          const uint32_t bsw[4] = {bsu.x, bsu.y, bsu.z, bsu.w};
+          const uint32_t rsw[4] = {rsu.x, rsu.y, rsu.z, rsu.w};
+#pragma unroll
+          for (int j2 = 0; j2 < 4; ++j2) {
+            const int cc = g * 8 + j2 * 2;
+            float2 v = dequant2<HAS_O>(acc[cc], acc[cc + 1], oacc[cc], oacc[cc + 1], xs, wsw[j2]);
+            if (has_add) {
+              const float2 of = __half22float2(*reinterpret_cast<const __half2*>(&olw[j2]));
+              v.x = __fadd_rn(v.x, of.x);
+              v.y = __fadd_rn(v.y, of.y);
+            }
+            if (silu) {
+              v.x = silu_f(v.x);
+              v.y = silu_f(v.y);
+            }
+            __half2 o2 = __floats2half2_rn(v.x, v.y);
+            // y1 += bias (linear.py:284-285) and the residual add are separate fp16 ops in the reference
+            if (has_bias) o2 = hadd2_via_f32(o2, *reinterpret_cast<const __half2*>(&bsw[j2]));
+            if (has_res) o2 = hadd2_via_f32(o2, *reinterpret_cast<const __half2*>(&rsw[j2]));
+            ow[j2] = *reinterpret_cast<const uint32_t*>(&o2);
+          }
         }
-        *epi_slot(stage, lane, (c >> 3) + g) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        sts128(slot, make_uint4(ow[0], ow[1], ow[2], ow[3]));
       }
 #ifdef MIXQ_EPI_PROFILE
       EPI_T(t_a); t_math += t_a - t_b;
@@ -267,7 +337,7 @@ __device__ __forceinline__ void epilogue_run_coalesced(const LinearParams& p, ui
     }
     __syncwarp();
     EPI_T(t_a);
-    epi_stage_out(stage, p.y, p.N, m_base, n0 + b, bc >> 3, p.M, p.N, lane);
+    epi_stage_out(stage_sa, p.y, p.N, m_base, n0 + b, bc >> 3, p.M, p.N, lane);
     __syncwarp();
 #ifdef MIXQ_EPI_PROFILE
     EPI_T(t_b); t_out += t_b - t_a;
@@ -296,9 +366,12 @@ __device__ __forceinline__ void epilogue_run_coalesced(const LinearParams& p, ui
 namespace mixq {
 
 template <bool HAS_O, int ROLE>   // ROLE 0 = gate warp, 1 = up warp
-__device__ __forceinline__ void epilogue_run_swiglu(const LinearParams& p, uint8_t* my_stage, uint8_t* gate_stage, int bar_id,
+__device__ __forceinline__ void epilogue_run_swiglu(const LinearParams& p, uint32_t my_sa, uint32_t gate_sa, int bar_id,
                                                     uint32_t t_int, uint32_t t_outl, int m_base, int n0, int ncols, float xs,
-                                                    const __half* s_scale, int lane) {
+                                                    uint32_t scale_sa, int lane) {
+  const uint32_t sw = lane & 7;
+  const uint32_t my_row = my_sa + lane * 128;
+  const uint32_t gate_row = gate_sa + lane * 128;
 #pragma unroll 1
   for (int b = 0; b < ncols; b += 64) {
     const int bc = (ncols - b < 64) ? (ncols - b) : 64;
@@ -311,34 +384,30 @@ __device__ __forceinline__ void epilogue_run_swiglu(const LinearParams& p, uint8
       tmem_ld_wait();
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
-        const uint4 wsu = *reinterpret_cast<const uint4*>(s_scale + b + c + g * 8);
+        const uint4 wsu = lds128(scale_sa + (b + c + g * 8) * 2);
         const uint32_t wsw[4] = {wsu.x, wsu.y, wsu.z, wsu.w};
         uint32_t ow[4];
 #pragma unroll
         for (int j2 = 0; j2 < 4; ++j2) {
-          const float2 wf = __half22float2(*reinterpret_cast<const __half2*>(&wsw[j2]));
-          float v[2];
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int cc = g * 8 + j2 * 2 + h;
-            float t = __fmul_rn(__fmul_rn(static_cast<float>(static_cast<int32_t>(acc[cc])), xs), h ? wf.y : wf.x);
-            if (HAS_O) t = __fadd_rn(t, __half2float(__float2half_rn(__uint_as_float(oacc[cc]))));
-            if (ROLE == 0) t = silu_f(t);
-            v[h] = t;
+          const int cc = g * 8 + j2 * 2;
+          float2 v = dequant2<HAS_O>(acc[cc], acc[cc + 1], oacc[cc], oacc[cc + 1], xs, wsw[j2]);
+          if (ROLE == 0) {
+            v.x = silu_f(v.x);
+            v.y = silu_f(v.y);
           }
-          const __half2 o2 = __floats2half2_rn(v[0], v[1]);
+          const __half2 o2 = __floats2half2_rn(v.x, v.y);
           ow[j2] = *reinterpret_cast<const uint32_t*>(&o2);
         }
-        *epi_slot(my_stage, lane, (c >> 3) + g) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        sts128(my_row + ((((c >> 3) + g) ^ sw) << 4), make_uint4(ow[0], ow[1], ow[2], ow[3]));
       }
     }
     named_bar_sync(bar_id, 64);            // gate tile published
     if (ROLE == 1) {
 #pragma unroll 1
       for (int ch = 0; ch < (bc >> 3); ++ch) {
-        const uint4 gu = *epi_slot(gate_stage, lane, ch);
-        uint4* mine = epi_slot(my_stage, lane, ch);
-        const uint4 uu = *mine;
+        const uint32_t off = (static_cast<uint32_t>(ch) ^ sw) << 4;
+        const uint4 gu = lds128(gate_row + off);
+        const uint4 uu = lds128(my_row + off);
         const uint32_t gw[4] = {gu.x, gu.y, gu.z, gu.w};
         const uint32_t uw[4] = {uu.x, uu.y, uu.z, uu.w};
         uint32_t ow[4];
@@ -347,13 +416,13 @@ __device__ __forceinline__ void epilogue_run_swiglu(const LinearParams& p, uint8
           const __half2 pr = __hmul2(*reinterpret_cast<const __half2*>(&gw[j]), *reinterpret_cast<const __half2*>(&uw[j]));
           ow[j] = *reinterpret_cast<const uint32_t*>(&pr);
         }
-        *mine = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        sts128(my_row + off, make_uint4(ow[0], ow[1], ow[2], ow[3]));
       }
     }
     named_bar_sync(bar_id, 64);            // gate tile consumed: its warp may overwrite it
     if (ROLE == 1) {
       __syncwarp();
-      epi_stage_out(my_stage, p.y, p.N, m_base, n0 + b, bc >> 3, p.M, p.N, lane);
+      epi_stage_out(my_sa, p.y, p.N, m_base, n0 + b, bc >> 3, p.M, p.N, lane);
       __syncwarp();
     }
   }

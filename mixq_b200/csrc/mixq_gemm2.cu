@@ -65,10 +65,15 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
   const int ntiles = MP * NT;
   const bool has_o = nko > 0;
   const uint32_t stage_tx = 2u * static_cast<uint32_t>(Cfg::A_BYTES + bh * 128);   // both CTAs' bytes land on one barrier
-  // outlier passes: R accumulator columns at a time (R = W when everything fits next to the int32 accumulator)
-  const int r_max = has_o ? ((512 - W) < W ? ((512 - W) & ~31) : W) : W;
-  const int P = (W + r_max - 1) / r_max;
-  const int R = ((W + P - 1) / P + 31) & ~31;          // balanced passes (352 -> 128 + 128 + 96, not 160 + 160 + 32)
+  // Outlier passes.  The fp32 accumulator of the skinny outlier GEMM gets what TMEM has left beside the int32 one: all W
+  // columns when 2 W <= 512 (one pass), otherwise TWO buffers of R columns that the MMA warp and the epilogue warps
+  // ping-pong (pass c + 1 is issued while pass c drains).  Passes are balanced (352 -> 6 x 64, not 5 x 64 + 32).
+  int P = 1, R = W;
+  if (has_o && 2 * W > 512) {
+    const int r_max = ((512 - W) >> 1) & ~31;     // host guarantees W <= 448 with outliers: r_max >= 32
+    P = (W + r_max - 1) / r_max;
+    R = ((W + P - 1) / P + 31) & ~31;
+  }
 
   auto stage_a = [&](int s) { return smem + static_cast<size_t>(s) * stage_bytes; };
   auto stage_b = [&](int s) { return smem + static_cast<size_t>(s) * stage_bytes + Cfg::A_BYTES; };
@@ -187,17 +192,26 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
     if (leader) {
       const uint32_t idesc_i8_1 = make_idesc_i8_rt(256, n1), idesc_i8_2 = make_idesc_i8_rt(256, n2 > 0 ? n2 : 32);
       const uint32_t d1 = tmem_base, d2 = tmem_base + static_cast<uint32_t>(n1);
-      const uint32_t d_outl = tmem_base + static_cast<uint32_t>(W);
       const uint64_t b2_off = static_cast<uint64_t>((n1 >> 1) * 128) >> 4;   // chunk 2 starts n1/2 rows into the half
       const bool two = n2 > 0;
       int s = 0;
       uint32_t ph = 0;
-      uint32_t consumed = 0;     // epilogue passes we have waited for so far (phase index of bar_tempty[0])
+      // accumulator buffer b (b = 0: also the int32 accumulator when there are no outliers) has been handed to the epilogue
+      // used_b times and handed back waited_b times so far
+      uint32_t used0 = 0, used1 = 0, waited0 = 0, waited1 = 0;
+      auto reclaim = [&](int b) {
+        uint32_t& used = b ? used1 : used0;
+        uint32_t& waited = b ? waited1 : waited0;
+        while (waited < used) {
+          mbar_wait(&bar_tempty[b], waited & 1, 2, b);
+          ++waited;
+        }
+        tc_fence_after();
+      };
       for (int i = 0; i < my_tiles; ++i) {
-        if (i > 0) {             // the previous tile's last pass has left TMEM (both CTAs)
-          mbar_wait(&bar_tempty[0], (consumed & 1), 2, i);
-          ++consumed;
-          tc_fence_after();
+        if (i > 0) {             // every pass of the previous tile has left TMEM (both CTAs)
+          reclaim(0);
+          reclaim(1);
         }
         for (int kb = 0; kb < nk; ++kb) {
           mbar_wait(&bar_full[s], ph, 4, s);
@@ -221,6 +235,7 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
         if (!has_o) {
           if (elect_one()) umma_commit_2cta(&bar_tfull[0], 0x3);
           __syncwarp();
+          ++used0;
         } else {
           // the nko outlier k-blocks sit in the next nko stages and stay there for all P passes
           const int s_o = s;
@@ -233,13 +248,11 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
           }
           tc_fence_after();
           for (int c = 0; c < P; ++c) {
-            if (c > 0) {         // region R is free again: pass c-1 was consumed
-              mbar_wait(&bar_tempty[0], (consumed & 1), 8, c);
-              ++consumed;
-              tc_fence_after();
-            }
+            const int b = c & 1;
+            reclaim(b);          // pass c - 2 (same buffer) was consumed
             const int nc = (W - c * R) < R ? (W - c * R) : R;
             const uint32_t idesc_f16 = make_idesc_f16_rt(256, nc);
+            const uint32_t d_outl = tmem_base + static_cast<uint32_t>(W + b * R);
             const uint64_t bo = static_cast<uint64_t>(c * (R >> 1) * 128) >> 4;
             if (elect_one()) {
               for (int kbo = 0; kbo < nko; ++kbo) {
@@ -252,7 +265,8 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
                 for (int k = 0; k < ksteps; ++k)   // K = 16 fp16 = 32 B
                   umma_f16_2cta(d_outl, da + 2 * k, db + 2 * k, idesc_f16, (kbo | k) != 0);
               }
-              umma_commit_2cta(&bar_tfull[0], 0x3);
+              umma_commit_2cta(&bar_tfull[b], 0x3);
+              if (trace && blockIdx.x == 0 && i == 0 && c < 16) p.trace[1600 + c] = globaltimer_ns();
               if (c == P - 1)
                 for (int kbo = 0; kbo < nko; ++kbo) {
                   int so = s_o + kbo;
@@ -261,6 +275,7 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
                 }
             }
             __syncwarp();
+            if (b) ++used1; else ++used0;
           }
           s += nko;
           if (s >= nstages) { s -= nstages; ph ^= 1; }
@@ -272,11 +287,14 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int half = (warp - 4) >> 2;       // which half of the tile's output columns
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    uint8_t* epi_stage = smem + Cfg::PIPE_BYTES + 256 + 512 + (warp - 4) * kEpiStageBytes;
+    const uint32_t stage_sa = smem_u32(smem + Cfg::PIPE_BYTES + 256 + 512 + (warp - 4) * kEpiStageBytes);
+    const uint32_t gate_sa = smem_u32(smem + Cfg::PIPE_BYTES + 256 + 512 + q * kEpiStageBytes);   // staging tile of warp (q, half 0)
     __half* s_scale = reinterpret_cast<__half*>(smem + Cfg::PIPE_BYTES + 256 + 512 + Cfg::EPI_WARPS * kEpiStageBytes) + half * 256;
-    const uint32_t tempty = mapa_u32(smem_u32(&bar_tempty[0]), 0);
+    const uint32_t scale_sa = smem_u32(s_scale);
+    const uint32_t tempty0 = mapa_u32(smem_u32(&bar_tempty[0]), 0), tempty1 = mapa_u32(smem_u32(&bar_tempty[1]), 0);
     const int h1 = n1 >> 1;                 // output columns of this half that live in MMA chunk 1
-    uint32_t pass_idx = 0;                  // phase index of bar_tfull[0]
+    const int mode = (p.outl != nullptr || p.bias != nullptr || p.act == 1) ? 2 : (p.residual != nullptr ? 1 : 0);
+    uint32_t seen0 = 0, seen1 = 0;          // phase counters of bar_tfull[0] / [1]
     for (int i = 0; i < my_tiles; ++i) {
       const int tile = pair + i * npairs;
       const int m0 = (tile % MP) * 256 + static_cast<int>(rank) * 128 + q * 32;   // first row of this warp
@@ -293,39 +311,51 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
                              : make_uint4(0, 0, 0, 0);
       named_bar_sync(13 + half, 128);
 
-      for (int c = 0; c < P; ++c, ++pass_idx) {
-        mbar_wait_warp(&bar_tfull[0], pass_idx & 1, 5, c);
+      for (int c = 0; c < P; ++c) {
+        const int buf = c & 1;
+        mbar_wait_warp(&bar_tfull[buf], (buf ? seen1 : seen0) & 1, 5, c);
+        if (buf) ++seen1; else ++seen0;
         tc_fence_after();
-        if (trace && !p.fused_prologue && warp == 4 && lane == 0 && pass_idx == 0) trace[7] = globaltimer_ns();
+        if (trace && !p.fused_prologue && warp == 4 && lane == 0 && i == 0 && c == 0) trace[7] = globaltimer_ns();
+        if (trace && blockIdx.x == 0 && warp == 4 && lane == 0 && i == 0 && c < 16) p.trace[1536 + 2 * c] = globaltimer_ns();
         const int x0 = c * (R >> 1);                                   // this pass: output columns [x0, x1) of the half
         const int nc = (W - c * R) < R ? (W - c * R) : R;
         const int x1 = x0 + (nc >> 1);
-        const uint32_t t_outl = lane_base + static_cast<uint32_t>(W + half * (nc >> 1));
+        const uint32_t t_outl = lane_base + static_cast<uint32_t>(W + buf * R + half * (nc >> 1));
         // split the run where the int32 accumulator switches from MMA chunk 1 to chunk 2
         for (int part = 0; part < 2; ++part) {
           const int a = part == 0 ? x0 : (x0 > h1 ? x0 : h1);
           const int b = part == 0 ? (x1 < h1 ? x1 : h1) : x1;
           if (a >= b) continue;
           const uint32_t t_int = lane_base + static_cast<uint32_t>(part == 0 ? half * h1 + a : n1 + half * (n2 >> 1) + (a - h1));
+          const uint32_t t_o = t_outl + (a - x0);
+          const uint32_t sc = scale_sa + a * 2;
           if (pairm) {
-            uint8_t* gate_stage = smem + Cfg::PIPE_BYTES + 256 + 512 + q * kEpiStageBytes;   // staging tile of warp (q, half 0)
             if (half == 0) {
-              if (has_o) epilogue_run_swiglu<true, 0>(p, epi_stage, gate_stage, 1 + q, t_int, t_outl + (a - x0), m0, n0 + a, b - a, xs, s_scale + a, lane);
-              else epilogue_run_swiglu<false, 0>(p, epi_stage, gate_stage, 1 + q, t_int, 0u, m0, n0 + a, b - a, xs, s_scale + a, lane);
+              if (has_o) epilogue_run_swiglu<true, 0>(p, stage_sa, gate_sa, 1 + q, t_int, t_o, m0, n0 + a, b - a, xs, sc, lane);
+              else epilogue_run_swiglu<false, 0>(p, stage_sa, gate_sa, 1 + q, t_int, 0u, m0, n0 + a, b - a, xs, sc, lane);
             } else {
-              if (has_o) epilogue_run_swiglu<true, 1>(p, epi_stage, gate_stage, 1 + q, t_int, t_outl + (a - x0), m0, n0 + a, b - a, xs, s_scale + a, lane);
-              else epilogue_run_swiglu<false, 1>(p, epi_stage, gate_stage, 1 + q, t_int, 0u, m0, n0 + a, b - a, xs, s_scale + a, lane);
+              if (has_o) epilogue_run_swiglu<true, 1>(p, stage_sa, gate_sa, 1 + q, t_int, t_o, m0, n0 + a, b - a, xs, sc, lane);
+              else epilogue_run_swiglu<false, 1>(p, stage_sa, gate_sa, 1 + q, t_int, 0u, m0, n0 + a, b - a, xs, sc, lane);
             }
           } else if (p.epilogue == EPI_DEQUANT_F16) {
-            if (has_o) epilogue_run_coalesced<true>(p, epi_stage, t_int, t_outl + (a - x0), m0, n0 + a, b - a, xs, s_scale + a, lane);
-            else epilogue_run_coalesced<false>(p, epi_stage, t_int, 0u, m0, n0 + a, b - a, xs, s_scale + a, lane);
+            if (has_o) {
+              if (mode == 0) epilogue_run_coalesced<true, 0>(p, stage_sa, t_int, t_o, m0, n0 + a, b - a, xs, sc, lane);
+              else if (mode == 1) epilogue_run_coalesced<true, 1>(p, stage_sa, t_int, t_o, m0, n0 + a, b - a, xs, sc, lane);
+              else epilogue_run_coalesced<true, 2>(p, stage_sa, t_int, t_o, m0, n0 + a, b - a, xs, sc, lane);
+            } else {
+              if (mode == 0) epilogue_run_coalesced<false, 0>(p, stage_sa, t_int, 0u, m0, n0 + a, b - a, xs, sc, lane);
+              else if (mode == 1) epilogue_run_coalesced<false, 1>(p, stage_sa, t_int, 0u, m0, n0 + a, b - a, xs, sc, lane);
+              else epilogue_run_coalesced<false, 2>(p, stage_sa, t_int, 0u, m0, n0 + a, b - a, xs, sc, lane);
+            }
           } else {   // raw int32 accumulators (mixlib.gemm)
             epilogue_span<false>(p, t_int, 0u, row, row < p.M, n0 + a, b - a, xs, nullptr, 0);
           }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(tempty);
+        if (trace && blockIdx.x == 0 && warp == 4 && lane == 0 && i == 0 && c < 16) p.trace[1536 + 2 * c + 1] = globaltimer_ns();
+        if (lane == 0) mbar_arrive_cluster(buf ? tempty1 : tempty0);
       }
     }
     if (trace && warp == 4 && lane == 0) trace[5] = globaltimer_ns();

@@ -43,6 +43,12 @@ for (N, K) in SHAPES:
             return (f"{(v.min()-t0)/1e3:6.2f}..{(v.max()-t0)/1e3:6.2f}" if len(v) else "      -       ")
         print(f"N={N} K={K} tile={TILE} {mode:5s} us since first CTA start: start {col(0)} | mask built {col(6)} | row0 absmax {col(7)} | prologue done {col(1)} | barrier passed {col(2)} | "
               f"first MMA {col(3)} | int MMAs issued {col(6)} | last MMA {col(4)} | epilogue done {col(5)}")
+        base0 = t[0, 0]
+        pp = full[1536:1568].view(16, 2)
+        if pp[0, 0] > 0:
+            print("    CTA 0 warp 4 passes (start..end us): " + " ".join(f"{(a - base0) / 1e3:.2f}..{(b - base0) / 1e3:.2f}" for a, b in pp.tolist() if a > 0))
+            mm = full[1600:1616]
+            print("    CTA 0 outlier-pass MMA issue times: " + " ".join(f"{(a - base0) / 1e3:.2f}" for a in mm.tolist() if a > 0))
         ep = full[2048:2048 + 148 * 8 * 4].view(148 * 8, 4)
         if ep[:, 3].sum() > 0:   # built with EXTRA=-DMIXQ_EPI_PROFILE: clock64 sums per epilogue warp
             ok = ep[:, 3] > 0
