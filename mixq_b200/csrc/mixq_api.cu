@@ -124,6 +124,22 @@ int make_map(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int elt, l
   return 0;
 }
 
+// The [byte in k-atom (128), row, k-atom] view of a row-major int8 matrix [rows, K] (K % 128 == 0): a box of
+// 128 B x box_rows x atoms lands in shared memory as `atoms` consecutive SWIZZLE_128B tiles of box_rows x 128 B.
+int make_map_katoms(CUtensorMap* m, const void* ptr, long long K, long long rows, int box_rows, int atoms) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return fail(MIXQ_EDRIVER, "cuTensorMapEncodeTiled not available from the driver");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(MIXQ_EINVAL, "TMA operand not 16-byte aligned");
+  cuuint64_t gdim[3] = {128, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(K / 128)};
+  cuuint64_t gstr[2] = {static_cast<cuuint64_t>(K), 128};
+  cuuint32_t box[3] = {128, static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(atoms)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MIXQ_EDRIVER, "cuTensorMapEncodeTiled (3-D) failed (CUresult " + std::to_string(r) + ")");
+  return 0;
+}
+
 template <int BN, bool W4>
 int launch_linear(const LinearParams& p, int grid, bool cooperative, cudaStream_t st) {
   using Cfg = GemmCfg<BN, W4>;
@@ -274,11 +290,21 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
     return fail(MIXQ_EINVAL, "SwiGLU pair needs bit 8, M > 128, N % 16 == 0, both scale/weight_cache sets, no bias/residual/addend");
   // pair: a tile of width W holds W/2 gate columns (staged by CTA 0) and the SAME W/2 up columns (staged by CTA 1)
   int bn = two_cta ? pick_w2(c.tile_n, c.M, pair ? 2 * c.N : c.N, c.n_out, npairs) : pick_tile_n(c.tile_n, c.M, c.N, di.sms, c.n_out > 0);
-  int stage2 = Gemm2Cfg::A_BYTES + (bn / 2) * 128;
-  if (const char* e = getenv("MIXQ_DEBUG_STAGE_BYTES")) { const int v = atoi(e); if (v >= stage2 && v % 1024 == 0) stage2 = v; }
-  int nstages2 = Gemm2Cfg::PIPE_BYTES / stage2;
-  if (nstages2 > Gemm2Cfg::MAX_STAGES) nstages2 = Gemm2Cfg::MAX_STAGES;
-  if (const char* e = getenv("MIXQ_DEBUG_STAGES")) { const int v = atoi(e); if (v >= 2 && v < nstages2) nstages2 = v; }
+  // narrow tiles are paced by the TMA op count (one op ~340 clocks of the SM's TMA unit whatever its size): two k-atoms
+  // (256 bytes of K) per op and pipeline stage whenever at least three such stages fit
+  int k_atoms = (two_cta && c.K % 128 == 0 && c.K >= 256 && bn <= 256) ? 2 : 1;
+  if (const char* e = getenv("MIXQ_DEBUG_KATOMS")) { const int v = atoi(e); if (v == 1) k_atoms = 1; }
+  int stage2 = 0, nstages2 = 0;
+  for (;;) {
+    stage2 = k_atoms * (Gemm2Cfg::A_BYTES + (bn / 2) * 128);
+    if (const char* e = getenv("MIXQ_DEBUG_STAGE_BYTES")) { const int v = atoi(e); if (v >= stage2 && v % 1024 == 0) stage2 = v; }
+    nstages2 = Gemm2Cfg::PIPE_BYTES / stage2;
+    if (nstages2 > Gemm2Cfg::MAX_STAGES) nstages2 = Gemm2Cfg::MAX_STAGES;
+    if (const char* e = getenv("MIXQ_DEBUG_STAGES")) { const int v = atoi(e); if (v >= 2 && v < nstages2) nstages2 = v; }
+    // the outlier k-blocks of a tile stay resident in the ring during the epilogue passes: with the big stages they may not fit
+    if (k_atoms == 2 && (nstages2 < 3 || (c.n_out + 63) / 64 > nstages2 - 1)) { k_atoms = 1; continue; }
+    break;
+  }
   // the outlier k-blocks of a tile stay resident in the ring during the epilogue passes: they must all fit
   if (two_cta && (c.n_out + 63) / 64 > nstages2 - 1) {
     if (pair) return fail(MIXQ_EINVAL, "SwiGLU pair: too many outlier columns for the resident outlier stages");
@@ -288,10 +314,16 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
   const int b_rows = two_cta ? bn / 2 : bn;
 
   LinearParams p{};
-  if (int r = make_map(&p.tm_a, c.q_x, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, c.K, c.M, c.K, 128, 128,
-                       CU_TENSOR_MAP_SWIZZLE_128B))
+  const bool ka2 = two_cta && k_atoms == 2;
+  if (ka2) {
+    if (int r = make_map_katoms(&p.tm_a, c.q_x, c.K, c.M, 128, 2)) return r;
+    if (int r = make_map_katoms(&p.tm_b, c.q_w, c.K, c.N, b_rows, 2)) return r;
+  } else if (int r = make_map(&p.tm_a, c.q_x, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, c.K, c.M, c.K, 128, 128,
+                              CU_TENSOR_MAP_SWIZZLE_128B)) {
     return r;
-  if (w4) {
+  }
+  if (ka2) {
+  } else if (w4) {
     if (int r = make_map(&p.tm_b, c.q_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, c.K / 2, c.N, c.K / 2, 64, bn,
                          CU_TENSOR_MAP_SWIZZLE_NONE))
       return r;
@@ -309,8 +341,12 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
       return r;
   }
   if (pair) {
-    if (int r = make_map(&p.tm_b2, c.q_w_up, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, c.K, c.N, c.K, 128, b_rows, CU_TENSOR_MAP_SWIZZLE_128B))
+    if (ka2) {
+      if (int r = make_map_katoms(&p.tm_b2, c.q_w_up, c.K, c.N, b_rows, 2)) return r;
+    } else if (int r = make_map(&p.tm_b2, c.q_w_up, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, c.K, c.N, c.K, 128, b_rows,
+                                CU_TENSOR_MAP_SWIZZLE_128B)) {
       return r;
+    }
     if (c.n_out > 0)
       if (int r = make_map(&p.tm_ob2, c.weight_cache_up, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c.n_out, c.N,
                            static_cast<long long>(c.ld_wc) * 2, 64, b_rows, CU_TENSOR_MAP_SWIZZLE_128B))
@@ -359,6 +395,7 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
   p.bn = bn;
   p.nstages = nstages2;
   p.stage_bytes = stage2;
+  p.k_atoms = ka2 ? 2 : 1;
   p.q_w = static_cast<const uint8_t*>(c.q_w);
   p.q_w_pitch = w4 ? c.K / 2 : c.K;
   if (two_cta) {

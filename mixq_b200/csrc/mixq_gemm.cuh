@@ -34,7 +34,8 @@ struct LinearParams {
   uint32_t* grid_sync;
   int bn;              // 2-CTA kernel: run-time tile width W (multiple of 32, <= 512)
   int nstages;         // 2-CTA kernel: pipeline stages that fit PIPE_BYTES at this W
-  int stage_bytes;     // 2-CTA kernel: bytes between consecutive stages (>= 16 KB + W/2 * 128, multiple of 1024)
+  int stage_bytes;     // 2-CTA kernel: bytes between consecutive stages (>= k_atoms * (16 KB + W/2 * 128), multiple of 1024)
+  int k_atoms;         // 2-CTA kernel: 128-byte k-atoms per pipeline stage and TMA op (1, or 2 with 3-D tm_a / tm_b / tm_b2)
   const uint8_t* q_w;  // raw weight pointer + row pitch in bytes (L2 prefetch of the weight stream)
   long long q_w_pitch;
   unsigned long long* trace;  // optional [gridDim.x * 8] globaltimer stamps (mixq_set_trace_buffer), debug/tuning only

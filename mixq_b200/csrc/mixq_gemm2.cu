@@ -55,7 +55,11 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
   const int n2 = W - n1;
   const int stage_bytes = p.stage_bytes;
   const int nstages = p.nstages;
-  const int nk = (p.K + 127) / 128;                  // int8 k-blocks of 128
+  // One TMA op costs the SM's TMA unit ~340 clocks whatever its size (tools/tma_mc_bw.cu: 16 KB boxes land at 43 B/clk/SM,
+  // 32 KB boxes at 78), and a k-block needs two ops (activations, weights): narrow tiles, whose MMAs take < 700 clocks per
+  // k-block, are paced by the op count.  They therefore move KA = 2 k-atoms (256 bytes of K) per op and stage.
+  const int KA = p.k_atoms;
+  const int nk = (p.K + 128 * KA - 1) / (128 * KA);  // int8 pipeline items (KA k-atoms of 128 bytes each)
   const int nko = (p.n_out + 63) / 64;               // fp16 outlier k-blocks of 64 — the LAST items of a tile
   const int nkt = nk + nko;
   const int MP = (p.M + 255) / 256;
@@ -64,7 +68,8 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
   const int NT = (p.N + wout - 1) / wout;
   const int ntiles = MP * NT;
   const bool has_o = nko > 0;
-  const uint32_t stage_tx = 2u * static_cast<uint32_t>(Cfg::A_BYTES + bh * 128);   // both CTAs' bytes land on one barrier
+  const uint32_t atom_tx = 2u * static_cast<uint32_t>(Cfg::A_BYTES + bh * 128);    // both CTAs' bytes land on one barrier
+  const uint32_t b_atom = static_cast<uint32_t>(bh) * 128u;                         // bytes between the k-atoms of a weight stage
   // Outlier passes.  The fp32 accumulator of the skinny outlier GEMM gets what TMEM has left beside the int32 one: all W
   // columns when 2 W <= 512 (one pass), otherwise TWO buffers of R columns that the MMA warp and the epilogue warps
   // ping-pong (pass c + 1 is issued while pass c drains).  Passes are balanced (352 -> 6 x 64, not 5 x 64 + 32).
@@ -76,7 +81,7 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
   }
 
   auto stage_a = [&](int s) { return smem + static_cast<size_t>(s) * stage_bytes; };
-  auto stage_b = [&](int s) { return smem + static_cast<size_t>(s) * stage_bytes + Cfg::A_BYTES; };
+  auto stage_b = [&](int s) { return smem + static_cast<size_t>(s) * stage_bytes + static_cast<size_t>(KA) * Cfg::A_BYTES; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tm_a);
@@ -121,12 +126,18 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
     const CUtensorMap* tmb = (pairm && rank == 1) ? &p.tm_b2 : &p.tm_b;
     const CUtensorMap* tmob = (pairm && rank == 1) ? &p.tm_ob2 : &p.tm_ob;
     const uint32_t full_leader = mapa_u32(smem_u32(&bar_full[s]), 0);
-    if (arm && leader) mbar_arrive_expect_tx(&bar_full[s], stage_tx);
     if (kb < nk) {
-      const int k0 = kb * 128;
-      if (do_wgt) tma_load_2d_2cta(tmb, full_leader, stage_b(s), k0, n0, kEvictFirst);
-      if (do_act) tma_load_2d_2cta(&p.tm_a, full_leader, stage_a(s), k0, m0, kEvictLast);
+      if (arm && leader) mbar_arrive_expect_tx(&bar_full[s], atom_tx * static_cast<uint32_t>(KA));
+      if (KA == 1) {
+        const int k0 = kb * 128;
+        if (do_wgt) tma_load_2d_2cta(tmb, full_leader, stage_b(s), k0, n0, kEvictFirst);
+        if (do_act) tma_load_2d_2cta(&p.tm_a, full_leader, stage_a(s), k0, m0, kEvictLast);
+      } else {   // atoms past the end of K are out of bounds of the 3-D view: zero-filled, counted, and harmless in the MMA
+        if (do_wgt) tma_load_3d_2cta(tmb, full_leader, stage_b(s), 0, n0, kb * KA, kEvictFirst);
+        if (do_act) tma_load_3d_2cta(&p.tm_a, full_leader, stage_a(s), 0, m0, kb * KA, kEvictLast);
+      }
     } else {
+      if (arm && leader) mbar_arrive_expect_tx(&bar_full[s], atom_tx);
       const int ko = (kb - nk) * 64;
       if (do_wgt) tma_load_2d_2cta(tmob, full_leader, stage_b(s), ko, n0, kEvictFirst);
       if (do_act) tma_load_2d_2cta(&p.tm_oa, full_leader, stage_a(s), ko, m0, kEvictLast);
@@ -159,7 +170,7 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
     rowquant_run(p.rq, rq_sm, rowbuf);
     if (trace && threadIdx.x == 0) trace[1] = globaltimer_ns();
     fence_proxy_async_all();   // q_x / act_outliers were written through the generic proxy; TMA reads them next
-    grid_barrier(p.grid_sync);
+    grid_barrier(p.grid_sync, p.trace ? p.trace + 1700 + static_cast<size_t>(blockIdx.x) * 4 : nullptr);
     if (trace && threadIdx.x == 0) trace[2] = globaltimer_ns();
   }
 
@@ -221,10 +232,14 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
           if (elect_one()) {
             if (trace && i == 0 && kb == 0) trace[3] = globaltimer_ns();
             const uint32_t first = (kb == 0) ? 0u : 1u;
+            for (int a = 0; a < KA; ++a) {
+              const uint64_t daa = da + static_cast<uint64_t>(a) * (Cfg::A_BYTES >> 4);
+              const uint64_t dba = db + static_cast<uint64_t>(a) * (b_atom >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {   // 4 x (K = 32 int8 = 32 B); +2 in the >>4-encoded start address
-              umma_i8_2cta(d1, da + 2 * k, db + 2 * k, idesc_i8_1, first | k);
-              if (two) umma_i8_2cta(d2, da + 2 * k, db + b2_off + 2 * k, idesc_i8_2, first | k);
+              for (int k = 0; k < 4; ++k) {   // 4 x (K = 32 int8 = 32 B); +2 in the >>4-encoded start address
+                umma_i8_2cta(d1, daa + 2 * k, dba + 2 * k, idesc_i8_1, first | a | k);
+                if (two) umma_i8_2cta(d2, daa + 2 * k, dba + b2_off + 2 * k, idesc_i8_2, first | a | k);
+              }
             }
             umma_commit_2cta(&bar_empty[s], 0x3);
           }

@@ -266,17 +266,21 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
 // Sense-reversing grid barrier on one 32-bit word that never needs resetting: block 0 adds
 // 0x80000000 - (grid-1), every other block adds 1, so each use flips the top bit exactly once.
 // Callers must guarantee co-residency of the whole grid (cooperative launch).
-__device__ __forceinline__ void grid_barrier(uint32_t* word) {
+__device__ __forceinline__ void grid_barrier(uint32_t* word, unsigned long long* dbg = nullptr) {
   __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t add = (blockIdx.x == 0) ? (0x80000000u - (gridDim.x - 1)) : 1u;
+    if (dbg) dbg[0] = globaltimer_ns();
     __threadfence();
+    if (dbg) dbg[1] = globaltimer_ns();
     uint32_t old = atomicAdd(word, add);
+    if (dbg) dbg[2] = globaltimer_ns();
     uint64_t t0 = globaltimer_ns();
     uint32_t spins = 0;
     while (((old ^ ld_acquire_u32(word)) & 0x80000000u) == 0) {
       if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > MIXQ_SPIN_TIMEOUT_NS) spin_timeout_trap(9, 0, 0);
     }
+    if (dbg) dbg[3] = globaltimer_ns();
     __threadfence();
   }
   __syncthreads();
@@ -326,6 +330,17 @@ __device__ __forceinline__ void tma_load_2d_2cta(const CUtensorMap* m, uint32_t 
       " [%0], [%1, {%3, %4}], [%2], %5;"
       :
       : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+// 3-D box {c0, c1, c2} (the [bytes in a 128 B k-atom, row, k-atom] view of a row-major int8 matrix): one op brings
+// several k-atoms of the same rows, landing as [atom][row][128 B].
+__device__ __forceinline__ void tma_load_3d_2cta(const CUtensorMap* m, uint32_t bar_cluster_addr, void* smem_dst, int c0, int c1,
+                                                 int c2, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
       : "memory");
 }
 // D[tmem, 256 x N over the CTA pair] (+)= A * B^T; issued by one thread of the pair's leader CTA.

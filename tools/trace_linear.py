@@ -49,6 +49,10 @@ for (N, K) in SHAPES:
             print("    CTA 0 warp 4 passes (start..end us): " + " ".join(f"{(a - base0) / 1e3:.2f}..{(b - base0) / 1e3:.2f}" for a, b in pp.tolist() if a > 0))
             mm = full[1600:1616]
             print("    CTA 0 outlier-pass MMA issue times: " + " ".join(f"{(a - base0) / 1e3:.2f}" for a in mm.tolist() if a > 0))
+        gb = full[1700:1700 + 148 * 4].view(148, 4)
+        if gb[:, 0].sum() > 0:
+            f = lambda i: f"{(gb[:, i].min() - t0) / 1e3:.2f}..{(gb[:, i].max() - t0) / 1e3:.2f}"
+            print(f"    grid barrier (all CTAs, us): enter {f(0)} | fence done {f(1)} | atomic done {f(2)} | flip seen {f(3)}")
         ep = full[2048:2048 + 148 * 8 * 4].view(148 * 8, 4)
         if ep[:, 3].sum() > 0:   # built with EXTRA=-DMIXQ_EPI_PROFILE: clock64 sums per epilogue warp
             ok = ep[:, 3] > 0
