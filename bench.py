@@ -280,24 +280,30 @@ def run_mixq(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
 
-    # ---- roofline of the dominant kernel (mixq_linear_kernel): per-launch CUDA-event time over all layers' distinct weights
+    # ---- roofline of the dominant kernel (mixq_linear2_kernel: every MixLinear launch of the step): per-launch CUDA-event
+    # time of each of the step's Linear launches, taken over all layers' distinct weights
     pk = peaks()
-    kinds = ["W_pack", "o_proj", "up_proj", "gate_proj", "down_proj"]
+    pair = model.fuse_swiglu
+    kinds = ["W_pack", "o_proj"] + (["swiglu_pair"] if pair else ["up_proj", "gate_proj"]) + ["down_proj"]
     h = torch.randn(B, cfg.hidden, device="cuda").half()
     per_kind = {}
     tot_t = tot_fl = tot_by = 0.0
     for kind in kinds:
-        mods = [L[kind] for L in model.layers]
+        mods = [L["gate_proj" if kind == "swiglu_pair" else kind] for L in model.layers]
+        ups = [L["up_proj"] for L in model.layers]
         K_in = mods[0].in_features
         xin = torch.randn(B, K_in, device="cuda").half()
         xw = xin.clone()
 
-        def launch(m):
+        def launch(i):
+            m = mods[i]
             if kind in ("W_pack", "up_proj"):
                 return m.forward_norm_fused(h, model.layers[0]["ln1"], cfg.eps)
+            if kind == "swiglu_pair":
+                return m.forward_swiglu_fused(ups[i], h, model.layers[0]["ln2"], cfg.eps)
             if kind == "gate_proj":
                 return m.forward_without_preconditionFusedSilu(h, model.cache)
-            return m(xw, None, True)
+            return m(xw, None, True, residual=h) if world == 1 else m(xw, None, True)
         if kind == "gate_proj":   # needs up_proj's q_x in the cache
             model.layers[0]["up_proj"].forward_norm_fused(h, model.layers[0]["ln2"], cfg.eps)
         # one CUDA graph holding this Linear of every layer (distinct weights: L2-cold, as in the step), so that the
@@ -305,14 +311,14 @@ def run_mixq(args):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for m in mods[:3]:
-                launch(m)
+            for i in range(min(3, len(mods))):
+                launch(i)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         gk = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gk):
-            for m in mods:
-                launch(m)
+            for i in range(len(mods)):
+                launch(i)
         gk.replay()
         torch.cuda.synchronize()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -326,9 +332,10 @@ def run_mixq(args):
         t_launch = g0.elapsed_time(g1) * 1e-3 / (reps * len(mods))
         m0 = mods[0]
         N_, n_ = m0.out_features, m0._n_ind
-        fl = 2.0 * B * N_ * K_in
-        by = N_ * K_in * m0.bit / 8 + 2 * B * K_in + 2 * B * N_ + 2 * N_ + 2 * n_ * N_
-        per_kind[kind] = {"N": N_, "K": K_in, "n_outliers": n_, "us": t_launch * 1e6, "tflops": fl / t_launch / 1e12,
+        nlin = 2 if kind == "swiglu_pair" else 1      # the pair launch holds two Linears (and writes one y)
+        fl = 2.0 * B * N_ * K_in * nlin
+        by = nlin * (N_ * K_in * m0.bit / 8 + 2 * N_ + 2 * n_ * N_) + 2 * B * K_in + 2 * B * N_
+        per_kind[kind] = {"N": N_, "K": K_in, "n_outliers": n_, "linears": nlin, "us": t_launch * 1e6, "tflops": fl / t_launch / 1e12,
                           "gbs": by / t_launch / 1e9}
         tot_t += t_launch
         tot_fl += fl
@@ -336,13 +343,21 @@ def run_mixq(args):
     int8_peak = 2.0 * pk["bf16_sustained"]
     ach_tf, ach_gb = tot_fl / tot_t / 1e12, tot_by / tot_t / 1e9
     tensor_bound = (tot_fl / (int8_peak * 1e12)) >= (tot_by / (pk["hbm_gbs"] * 1e9))
+    # DRAM bytes per launch from the committed `ncu --set full` capture of the same four launches (profiles/)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath) and world == 1 and args.model == "llama-2-7b" and args.bit == 8 and B == 512:
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj["dram_bytes_per_launch_avg"], tj["source"]
     roofline = {
-        "kernel": "mixq_linear_kernel (5 launches per layer: W_pack, o_proj, up_proj, gate_proj, down_proj)",
+        "kernel": f"mixq_linear2_kernel ({len(kinds)} launches per layer: " + ", ".join(kinds) + ")",
         "bound": "tensor" if tensor_bound else "hbm",
         "achieved": ach_tf if tensor_bound else ach_gb, "peak": int8_peak if tensor_bound else pk["hbm_gbs"],
         "unit": "TFLOP/s" if tensor_bound else "GB/s",
         "frac": (ach_tf / int8_peak) if tensor_bound else (ach_gb / pk["hbm_gbs"]),
-        "traffic": None,
+        "traffic": traffic, "traffic_source": traffic_src,
+        "algorithmic_bytes_per_launch_avg": tot_by / len(kinds), "algorithmic_flops_per_launch_avg": tot_fl / len(kinds),
+        "avg_launch_us": tot_t / len(kinds) * 1e6,
         "peak_source": f"{pk['source']}: int8 tensor pipe taken as 2 x bf16_tflops_sustained ({pk['bf16_sustained']}); hbm_gbs {pk['hbm_gbs']}",
         "other_bound": {"tflops": ach_tf, "frac_int8": ach_tf / int8_peak, "gbs": ach_gb, "frac_hbm": ach_gb / pk["hbm_gbs"]},
         "per_linear": per_kind, "linear_share_of_step": tot_t * len(model.layers) / (ms * 1e-3 / args.steps),
@@ -360,7 +375,7 @@ def run_mixq(args):
                        "layers": len(model.layers), "global_batch": B, "parallelism": f"tp{world}", "bit": args.bit,
                        "l2": "weights (>= 6 GB per step) exceed the 126 MB L2: inputs larger than L2, no flush",
                        "outliers_layer0": {k: m._n_ind for k, m in model.layers[0].items() if isinstance(m, MixLinear_GEMM)},
-                       "cuda_graph": True},
+                       "cuda_graph": True, "programmatic_dependent_launch": True},
             "e2e": {"value": B / (ms_e2e * 1e-3 / args.steps), "unit": "tokens/s", "h2d_bytes_per_step": B * 8,
                     "d2h_bytes_per_step": B * 8, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,

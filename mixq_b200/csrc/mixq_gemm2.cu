@@ -194,6 +194,7 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
           } else {
             produce(tile, kb, s, true, false, false);
           }
+          if (p.trace && blockIdx.x == 0 && it < 48) p.trace[2048 + (wgt ? 256 : 512) + it] = globaltimer_ns();
         }
         __syncwarp();
         if (++s == nstages) { s = 0; ph ^= 1; }
@@ -231,6 +232,7 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
           const uint64_t db = make_sw128_kmajor_desc(smem_u32(stage_b(s)));
           if (elect_one()) {
             if (trace && i == 0 && kb == 0) trace[3] = globaltimer_ns();
+            if (trace && blockIdx.x == 0 && i == 0 && kb < 48) p.trace[2048 + kb] = globaltimer_ns();
             const uint32_t first = (kb == 0) ? 0u : 1u;
             for (int a = 0; a < KA; ++a) {
               const uint64_t daa = da + static_cast<uint64_t>(a) * (Cfg::A_BYTES >> 4);

@@ -439,6 +439,48 @@ def test_linear_fused_swiglu_pair(lib, M, N, K, n, norm):
     rel_close(host(t["y"]), ref, "silu(gate) * up", 2e-3 if n == 0 else REL_TOL)
 
 
+@pytest.mark.parametrize("M,N,K,n", [(512, 1024, 4096, 41), (300, 2048, 1024, 0), (512, 4096, 2048, 130)])
+def test_linear_fused_residual_only(lib, M, N, K, n):
+    """The decoder's o_proj / down_proj call: residual add, no bias (the epilogue's staged-residual variant)."""
+    rng = np.random.default_rng(7 * M + N + n)
+    x, cols = make_x(rng, M, K, n)
+    W = (rng.standard_normal((N, K)) * 0.02).astype(np.float16)
+    qw, ws = O.quant_weight_w8(W)
+    wc = O.weight_cache_columns(qw, ws, cols, 8)
+    res = rng.standard_normal((M, N)).astype(np.float16)
+    t = run_fused(lib, x, qw, ws, cols, wc, 8, residual=res)
+    r = oracle_fused(x, qw, ws, cols, wc, 8, residual=res)
+    bits_equal(host(t["q_x"]), r["q_x"], "q_x")
+    if n:
+        rel_close(host(t["y"]), r["y"], "y")
+    else:
+        bits_equal(host(t["y"]), r["y"], "y (no outliers: bit-exact)")
+
+
+def test_launch_modes_bit_identical(lib, monkeypatch):
+    """Programmatic dependent launch on/off and one/two k-atoms per TMA op are scheduling choices: y must not change."""
+    M, N, K, n = 512, 1024, 4096, 41
+    rng = np.random.default_rng(3)
+    x, cols = make_x(rng, M, K, n)
+    W = (rng.standard_normal((N, K)) * 0.02).astype(np.float16)
+    qw, ws = O.quant_weight_w8(W)
+    wc = O.weight_cache_columns(qw, ws, cols, 8)
+    res = rng.standard_normal((M, N)).astype(np.float16)
+    ys = []
+    try:
+        for pdl, katoms in ((1, None), (0, None), (1, "1"), (0, "1")):
+            check(lib.mixq_set_pdl(pdl))
+            if katoms is None:
+                monkeypatch.delenv("MIXQ_DEBUG_KATOMS", raising=False)
+            else:
+                monkeypatch.setenv("MIXQ_DEBUG_KATOMS", katoms)
+            ys.append(host(run_fused(lib, x, qw, ws, cols, wc, 8, residual=res)["y"]))
+    finally:
+        check(lib.mixq_set_pdl(1))
+    for y in ys[1:]:
+        bits_equal(y, ys[0], "y across launch modes")
+
+
 # ----------------------------------------------------------------------------- properties at BASELINE.json sizes
 @pytest.mark.parametrize("N,K", [(12288, 4096), (4096, 4096), (11008, 4096), (4096, 11008)])
 def test_full_size_properties(lib, N, K):

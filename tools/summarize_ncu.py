@@ -47,13 +47,24 @@ if os.path.exists(rep):
             "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
             "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
             "smsp__cycles_active.avg", "sm__cycles_elapsed.max"]
-    names = ["W_pack", "o_proj", "up_proj", "gate_proj", "down_proj"]
+    names = ["W_pack", "o_proj", "swiglu_pair", "down_proj"] if len(data) == 4 else ["W_pack", "o_proj", "up_proj", "gate_proj", "down_proj"]
     out += ["## `ncu --set full` of the MixLinear kernel, layer 0 (one launch each)", "",
             "| metric | unit | " + " | ".join(names[: len(data)]) + " |", "|---|---|" + "---:|" * len(data)]
     for w in want:
         if w in idx:
             out.append(f"| `{w}` | {units[idx[w]]} | " + " | ".join(r[idx[w]] for r in data) + " |")
     out.append("")
+    # DRAM bytes per launch for bench.py's roofline.traffic (average over the Linear launches of one layer)
+    import json
+    rd = [float(r[idx["dram__bytes_read.sum"]].replace(",", "")) for r in data]
+    wr = [float(r[idx["dram__bytes_write.sum"]].replace(",", "")) for r in data]
+    scale = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
+    ru, wu = scale[units[idx["dram__bytes_read.sum"]]], scale[units[idx["dram__bytes_write.sum"]]]
+    per = [a * ru + b * wu for a, b in zip(rd, wr)]
+    json.dump({"dram_bytes_per_launch_avg": sum(per) / len(per), "dram_bytes_per_launch": dict(zip(names, per)),
+               "source": f"profiles/{tag}_ncu_summary.md: ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, "
+                         f"one launch each of {', '.join(names[:len(per)])} (Llama-2-7B layer 0, batch 512)"},
+              open("profiles/ncu_traffic.json", "w"), indent=1)
 bl = f"gpurun_out/{tag}_bench_linear.jsonl"
 if os.path.exists(bl):
     out += ["## tools/bench_linear.py (CUDA-event times, graph of 12 launches on distinct weights, NOT under ncu)", "", "```"]

@@ -61,7 +61,7 @@ for (N, K) in SHAPES:
         if os.environ.get("CADENCE"):
             base = t[0, 0]
             for name, off in (("mma", 2048), ("wgt-tma", 2048 + 256), ("act-tma", 2048 + 512)):
-                v = full[off:off + 40]
+                v = full[off:off + 48]
                 v = v[v > 0]
                 print("   ", name, " ".join(f"{(x - base) / 1e3:.2f}" for x in v.tolist()))
 lib.mixq_set_trace_buffer(0)
