@@ -231,127 +231,125 @@ __device__ __forceinline__ float2 dequant2(uint32_t a0, uint32_t a1, uint32_t o0
   return v;
 }
 
-// One contiguous run of `ncols` (multiple of 16) output columns of a tile for the 32 rows of this warp:
-//   y = act(fp16((f32(acc_int) * xs) * ws + fp16(acc_outl) [+ addend])) [+ bias] [+ residual]
-// t_int / t_outl: TMEM addresses (lane quarter included) of the first int32 / fp32-outlier accumulator column of the run
-// (t_outl unused when !HAS_O); scale_sa: shared-window address of scale_col (fp16) of the run's first column.
-// MODE 0: nothing else.  MODE 1: + residual (staged in through the tile).  MODE 2: any of addend / bias / residual / SiLU.
-template <bool HAS_O, int MODE>
-__device__ __forceinline__ void epilogue_run_coalesced(const LinearParams& p, uint32_t stage_sa, uint32_t t_int, uint32_t t_outl,
-                                                       int m_base, int n0, int ncols, float xs, uint32_t scale_sa, int lane) {
+// 16 accumulator columns of one row -> two 16-byte chunks of the staging tile.
+template <bool HAS_O, int MODE, int OFF, int NA>
+__device__ __forceinline__ void epilogue_group16(const LinearParams& p, const uint32_t (&acc)[NA], const uint32_t (&oacc)[NA],
+                                                 float xs, uint32_t scale_sa16, uint32_t row_sa, uint32_t sw, int chunk0, int row,
+                                                 bool row_ok, int n16) {
   const bool has_add = MODE == 2 && p.outl != nullptr;
   const bool has_bias = MODE == 2 && p.bias != nullptr;
   const bool has_res = MODE == 2 && p.residual != nullptr;
   const bool silu = MODE == 2 && p.act == 1;
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const uint4 wsu = lds128(scale_sa16 + g * 16);
+    const uint32_t slot = row_sa + (((chunk0 + g) ^ sw) << 4);
+    const uint32_t wsw[4] = {wsu.x, wsu.y, wsu.z, wsu.w};
+    uint32_t ow[4];
+    if (MODE == 0) {
+#pragma unroll
+      for (int j2 = 0; j2 < 4; ++j2) {
+        const int cc = OFF + g * 8 + j2 * 2;
+        const float2 v = dequant2<HAS_O>(acc[cc], acc[cc + 1], oacc[cc], oacc[cc + 1], xs, wsw[j2]);
+        const __half2 o2 = __floats2half2_rn(v.x, v.y);
+        ow[j2] = *reinterpret_cast<const uint32_t*>(&o2);
+      }
+    } else if (MODE == 1) {
+      const uint4 rsu = lds128(slot);
+      const uint32_t rsw[4] = {rsu.x, rsu.y, rsu.z, rsu.w};
+#pragma unroll
+      for (int j2 = 0; j2 < 4; ++j2) {
+        const int cc = OFF + g * 8 + j2 * 2;
+        const float2 v = dequant2<HAS_O>(acc[cc], acc[cc + 1], oacc[cc], oacc[cc + 1], xs, wsw[j2]);
+        // the decoder's residual add is a separate fp16 op in the reference: round, then add in fp32, round again
+        const __half2 o2 = hadd2_via_f32(__floats2half2_rn(v.x, v.y), *reinterpret_cast<const __half2*>(&rsw[j2]));
+        ow[j2] = *reinterpret_cast<const uint32_t*>(&o2);
+      }
+    } else {
+      const int ng = n16 + g * 8;
+      const bool ok = row_ok && ng < p.N;
+      uint4 olu = make_uint4(0, 0, 0, 0), bsu = make_uint4(0, 0, 0, 0), rsu = make_uint4(0, 0, 0, 0);
+      if (has_add) olu = lds128(slot);
+      if (has_bias && ng < p.N) bsu = __ldg(reinterpret_cast<const uint4*>(p.bias + ng));
+      if (has_res && ok) rsu = *reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(row) * p.ld_res + ng);
+      const uint32_t olw[4] = {olu.x, olu.y, olu.z, olu.w};
+      const uint32_t bsw[4] = {bsu.x, bsu.y, bsu.z, bsu.w};
+      const uint32_t rsw[4] = {rsu.x, rsu.y, rsu.z, rsu.w};
+#pragma unroll
+      for (int j2 = 0; j2 < 4; ++j2) {
+        const int cc = OFF + g * 8 + j2 * 2;
+        float2 v = dequant2<HAS_O>(acc[cc], acc[cc + 1], oacc[cc], oacc[cc + 1], xs, wsw[j2]);
+        if (has_add) {
+          const float2 of = __half22float2(*reinterpret_cast<const __half2*>(&olw[j2]));
+          v.x = __fadd_rn(v.x, of.x);
+          v.y = __fadd_rn(v.y, of.y);
+        }
+        if (silu) {
+          v.x = silu_f(v.x);
+          v.y = silu_f(v.y);
+        }
+        __half2 o2 = __floats2half2_rn(v.x, v.y);
+        // y1 += bias (linear.py:284-285) and the residual add are separate fp16 ops in the reference
+        if (has_bias) o2 = hadd2_via_f32(o2, *reinterpret_cast<const __half2*>(&bsw[j2]));
+        if (has_res) o2 = hadd2_via_f32(o2, *reinterpret_cast<const __half2*>(&rsw[j2]));
+        ow[j2] = *reinterpret_cast<const uint32_t*>(&o2);
+      }
+    }
+    sts128(slot, make_uint4(ow[0], ow[1], ow[2], ow[3]));
+  }
+}
+
+// One contiguous run of `ncols` (multiple of 16) output columns of a tile for the 32 rows of this warp:
+//   y = act(fp16((f32(acc_int) * xs) * ws + fp16(acc_outl) [+ addend])) [+ bias] [+ residual]
+// t_int / t_outl: TMEM addresses (lane quarter included) of the first int32 / fp32-outlier accumulator column of the run
+// (t_outl unused when !HAS_O); scale_sa: shared-window address of scale_col (fp16) of the run's first column.
+// MODE 0: nothing else.  MODE 1: + residual (staged in through the tile; `pre_staged`: the caller already brought the
+// first 64-column block in while it waited for the accumulator).  MODE 2: any of addend / bias / residual / SiLU.
+// Without outliers the accumulator is read 32 columns per tcgen05.ld / wait (half the exposed round trips; a software-
+// pipelined second register set was tried: ptxas keeps it in local memory).
+template <bool HAS_O, int MODE>
+__device__ __forceinline__ void epilogue_run_coalesced(const LinearParams& p, uint32_t stage_sa, uint32_t t_int, uint32_t t_outl,
+                                                       int m_base, int n0, int ncols, float xs, uint32_t scale_sa, int lane,
+                                                       bool pre_staged = false) {
+  const bool has_add = MODE == 2 && p.outl != nullptr;
   const int row = m_base + lane;
   const bool row_ok = row < p.M;
   const uint32_t row_sa = stage_sa + lane * 128;
   const uint32_t sw = lane & 7;
-#ifdef MIXQ_EPI_PROFILE
-  long long t_ld = 0, t_math = 0, t_out = 0, t_a, t_b;
-#define EPI_T(x) x = clock64()
-#else
-#define EPI_T(x)
-#endif
+  const int ngroups = ncols >> 4;
 #pragma unroll 1
-  for (int b = 0; b < ncols; b += 64) {
-    const int bc = (ncols - b < 64) ? (ncols - b) : 64;
-    if (MODE == 1) {
-      epi_stage_in(stage_sa, p.residual, p.ld_res, m_base, n0 + b, bc >> 3, p.M, p.N, lane);
-      __syncwarp();
-    } else if (has_add) {
-      epi_stage_in(stage_sa, p.outl, p.ld_outl, m_base, n0 + b, bc >> 3, p.M, p.N, lane);
-      __syncwarp();
+  for (int g = 0; g < ngroups; g += 2) {
+    if ((g & 3) == 0) {     // first group of a 64-column block: bring the residual / addend tile in
+      const int bc = (ncols - g * 16 < 64) ? (ncols - g * 16) : 64;
+      if (MODE == 1 && !(pre_staged && g == 0)) epi_stage_in(stage_sa, p.residual, p.ld_res, m_base, n0 + g * 16, bc >> 3, p.M, p.N, lane);
+      else if (has_add) epi_stage_in(stage_sa, p.outl, p.ld_outl, m_base, n0 + g * 16, bc >> 3, p.M, p.N, lane);
+      if (MODE == 1 || has_add) __syncwarp();
     }
-#pragma unroll 1
-    for (int c = 0; c < bc; c += 16) {
-      uint32_t acc[16];
-      uint32_t oacc[16];
-      EPI_T(t_a);
-      tmem_ld_32x16(t_int + b + c, acc);
-      if (HAS_O) tmem_ld_32x16(t_outl + b + c, oacc);
+    const bool two = g + 1 < ngroups;
+    if (!HAS_O && two && !(p.ablate & 8)) {
+      uint32_t acc[32];
+      tmem_ld_32x32(t_int + g * 16, acc);
       tmem_ld_wait();
-#ifdef MIXQ_EPI_PROFILE
-      EPI_T(t_b); t_ld += t_b - t_a;
-#endif
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        const uint4 wsu = lds128(scale_sa + (b + c + g * 8) * 2);
-        const uint32_t slot = row_sa + ((((c >> 3) + g) ^ sw) << 4);
-        const uint32_t wsw[4] = {wsu.x, wsu.y, wsu.z, wsu.w};
-        uint32_t ow[4];
-        if (MODE == 0) {
-#pragma unroll
-          for (int j2 = 0; j2 < 4; ++j2) {
-            const int cc = g * 8 + j2 * 2;
-            const float2 v = dequant2<HAS_O>(acc[cc], acc[cc + 1], oacc[cc], oacc[cc + 1], xs, wsw[j2]);
-            const __half2 o2 = __floats2half2_rn(v.x, v.y);
-            ow[j2] = *reinterpret_cast<const uint32_t*>(&o2);
-          }
-        } else if (MODE == 1) {
-          const uint4 rsu = lds128(slot);
-          const uint32_t rsw[4] = {rsu.x, rsu.y, rsu.z, rsu.w};
-#pragma unroll
-          for (int j2 = 0; j2 < 4; ++j2) {
-            const int cc = g * 8 + j2 * 2;
-            const float2 v = dequant2<HAS_O>(acc[cc], acc[cc + 1], oacc[cc], oacc[cc + 1], xs, wsw[j2]);
-            // the decoder's residual add is a separate fp16 op in the reference: round, then add in fp32, round again
-            const __half2 o2 = hadd2_via_f32(__floats2half2_rn(v.x, v.y), *reinterpret_cast<const __half2*>(&rsw[j2]));
-            ow[j2] = *reinterpret_cast<const uint32_t*>(&o2);
-          }
-        } else {
-          const int ng = n0 + b + c + g * 8;
-          const bool ok = row_ok && ng < p.N;
-          uint4 olu = make_uint4(0, 0, 0, 0), bsu = make_uint4(0, 0, 0, 0), rsu = make_uint4(0, 0, 0, 0);
-          if (has_add) olu = lds128(slot);
-          if (has_bias && ng < p.N) bsu = __ldg(reinterpret_cast<const uint4*>(p.bias + ng));
-          if (has_res && ok) rsu = *reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(row) * p.ld_res + ng);
-          const uint32_t olw[4] = {olu.x, olu.y, olu.z, olu.w};
-          const uint32_t bsw[4] = {bsu.x, bsu.y, bsu.z, bsu.w};
-          const uint32_t rsw[4] = {rsu.x, rsu.y, rsu.z, rsu.w};
-#pragma unroll
-          for (int j2 = 0; j2 < 4; ++j2) {
-            const int cc = g * 8 + j2 * 2;
-            float2 v = dequant2<HAS_O>(acc[cc], acc[cc + 1], oacc[cc], oacc[cc + 1], xs, wsw[j2]);
-            if (has_add) {
-              const float2 of = __half22float2(*reinterpret_cast<const __half2*>(&olw[j2]));
-              v.x = __fadd_rn(v.x, of.x);
-              v.y = __fadd_rn(v.y, of.y);
-            }
-            if (silu) {
-              v.x = silu_f(v.x);
-              v.y = silu_f(v.y);
-            }
-            __half2 o2 = __floats2half2_rn(v.x, v.y);
-            // y1 += bias (linear.py:284-285) and the residual add are separate fp16 ops in the reference
-            if (has_bias) o2 = hadd2_via_f32(o2, *reinterpret_cast<const __half2*>(&bsw[j2]));
-            if (has_res) o2 = hadd2_via_f32(o2, *reinterpret_cast<const __half2*>(&rsw[j2]));
-            ow[j2] = *reinterpret_cast<const uint32_t*>(&o2);
-          }
-        }
-        sts128(slot, make_uint4(ow[0], ow[1], ow[2], ow[3]));
+      epilogue_group16<false, MODE, 0, 32>(p, acc, acc, xs, scale_sa + g * 32, row_sa, sw, (g & 3) * 2, row, row_ok, n0 + g * 16);
+      epilogue_group16<false, MODE, 16, 32>(p, acc, acc, xs, scale_sa + (g + 1) * 32, row_sa, sw, ((g + 1) & 3) * 2, row, row_ok, n0 + (g + 1) * 16);
+    } else {
+#pragma unroll 1
+      for (int h = 0; h < (two ? 2 : 1); ++h) {
+        uint32_t acc[16];
+        uint32_t oacc[16];
+        tmem_ld_32x16(t_int + (g + h) * 16, acc);
+        if (HAS_O) tmem_ld_32x16(t_outl + (g + h) * 16, oacc);
+        tmem_ld_wait();
+        epilogue_group16<HAS_O, MODE, 0, 16>(p, acc, oacc, xs, scale_sa + (g + h) * 32, row_sa, sw, ((g + h) & 3) * 2, row, row_ok, n0 + (g + h) * 16);
       }
-#ifdef MIXQ_EPI_PROFILE
-      EPI_T(t_a); t_math += t_a - t_b;
-#endif
     }
-    __syncwarp();
-    EPI_T(t_a);
-    epi_stage_out(stage_sa, p.y, p.N, m_base, n0 + b, bc >> 3, p.M, p.N, lane);
-    __syncwarp();
-#ifdef MIXQ_EPI_PROFILE
-    EPI_T(t_b); t_out += t_b - t_a;
-#endif
+    const int last = two ? g + 1 : g;
+    if ((last & 3) == 3 || last == ngroups - 1) {   // block complete (or run finished): 64 columns out, coalesced
+      __syncwarp();
+      epi_stage_out(stage_sa, p.y, p.N, m_base, n0 + (g & ~3) * 16, ((last & 3) + 1) * 2, p.M, p.N, lane);
+      __syncwarp();
+    }
   }
-#ifdef MIXQ_EPI_PROFILE
-  if (p.trace && lane == 0) {
-    unsigned long long* t = p.trace + 2048 + (static_cast<size_t>(blockIdx.x) * 8 + ((threadIdx.x >> 5) - 4)) * 4;
-    atomicAdd(t + 0, static_cast<unsigned long long>(t_ld));
-    atomicAdd(t + 1, static_cast<unsigned long long>(t_math));
-    atomicAdd(t + 2, static_cast<unsigned long long>(t_out));
-    atomicAdd(t + 3, 1ull);
-  }
-#endif
 }
 
 }  // namespace mixq

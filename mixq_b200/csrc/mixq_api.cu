@@ -396,6 +396,7 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
   p.nstages = nstages2;
   p.stage_bytes = stage2;
   p.k_atoms = ka2 ? 2 : 1;
+  if (const char* e = getenv("MIXQ_DEBUG_ABLATE")) p.ablate = atoi(e);
   p.q_w = static_cast<const uint8_t*>(c.q_w);
   p.q_w_pitch = w4 ? c.K / 2 : c.K;
   if (two_cta) {

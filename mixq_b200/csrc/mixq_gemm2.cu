@@ -120,6 +120,9 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
 
   // ------------------------------------------------------------------ producer helper
   // k-block order within a tile: the nk int8 blocks, then the nko outlier blocks.
+  // (Tried and dropped: letting every N-strip start its K loop at a different block so that the ~35 pairs of an M-block
+  // do not ask L2 for the same q_x lines at the same moment — 10 % SLOWER: simultaneous identical requests are merged
+  // in L2, lock-step is the cheap case.)
   auto produce = [&](int tile, int kb, int s, bool do_act, bool do_wgt, bool arm) {
     const int m0 = (tile % MP) * 256 + static_cast<int>(rank) * 128;
     const int n0 = pairm ? (tile / MP) * bh : (tile / MP) * W + static_cast<int>(rank) * bh;
@@ -127,6 +130,13 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
     const CUtensorMap* tmob = (pairm && rank == 1) ? &p.tm_ob2 : &p.tm_ob;
     const uint32_t full_leader = mapa_u32(smem_u32(&bar_full[s]), 0);
     if (kb < nk) {
+      if (p.ablate & 6) {   // tuning aid: leave one operand stream out (the MMAs then chew on stale shared memory)
+        if (p.ablate & 2) do_act = false;
+        if (p.ablate & 4) do_wgt = false;
+        if (arm && leader)
+          mbar_arrive_expect_tx(&bar_full[s], 2u * KA * (((p.ablate & 2) ? 0u : Cfg::A_BYTES) + ((p.ablate & 4) ? 0u : b_atom)));
+        arm = false;
+      }
       if (arm && leader) mbar_arrive_expect_tx(&bar_full[s], atom_tx * static_cast<uint32_t>(KA));
       if (KA == 1) {
         const int k0 = kb * 128;
@@ -204,7 +214,10 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
     if (leader) {
       const uint32_t idesc_i8_1 = make_idesc_i8_rt(256, n1), idesc_i8_2 = make_idesc_i8_rt(256, n2 > 0 ? n2 : 32);
       const uint32_t d1 = tmem_base, d2 = tmem_base + static_cast<uint32_t>(n1);
-      const uint64_t b2_off = static_cast<uint64_t>((n1 >> 1) * 128) >> 4;   // chunk 2 starts n1/2 rows into the half
+      const uint32_t b2_off32 = static_cast<uint32_t>((n1 >> 1) * 128) >> 4;   // chunk 2 starts n1/2 rows into the half
+      const uint32_t lo_a0 = desc_lo_sw128(smem_u32(stage_a(0))), lo_b0 = desc_lo_sw128(smem_u32(stage_b(0)));
+      const uint32_t stage_step = static_cast<uint32_t>(stage_bytes) >> 4;   // descriptor low-word steps: stage, k-atom
+      const uint32_t a_step = Cfg::A_BYTES >> 4, b_step = b_atom >> 4;
       const bool two = n2 > 0;
       int s = 0;
       uint32_t ph = 0;
@@ -228,19 +241,16 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
         for (int kb = 0; kb < nk; ++kb) {
           mbar_wait(&bar_full[s], ph, 4, s);
           tc_fence_after();
-          const uint64_t da = make_sw128_kmajor_desc(smem_u32(stage_a(s)));
-          const uint64_t db = make_sw128_kmajor_desc(smem_u32(stage_b(s)));
+          const uint32_t lo_a = lo_a0 + static_cast<uint32_t>(s) * stage_step;
+          const uint32_t lo_b = lo_b0 + static_cast<uint32_t>(s) * stage_step;
           if (elect_one()) {
             if (trace && i == 0 && kb == 0) trace[3] = globaltimer_ns();
             if (trace && blockIdx.x == 0 && i == 0 && kb < 48) p.trace[2048 + kb] = globaltimer_ns();
-            const uint32_t first = (kb == 0) ? 0u : 1u;
-            for (int a = 0; a < KA; ++a) {
-              const uint64_t daa = da + static_cast<uint64_t>(a) * (Cfg::A_BYTES >> 4);
-              const uint64_t dba = db + static_cast<uint64_t>(a) * (b_atom >> 4);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {   // 4 x (K = 32 int8 = 32 B); +2 in the >>4-encoded start address
-                umma_i8_2cta(d1, daa + 2 * k, dba + 2 * k, idesc_i8_1, first | a | k);
-                if (two) umma_i8_2cta(d2, daa + 2 * k, dba + b2_off + 2 * k, idesc_i8_2, first | a | k);
+            if (!(p.ablate & 1)) {
+              for (int a = 0; a < KA; ++a) {
+                const uint32_t acc = (kb | a) != 0;
+                if (two) umma_i8_2cta_atom2(d1, d2, lo_a + a * a_step, lo_b + a * b_step, lo_b + a * b_step + b2_off32, idesc_i8_1, idesc_i8_2, acc);
+                else umma_i8_2cta_atom(d1, lo_a + a * a_step, lo_b + a * b_step, idesc_i8_1, acc);
               }
             }
             umma_commit_2cta(&bar_empty[s], 0x3);
@@ -330,6 +340,15 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
 
       for (int c = 0; c < P; ++c) {
         const int buf = c & 1;
+        bool pre_staged = false;
+        if (c == 0 && mode == 1 && !pairm && p.epilogue == EPI_DEQUANT_F16) {
+          // the residual tile of the first 64 columns comes in while the accumulator is still being computed
+          const int nc0 = W < R ? W : R;
+          const int b0 = (nc0 >> 1) < h1 ? (nc0 >> 1) : h1;
+          epi_stage_in(stage_sa, p.residual, p.ld_res, m0, n0, (b0 < 64 ? b0 : 64) >> 3, p.M, p.N, lane);
+          __syncwarp();
+          pre_staged = true;
+        }
         mbar_wait_warp(&bar_tfull[buf], (buf ? seen1 : seen0) & 1, 5, c);
         if (buf) ++seen1; else ++seen0;
         tc_fence_after();
@@ -358,11 +377,11 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
           } else if (p.epilogue == EPI_DEQUANT_F16) {
             if (has_o) {
               if (mode == 0) epilogue_run_coalesced<true, 0>(p, stage_sa, t_int, t_o, m0, n0 + a, b - a, xs, sc, lane);
-              else if (mode == 1) epilogue_run_coalesced<true, 1>(p, stage_sa, t_int, t_o, m0, n0 + a, b - a, xs, sc, lane);
+              else if (mode == 1) epilogue_run_coalesced<true, 1>(p, stage_sa, t_int, t_o, m0, n0 + a, b - a, xs, sc, lane, pre_staged && part == 0);
               else epilogue_run_coalesced<true, 2>(p, stage_sa, t_int, t_o, m0, n0 + a, b - a, xs, sc, lane);
             } else {
               if (mode == 0) epilogue_run_coalesced<false, 0>(p, stage_sa, t_int, 0u, m0, n0 + a, b - a, xs, sc, lane);
-              else if (mode == 1) epilogue_run_coalesced<false, 1>(p, stage_sa, t_int, 0u, m0, n0 + a, b - a, xs, sc, lane);
+              else if (mode == 1) epilogue_run_coalesced<false, 1>(p, stage_sa, t_int, 0u, m0, n0 + a, b - a, xs, sc, lane, pre_staged && part == 0);
               else epilogue_run_coalesced<false, 2>(p, stage_sa, t_int, 0u, m0, n0 + a, b - a, xs, sc, lane);
             }
           } else {   // raw int32 accumulators (mixlib.gemm)

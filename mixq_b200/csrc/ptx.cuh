@@ -364,6 +364,54 @@ __device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t desc_a, 
       : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The four K = 32 steps of one 128-byte k-atom in ONE asm block, for one or two accumulator column chunks.
+// The MMA warp runs one such block per k-atom and nothing else in its loop: with the descriptors built in C++ (64-bit adds
+// in the uniform datapath, a predicate per MMA) the loop was ~110 mostly dependent instructions per stage and paced narrow
+// tiles at ~680 clocks per stage even with every load and every MMA removed (MIXQ_DEBUG_ABLATE, profiles/).
+//   lo_a / lo_b: low words of the SWIZZLE_128B K-major descriptors of the atom (start address >> 4 | LBO); the high word is
+//   the constant kDescHi; +2 in the low word = +32 bytes = the next K step.  acc = 0: the first step overwrites D.
+static constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ void umma_i8_2cta_atom(uint32_t d1, uint32_t lo_a, uint32_t lo_b, uint32_t idesc1, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t.reg .b32 a, b;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 q, 0, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], da, db, %3, p;\n\t"
+      "add.u32 a, %1, 2;\n\tadd.u32 b, %2, 2;\n\tmov.b64 da, {a, %5};\n\tmov.b64 db, {b, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], da, db, %3, q;\n\t"
+      "add.u32 a, %1, 4;\n\tadd.u32 b, %2, 4;\n\tmov.b64 da, {a, %5};\n\tmov.b64 db, {b, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], da, db, %3, q;\n\t"
+      "add.u32 a, %1, 6;\n\tadd.u32 b, %2, 6;\n\tmov.b64 da, {a, %5};\n\tmov.b64 db, {b, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], da, db, %3, q;\n\t}"
+      :
+      : "r"(d1), "r"(lo_a), "r"(lo_b), "r"(idesc1), "r"(acc), "r"(kDescHi)
+      : "memory");
+}
+// Two column chunks per K step: D1 (+)= A * B[rows 0..], D2 (+)= A * B[rows off2..]  (lo_b2 = lo_b + row offset >> 4).
+__device__ __forceinline__ void umma_i8_2cta_atom2(uint32_t d1, uint32_t d2, uint32_t lo_a, uint32_t lo_b, uint32_t lo_b2,
+                                                   uint32_t idesc1, uint32_t idesc2, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db, dc;\n\t.reg .b32 a, b, c;\n\t"
+      "setp.ne.b32 p, %7, 0;\n\t"
+      "setp.eq.b32 q, 0, 0;\n\t"
+      "mov.b64 da, {%2, %8};\n\tmov.b64 db, {%3, %8};\n\tmov.b64 dc, {%4, %8};\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], da, db, %5, p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%1], da, dc, %6, p;\n\t"
+      "add.u32 a, %2, 2;\n\tadd.u32 b, %3, 2;\n\tadd.u32 c, %4, 2;\n\tmov.b64 da, {a, %8};\n\tmov.b64 db, {b, %8};\n\tmov.b64 dc, {c, %8};\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], da, db, %5, q;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%1], da, dc, %6, q;\n\t"
+      "add.u32 a, %2, 4;\n\tadd.u32 b, %3, 4;\n\tadd.u32 c, %4, 4;\n\tmov.b64 da, {a, %8};\n\tmov.b64 db, {b, %8};\n\tmov.b64 dc, {c, %8};\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], da, db, %5, q;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%1], da, dc, %6, q;\n\t"
+      "add.u32 a, %2, 6;\n\tadd.u32 b, %3, 6;\n\tadd.u32 c, %4, 6;\n\tmov.b64 da, {a, %8};\n\tmov.b64 db, {b, %8};\n\tmov.b64 dc, {c, %8};\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], da, db, %5, q;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%1], da, dc, %6, q;\n\t}"
+      :
+      : "r"(d1), "r"(d2), "r"(lo_a), "r"(lo_b), "r"(lo_b2), "r"(idesc1), "r"(idesc2), "r"(acc), "r"(kDescHi)
+      : "memory");
+}
 // All tcgen05 ops issued so far by this thread arrive (once) on the barrier at this offset in every CTA of `mask`.
 __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
