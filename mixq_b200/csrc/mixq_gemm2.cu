@@ -70,15 +70,25 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
   const bool has_o = nko > 0;
   const uint32_t atom_tx = 2u * static_cast<uint32_t>(Cfg::A_BYTES + bh * 128);    // both CTAs' bytes land on one barrier
   const uint32_t b_atom = static_cast<uint32_t>(bh) * 128u;                         // bytes between the k-atoms of a weight stage
-  // Outlier passes.  The fp32 accumulator of the skinny outlier GEMM gets what TMEM has left beside the int32 one: all W
-  // columns when 2 W <= 512 (one pass), otherwise TWO buffers of R columns that the MMA warp and the epilogue warps
-  // ping-pong (pass c + 1 is issued while pass c drains).  Passes are balanced (352 -> 6 x 64, not 5 x 64 + 32).
-  int P = 1, R = W;
-  if (has_o && 2 * W > 512) {
-    const int r_max = ((512 - W) >> 1) & ~31;     // host guarantees W <= 448 with outliers: r_max >= 32
-    P = (W + r_max - 1) / r_max;
-    R = ((W + P - 1) / P + 31) & ~31;
+  // TMEM plan (512 columns).  SLOTS int32 accumulators of W columns: two when a pair has several tiles and they fit, so
+  // that the MMAs of tile i + 1 run while the epilogue drains tile i.  What is left holds the fp32 accumulator of the skinny
+  // outlier GEMM: all W columns at once when they fit (one pass), otherwise NB = 1 or 2 buffers of R columns that the MMA
+  // warp refills while the epilogue drains the tile pass by pass (balanced: 352 -> 6 x 64, not 5 x 64 + 32).  Without
+  // outliers a "pass" is the whole tile and the pass buffers ARE the accumulator slots.
+  // Passes are numbered globally (G = tile * P + c): pass G uses barrier pair / buffer G % NB in phase (G / NB) & 1.
+  const int my_tiles_geo = (pair < ntiles) ? (ntiles - 1 - pair) / npairs + 1 : 0;
+  const int SLOTS = (my_tiles_geo > 1 && 2 * W + (has_o ? 64 : 0) <= 512) ? 2 : 1;
+  int P = 1, R = W, NB = has_o ? 1 : SLOTS;
+  if (has_o) {
+    const int spare = 512 - SLOTS * W;               // host guarantees W <= 448 with outliers: spare >= 64
+    if (spare < W) {
+      if (spare >= 128) { NB = 2; R = (spare >> 1) & ~31; }
+      else { NB = 1; R = spare & ~31; }
+      P = (W + R - 1) / R;
+      R = ((W + P - 1) / P + 31) & ~31;
+    }
   }
+  const uint32_t outl_col0 = static_cast<uint32_t>(SLOTS * W);   // first TMEM column of the outlier buffers
 
   auto stage_a = [&](int s) { return smem + static_cast<size_t>(s) * stage_bytes; };
   auto stage_b = [&](int s) { return smem + static_cast<size_t>(s) * stage_bytes + static_cast<size_t>(KA) * Cfg::A_BYTES; };
@@ -213,7 +223,6 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
   } else if (warp == 1) {
     if (leader) {
       const uint32_t idesc_i8_1 = make_idesc_i8_rt(256, n1), idesc_i8_2 = make_idesc_i8_rt(256, n2 > 0 ? n2 : 32);
-      const uint32_t d1 = tmem_base, d2 = tmem_base + static_cast<uint32_t>(n1);
       const uint32_t b2_off32 = static_cast<uint32_t>((n1 >> 1) * 128) >> 4;   // chunk 2 starts n1/2 rows into the half
       const uint32_t lo_a0 = desc_lo_sw128(smem_u32(stage_a(0))), lo_b0 = desc_lo_sw128(smem_u32(stage_b(0)));
       const uint32_t stage_step = static_cast<uint32_t>(stage_bytes) >> 4;   // descriptor low-word steps: stage, k-atom
@@ -221,23 +230,23 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
       const bool two = n2 > 0;
       int s = 0;
       uint32_t ph = 0;
-      // accumulator buffer b (b = 0: also the int32 accumulator when there are no outliers) has been handed to the epilogue
-      // used_b times and handed back waited_b times so far
-      uint32_t used0 = 0, used1 = 0, waited0 = 0, waited1 = 0;
-      auto reclaim = [&](int b) {
-        uint32_t& used = b ? used1 : used0;
+      // pass buffer b has been handed back (bar_tempty[b] completed) waited_b times so far
+      uint32_t waited0 = 0, waited1 = 0;
+      auto wait_consumed = [&](int G) {      // global pass G has been drained by every epilogue warp of the pair
+        if (G < 0) return;
+        const int b = G % NB;
+        const uint32_t k = static_cast<uint32_t>(G / NB);
         uint32_t& waited = b ? waited1 : waited0;
-        while (waited < used) {
+        while (waited <= k) {
           mbar_wait(&bar_tempty[b], waited & 1, 2, b);
           ++waited;
         }
         tc_fence_after();
       };
       for (int i = 0; i < my_tiles; ++i) {
-        if (i > 0) {             // every pass of the previous tile has left TMEM (both CTAs)
-          reclaim(0);
-          reclaim(1);
-        }
+        const int G0 = i * P;                                       // first pass of this tile
+        wait_consumed((i - SLOTS + 1) * P - 1);                     // the tile that last used this accumulator slot has left TMEM
+        const uint32_t d1 = tmem_base + static_cast<uint32_t>((SLOTS == 2 ? (i & 1) : 0) * W), d2 = d1 + static_cast<uint32_t>(n1);
         for (int kb = 0; kb < nk; ++kb) {
           mbar_wait(&bar_full[s], ph, 4, s);
           tc_fence_after();
@@ -245,7 +254,7 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
           const uint32_t lo_b = lo_b0 + static_cast<uint32_t>(s) * stage_step;
           if (elect_one()) {
             if (trace && i == 0 && kb == 0) trace[3] = globaltimer_ns();
-            if (trace && blockIdx.x == 0 && i == 0 && kb < 48) p.trace[2048 + kb] = globaltimer_ns();
+            if (trace && blockIdx.x == 0 && i * nk + kb < 96) p.trace[2048 + i * nk + kb] = globaltimer_ns();
             if (!(p.ablate & 1)) {
               for (int a = 0; a < KA; ++a) {
                 const uint32_t acc = (kb | a) != 0;
@@ -260,9 +269,8 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
         }
         if (trace && lane == 0 && i == 0) trace[6] = globaltimer_ns();   // int8 k-blocks of the first tile issued
         if (!has_o) {
-          if (elect_one()) umma_commit_2cta(&bar_tfull[0], 0x3);
+          if (elect_one()) umma_commit_2cta(&bar_tfull[G0 % NB], 0x3);
           __syncwarp();
-          ++used0;
         } else {
           // the nko outlier k-blocks sit in the next nko stages and stay there for all P passes
           const int s_o = s;
@@ -275,11 +283,11 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
           }
           tc_fence_after();
           for (int c = 0; c < P; ++c) {
-            const int b = c & 1;
-            reclaim(b);          // pass c - 2 (same buffer) was consumed
+            const int b = (G0 + c) % NB;
+            wait_consumed(G0 + c - NB);   // the previous pass in this buffer was consumed
             const int nc = (W - c * R) < R ? (W - c * R) : R;
             const uint32_t idesc_f16 = make_idesc_f16_rt(256, nc);
-            const uint32_t d_outl = tmem_base + static_cast<uint32_t>(W + b * R);
+            const uint32_t d_outl = tmem_base + outl_col0 + static_cast<uint32_t>(b * R);
             const uint64_t bo = static_cast<uint64_t>(c * (R >> 1) * 128) >> 4;
             if (elect_one()) {
               for (int kbo = 0; kbo < nko; ++kbo) {
@@ -302,7 +310,6 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
                 }
             }
             __syncwarp();
-            if (b) ++used1; else ++used0;
           }
           s += nko;
           if (s >= nstages) { s -= nstages; ph ^= 1; }
@@ -321,7 +328,6 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
     const uint32_t tempty0 = mapa_u32(smem_u32(&bar_tempty[0]), 0), tempty1 = mapa_u32(smem_u32(&bar_tempty[1]), 0);
     const int h1 = n1 >> 1;                 // output columns of this half that live in MMA chunk 1
     const int mode = (p.outl != nullptr || p.bias != nullptr || p.act == 1) ? 2 : (p.residual != nullptr ? 1 : 0);
-    uint32_t seen0 = 0, seen1 = 0;          // phase counters of bar_tfull[0] / [1]
     for (int i = 0; i < my_tiles; ++i) {
       const int tile = pair + i * npairs;
       const int m0 = (tile % MP) * 256 + static_cast<int>(rank) * 128 + q * 32;   // first row of this warp
@@ -338,8 +344,10 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
                              : make_uint4(0, 0, 0, 0);
       named_bar_sync(13 + half, 128);
 
+      const uint32_t int_col0 = static_cast<uint32_t>((SLOTS == 2 ? (i & 1) : 0) * W);   // this tile's int32 accumulator slot
       for (int c = 0; c < P; ++c) {
-        const int buf = c & 1;
+        const int G = i * P + c;
+        const int buf = G % NB;
         bool pre_staged = false;
         if (c == 0 && mode == 1 && !pairm && p.epilogue == EPI_DEQUANT_F16) {
           // the residual tile of the first 64 columns comes in while the accumulator is still being computed
@@ -349,21 +357,20 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
           __syncwarp();
           pre_staged = true;
         }
-        mbar_wait_warp(&bar_tfull[buf], (buf ? seen1 : seen0) & 1, 5, c);
-        if (buf) ++seen1; else ++seen0;
+        mbar_wait_warp(&bar_tfull[buf], (G / NB) & 1, 5, c);
         tc_fence_after();
         if (trace && !p.fused_prologue && warp == 4 && lane == 0 && i == 0 && c == 0) trace[7] = globaltimer_ns();
         if (trace && blockIdx.x == 0 && warp == 4 && lane == 0 && i == 0 && c < 16) p.trace[1536 + 2 * c] = globaltimer_ns();
         const int x0 = c * (R >> 1);                                   // this pass: output columns [x0, x1) of the half
         const int nc = (W - c * R) < R ? (W - c * R) : R;
         const int x1 = x0 + (nc >> 1);
-        const uint32_t t_outl = lane_base + static_cast<uint32_t>(W + buf * R + half * (nc >> 1));
+        const uint32_t t_outl = lane_base + outl_col0 + static_cast<uint32_t>(buf * R + half * (nc >> 1));
         // split the run where the int32 accumulator switches from MMA chunk 1 to chunk 2
         for (int part = 0; part < 2; ++part) {
           const int a = part == 0 ? x0 : (x0 > h1 ? x0 : h1);
           const int b = part == 0 ? (x1 < h1 ? x1 : h1) : x1;
           if (a >= b) continue;
-          const uint32_t t_int = lane_base + static_cast<uint32_t>(part == 0 ? half * h1 + a : n1 + half * (n2 >> 1) + (a - h1));
+          const uint32_t t_int = lane_base + int_col0 + static_cast<uint32_t>(part == 0 ? half * h1 + a : n1 + half * (n2 >> 1) + (a - h1));
           const uint32_t t_o = t_outl + (a - x0);
           const uint32_t sc = scale_sa + a * 2;
           if (pairm) {

@@ -457,6 +457,26 @@ def test_linear_fused_residual_only(lib, M, N, K, n):
         bits_equal(host(t["y"]), r["y"], "y (no outliers: bit-exact)")
 
 
+@pytest.mark.parametrize("n", [0, 41, 130])
+def test_linear_fused_two_accumulator_slots(lib, n):
+    """Several tiles per CTA pair with tiles narrow enough for TWO int32 accumulator slots in TMEM (the MMAs of tile i + 1
+    overlap the epilogue of tile i): 2 x 80 tiles of 256 x 128 on 74 pairs."""
+    M, N, K = 512, 10240, 1024
+    rng = np.random.default_rng(40 + n)
+    x, cols = make_x(rng, M, K, n)
+    W = (rng.standard_normal((N, K)) * 0.02).astype(np.float16)
+    qw, ws = O.quant_weight_w8(W)
+    wc = O.weight_cache_columns(qw, ws, cols, 8)
+    res = rng.standard_normal((M, N)).astype(np.float16)
+    t = run_fused(lib, x, qw, ws, cols, wc, 8, residual=res, tile=128)
+    r = oracle_fused(x, qw, ws, cols, wc, 8, residual=res)
+    bits_equal(host(t["q_x"]), r["q_x"], "q_x")
+    if n:
+        rel_close(host(t["y"]), r["y"], "y")
+    else:
+        bits_equal(host(t["y"]), r["y"], "y (no outliers: bit-exact)")
+
+
 def test_launch_modes_bit_identical(lib, monkeypatch):
     """Programmatic dependent launch on/off and one/two k-atoms per TMA op are scheduling choices: y must not change."""
     M, N, K, n = 512, 1024, 4096, 41

@@ -9,6 +9,8 @@ dev = "cuda"
 g = torch.Generator(device=dev).manual_seed(0)
 trace = torch.zeros(16384, dtype=torch.int64, device=dev)
 NOUT = int(os.environ.get('NOUT', '41'))
+PAIR = os.environ.get('PAIR') == '1'   # SwiGLU pair launch (gate + up)
+NORM = os.environ.get('NORM') == '1'
 TILE = int(os.environ.get('TILE', '0'))
 MODES = os.environ.get('MODES', 'plain,skip').split(',')
 SHAPES = [tuple(int(v) for v in t.split('x')) for t in os.environ.get('SHAPES', '12288x4096,4096x4096,4096x11008').split(',')]
@@ -21,7 +23,7 @@ for (N, K) in SHAPES:
              (torch.randn(N, cap, generator=g, device=dev) * 0.02).half()) for _ in range(4)]
     q_x = torch.zeros(M, K, dtype=torch.int8, device=dev); xs = torch.zeros(M, dtype=torch.float16, device=dev)
     ao = torch.zeros(M, cap, dtype=torch.float16, device=dev); y = torch.zeros(M, N, dtype=torch.float16, device=dev)
-    sync = torch.zeros(1, dtype=torch.int32, device=dev); x = x0.clone()
+    sync = torch.zeros(1, dtype=torch.int32, device=dev); x = x0.clone(); nw = torch.ones(K, dtype=torch.float16, device=dev)
     for mode in MODES:
         for it, (qw, ws, wc) in enumerate(ws_l):
             a = _lib.LinearArgs()
@@ -29,6 +31,11 @@ for (N, K) in SHAPES:
             a.q_weight = qw.data_ptr(); a.scale_col = ws.data_ptr(); a.bit = 8
             a.ind = cols.data_ptr(); a.n_ind = n; a.weight_cache = wc.data_ptr(); a.ld_wc = cap
             a.q_x = q_x.data_ptr(); a.x_scale = xs.data_ptr(); a.act_outliers = ao.data_ptr(); a.ld_ao = cap
+            if PAIR:
+                qw2, ws2, wc2 = ws_l[(it + 1) % 4]
+                a.q_weight_up = qw2.data_ptr(); a.scale_col_up = ws2.data_ptr(); a.weight_cache_up = wc2.data_ptr()
+            if NORM:
+                a.norm_weight = nw.data_ptr(); a.eps = 1e-5
             a.sigma = 6.0; a.y = y.data_ptr(); a.grid_sync = sync.data_ptr(); a.skip_prologue = 1 if mode == "skip" else 0; a.tile_n = TILE
             lib.mixq_set_trace_buffer(trace.data_ptr() if it == 3 else 0)
             trace.zero_()
@@ -60,8 +67,8 @@ for (N, K) in SHAPES:
                   f"stage-out {ep[ok, 2].mean():8.0f} | calls {ep[ok, 3].mean():.1f}")
         if os.environ.get("CADENCE"):
             base = t[0, 0]
-            for name, off in (("mma", 2048), ("wgt-tma", 2048 + 256), ("act-tma", 2048 + 512)):
-                v = full[off:off + 48]
+            for name, off, cnt in (("mma", 2048, 96), ("wgt-tma", 2048 + 256, 48), ("act-tma", 2048 + 512, 48)):
+                v = full[off:off + cnt]
                 v = v[v > 0]
                 print("   ", name, " ".join(f"{(x - base) / 1e3:.2f}" for x in v.tolist()))
 lib.mixq_set_trace_buffer(0)
