@@ -182,6 +182,19 @@ def main():
         path = os.path.join(OUT, f"{name}.npz")
         np.savez_compressed(path, **d)
         print(f"{name}: {len(d)} arrays, {os.path.getsize(path)/1024:.0f} KiB")
+    # the reference's checkpoint layout: state_dict() keys / dtypes / shapes of its own MixLinear_GEMM (linear.py:39-65),
+    # which is what save_quantized writes (base.py:78-119); mixq_b200/checkpoint.py must produce exactly these entries
+    import json
+    manifest = {}
+    for tag, bit, bias in (("w8", 8, False), ("w8_bias", 8, True), ("w4", 4, False)):
+        K, N = 256, 96
+        cache = cache_mod.MixLibCache(inputdim=16, sigma=6, bit=bit)
+        m = linear_mod.MixLinear_GEMM(K, N, bias, "cpu", bit, False, cache)
+        manifest[tag] = {"in_features": K, "out_features": N,
+                         "state": {k: [str(v.dtype).replace("torch.", ""), list(v.shape)] for k, v in m.state_dict().items()}}
+    with open(os.path.join(OUT, "state_manifest.json"), "w") as f:
+        json.dump(manifest, f, indent=1, sort_keys=True)
+    print("state_manifest.json:", {k: sorted(v["state"]) for k, v in manifest.items()})
 
 
 if __name__ == "__main__":
