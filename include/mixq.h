@@ -177,6 +177,35 @@ int mixq_rope_attention_decode(const void* qkv, void* k_cache, void* v_cache, in
 /* elementwise gate *= up (mlp.py:64) kept for the decode harness */
 int mixq_mul_inplace(void* a, const void* b, long long n, void* stream);
 
+/* ---- The exchange step of the row-parallel Linears (o_proj, down_proj) under tensor parallelism, over NVLink peer memory.
+ * The reference has no multi-GPU code (models/base.py:196-225 is accelerate placement); this replaces ncclAllReduce + the
+ * decoder's residual add by ONE kernel per rank: out = fp16( fp16(sum over ranks of partial, fp32, rank order) + residual ).
+ * Set-up (once per process): every rank allocates two partial buffers and kMaxPeers flag words with mixq_peer_alloc,
+ * publishes their handles (mixq_ipc_get_handle, 64 bytes) to the other ranks of the node, and maps theirs
+ * (mixq_ipc_open_handle).  Per exchange: the rank's Linear writes its partial into ITS buffer `buf`, then every rank calls
+ * mixq_allreduce_residual with the same n and buf.  Callers ALTERNATE buf = 0, 1, 0, 1, ... over successive exchanges (a rank
+ * may overwrite a buffer only after the following exchange, which proves every peer has finished reading it); a CUDA graph
+ * that is replayed must therefore hold an even number of exchanges.  `epoch` / `done`: two zero-initialised local uint32 (the
+ * kernel keeps the exchange count on the device, so the call is graph replayable). */
+typedef struct mixq_allreduce_args {
+  const void* partial0[8]; /* [rank]: that rank's partial buffer 0, as mapped in this process (own rank: the local pointer) */
+  const void* partial1[8]; /* [rank]: buffer index 1 */
+  void* flags[8];          /* [rank]: that rank's 8 flag words (uint32), as mapped in this process */
+  void* epoch;             /* local uint32 */
+  void* done;              /* local uint32 */
+  const void* residual;    /* local fp16 [n] or NULL */
+  void* out;               /* local fp16 [n] */
+  long long n;             /* elements, multiple of 8 */
+  int world, rank;         /* 2 <= world <= 8 */
+  int buf;                 /* 0 or 1: which partial buffer holds this exchange */
+} mixq_allreduce_args;
+int mixq_peer_alloc(unsigned long long bytes, void** ptr);
+int mixq_peer_free(void* ptr);
+int mixq_ipc_get_handle(const void* ptr, void* handle64);
+int mixq_ipc_open_handle(const void* handle64, void** ptr);
+int mixq_ipc_close_handle(void* ptr);
+int mixq_allreduce_residual(const mixq_allreduce_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

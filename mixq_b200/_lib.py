@@ -56,6 +56,24 @@ class LinearArgs(C.Structure):
     ]
 
 
+class AllReduceArgs(C.Structure):
+    """Mirror of `mixq_allreduce_args` (include/mixq.h)."""
+
+    _fields_ = [
+        ("partial0", C.c_void_p * 8),
+        ("partial1", C.c_void_p * 8),
+        ("flags", C.c_void_p * 8),
+        ("epoch", C.c_void_p),
+        ("done", C.c_void_p),
+        ("residual", C.c_void_p),
+        ("out", C.c_void_p),
+        ("n", C.c_longlong),
+        ("world", C.c_int),
+        ("rank", C.c_int),
+        ("buf", C.c_int),
+    ]
+
+
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 
 # name -> argtypes; every function returns int unless listed in _RESTYPES
@@ -75,6 +93,12 @@ SIGNATURES = {
     "mixq_linear_fused": [C.POINTER(LinearArgs), _vp],
     "mixq_rope_attention_decode": [_vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _f, _vp],
     "mixq_mul_inplace": [_vp, _vp, _ll, _vp],
+    "mixq_peer_alloc": [C.c_ulonglong, C.POINTER(C.c_void_p)],
+    "mixq_peer_free": [_vp],
+    "mixq_ipc_get_handle": [_vp, C.c_char_p],
+    "mixq_ipc_open_handle": [C.c_char_p, C.POINTER(C.c_void_p)],
+    "mixq_ipc_close_handle": [_vp],
+    "mixq_allreduce_residual": [C.POINTER(AllReduceArgs), _vp],
     "mixq_set_tile_n": [_i],
     "mixq_set_pdl": [_i],
     "mixq_set_trace_buffer": [_vp],

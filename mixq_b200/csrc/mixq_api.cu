@@ -2,6 +2,7 @@
 // TMA tensor-map encoding, launch configuration.  No allocation, no synchronisation.
 #include <atomic>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -694,6 +695,62 @@ int mixq_rope_attention_decode(const void* qkv, void* k_cache, void* v_cache, in
   MIXQ_CUDA(launch_rope_attn_decode(static_cast<const __half*>(qkv), static_cast<__half*>(k_cache),
                                     static_cast<__half*>(v_cache), cache_cap, past_len, static_cast<__half*>(out), M, H,
                                     Hkv, D, theta, pdl_on(), static_cast<cudaStream_t>(stream)));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int mixq_peer_alloc(unsigned long long bytes, void** ptr) {
+  if (!ptr || bytes == 0) return fail(MIXQ_EINVAL, "bad peer_alloc arguments");
+  MIXQ_CUDA(cudaMalloc(ptr, bytes));            // its own allocation: the IPC handle maps exactly this buffer
+  MIXQ_CUDA(cudaMemset(*ptr, 0, bytes));
+  MIXQ_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+int mixq_peer_free(void* ptr) {
+  MIXQ_CUDA(cudaFree(ptr));
+  return 0;
+}
+int mixq_ipc_get_handle(const void* ptr, void* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!ptr || !handle64) return fail(MIXQ_EINVAL, "null pointer");
+  MIXQ_CUDA(cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(handle64), const_cast<void*>(ptr)));
+  return 0;
+}
+int mixq_ipc_open_handle(const void* handle64, void** ptr) {
+  if (!ptr || !handle64) return fail(MIXQ_EINVAL, "null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  MIXQ_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+int mixq_ipc_close_handle(void* ptr) {
+  MIXQ_CUDA(cudaIpcCloseMemHandle(ptr));
+  return 0;
+}
+
+int mixq_allreduce_residual(const mixq_allreduce_args* a, void* stream) {
+  if (!a || a->world < 2 || a->world > kMaxPeers || a->rank < 0 || a->rank >= a->world || !a->out || !a->epoch || !a->done ||
+      a->n < 8 || (a->n & 7))
+    return fail(MIXQ_EINVAL, "bad all-reduce arguments (2 <= world <= 8, n % 8 == 0)");
+  AllReduceArgs k{};
+  for (int p = 0; p < a->world; ++p) {
+    if (!a->partial0[p] || !a->partial1[p] || !a->flags[p]) return fail(MIXQ_EINVAL, "missing peer pointer");
+    k.partial[p][0] = static_cast<const __half*>(a->partial0[p]);
+    k.partial[p][1] = static_cast<const __half*>(a->partial1[p]);
+    k.flags[p] = static_cast<uint32_t*>(a->flags[p]);
+  }
+  k.epoch = static_cast<uint32_t*>(a->epoch);
+  k.done = static_cast<uint32_t*>(a->done);
+  k.residual = static_cast<const __half*>(a->residual);
+  k.out = static_cast<__half*>(a->out);
+  k.n = a->n;
+  k.world = a->world;
+  k.rank = a->rank;
+  k.buf = a->buf & 1;
+  DeviceInfo di;
+  if (int r = device_info(&di)) return r;
+  const int grid = grid_for(a->n / 8, 256, di.sms, 4);
+  MIXQ_CUDA(launch_small(allreduce_residual_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), k));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }

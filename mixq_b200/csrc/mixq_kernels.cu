@@ -234,6 +234,80 @@ cudaError_t launch_rope_attn_decode(const __half* qkv, __half* k_cache, __half* 
   return cudaLaunchKernelEx(&cfg, rope_attn_decode_kernel<64>, qkv, k_cache, v_cache, cache_cap, past_len, out, M, H, Hkv, theta, scale);
 }
 
+// ---------------------------------------------------------------- all-reduce (+ residual) over NVLink peer memory
+// The exchange step of the row-parallel Linears (o_proj, down_proj): every rank has written its fp16 partial [n] into its own
+// peer-mapped buffer; each rank then reads ALL partials (local HBM + peers over NVLink / NVSwitch), sums them in fp32 in rank
+// order (bit-identical on every rank), rounds to fp16 (what an fp16 all-reduce returns), adds the residual stream as a separate
+// fp16 op and writes h.  One launch replaces ncclAllReduce + the residual add.
+//   flags[r][p]: word in rank r's memory that rank p sets to the epoch it has reached ("my partial e is complete").
+//   *epoch: this rank's count of finished exchanges; every block reads it on entry, the last block to leave bumps it — so
+//   the kernel is replayable from a CUDA graph.  Callers alternate between two partial buffers: a rank overwrites the
+//   buffer of exchange e only after its exchange e + 1, which needed every peer's signal e + 1, which a peer sends only
+//   after its own exchange e (its reads of that buffer) has completed.
+__global__ void __launch_bounds__(256) allreduce_residual_kernel(AllReduceArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();                                   // my partial (previous kernel of the stream) is complete and visible
+  __shared__ uint32_t s_epoch;
+  if (threadIdx.x == 0) {
+    const uint32_t e = *reinterpret_cast<volatile uint32_t*>(a.epoch) + 1;
+    s_epoch = e;
+    if (blockIdx.x == 0) {
+      __threadfence_system();
+      for (int p = 0; p < a.world; ++p)
+        if (p != a.rank) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flags[p] + a.rank), "r"(e) : "memory");
+    }
+    const uint64_t t0 = globaltimer_ns();
+    for (int p = 0; p < a.world; ++p) {
+      if (p == a.rank) continue;
+      uint32_t v, spins = 0;
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a.flags[a.rank] + p) : "memory");
+        if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > MIXQ_SPIN_TIMEOUT_NS) spin_timeout_trap(11, p, static_cast<int>(e));
+      } while (static_cast<int32_t>(v - e) < 0);
+    }
+  }
+  __syncthreads();
+  const int buf = a.buf;
+  const long long nv = a.n >> 3;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int p = 0; p < a.world; ++p) {
+      H8 v;
+      v.u = __ldcv(reinterpret_cast<const uint4*>(a.partial[p][buf]) + i);   // never from a stale L1 line
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(v.h2[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+    H8 r, o;
+    if (a.residual != nullptr) r.u = *(reinterpret_cast<const uint4*>(a.residual) + i);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __half2 y2 = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+      if (a.residual != nullptr) {
+        const float2 yf = __half22float2(y2), rf = __half22float2(r.h2[j]);
+        y2 = __floats2half2_rn(__fadd_rn(yf.x, rf.x), __fadd_rn(yf.y, rf.y));
+      }
+      o.h2[j] = y2;
+    }
+    *(reinterpret_cast<uint4*>(a.out) + i) = o.u;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(a.done, 1u) == gridDim.x - 1) {   // last block out: everybody has read *epoch
+      *a.done = 0;
+      __threadfence();
+      *reinterpret_cast<volatile uint32_t*>(a.epoch) = s_epoch;
+    }
+  }
+}
+
 __global__ void mul_inplace_kernel(__half2* a, const __half2* __restrict__ b, long long n2) {
   pdl_launch_dependents();
   pdl_wait();

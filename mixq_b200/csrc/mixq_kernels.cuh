@@ -17,4 +17,17 @@ cudaError_t launch_rope_attn_decode(const __half* qkv, __half* k_cache, __half* 
                                     __half* out, int M, int H, int Hkv, int D, float theta, bool pdl, cudaStream_t st);
 __global__ void mul_inplace_kernel(__half2* a, const __half2* b, long long n2);
 
+constexpr int kMaxPeers = 8;
+struct AllReduceArgs {
+  const __half* partial[kMaxPeers][2];   // [rank][buffer]: every rank's two partial buffers as mapped into THIS process
+  uint32_t* flags[kMaxPeers];            // [rank]: that rank's flag words (kMaxPeers of them), as mapped into this process
+  uint32_t* epoch;                       // local: exchanges finished so far
+  uint32_t* done;                        // local: blocks finished in the current launch
+  const __half* residual;                // local [n] or nullptr
+  __half* out;                           // local [n]
+  long long n;                           // elements, multiple of 8
+  int world, rank, buf;
+};
+__global__ void allreduce_residual_kernel(AllReduceArgs a);
+
 }  // namespace mixq

@@ -281,10 +281,11 @@ class MixLinear_GEMM(nn.Module):
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
-    def forward(self, x, cache=None, unfused=False, residual=None):
+    def forward(self, x, cache=None, unfused=False, residual=None, out=None):
         """linear.py:165-289.  unfused=True: x holds raw fp16 activations (their outlier columns are zeroed IN
         PLACE, as the reference does); unfused=False: the preceding FasterTransformerRMSNorm already left
-        q_xcache / x_scale / activation_outliers in the cache.  `residual` (extension): y = fp16(y + residual)."""
+        q_xcache / x_scale / activation_outliers in the cache.  `residual` (extension): y = fp16(y + residual);
+        `out` (extension): caller-owned contiguous fp16 [M, N] to write y into (e.g. a peer-mapped exchange buffer)."""
         if cache is None:
             cache = self.cache
         cache.shape = x.shape[:-1] + (self.out_features,)
@@ -293,7 +294,12 @@ class MixLinear_GEMM(nn.Module):
         if unfused and inputs.data_ptr() != x.data_ptr():
             raise _lib.MixqError("unfused MixLinear needs a contiguous activation tensor (columns are zeroed in place)")
         M = inputs.shape[0]
-        y = torch.empty((M, self.out_features), dtype=torch.float16, device=inputs.device)
+        if out is None:
+            y = torch.empty((M, self.out_features), dtype=torch.float16, device=inputs.device)
+        else:
+            if out.dtype != torch.float16 or not out.is_contiguous() or out.numel() != M * self.out_features:
+                raise _lib.MixqError("out must be a contiguous fp16 tensor of M * out_features elements")
+            y = out.view(M, self.out_features)
         res2 = None if residual is None else residual.reshape(M, self.out_features)
 
         if not self.add_outliers:

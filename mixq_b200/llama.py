@@ -21,6 +21,7 @@ heads / intermediate channels), o_proj / down_proj shard K and all-reduce their 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import torch
@@ -28,7 +29,7 @@ import torch
 from . import _lib
 from .cache import MixLibCache
 from .linear import MixLinear_GEMM
-from .tp import all_reduce_sum, pack_qkv_shard, shard_cols, shard_rows
+from .tp import PeerExchange, all_reduce_sum, pack_qkv_shard, shard_cols, shard_rows
 
 
 @dataclass
@@ -149,6 +150,10 @@ class LlamaDecoder:
         self._static_logits = None
         self.kv = None
         self.lib = _lib.load()
+        # row-parallel exchange: one peer-memory kernel (all-reduce + residual) unless MIXQ_TP_EXCHANGE=nccl
+        self.xchg = None
+        if world_size > 1 and os.environ.get("MIXQ_TP_EXCHANGE", "peer") == "peer":
+            self.xchg = PeerExchange(batch, H, rank, world_size, group=group, device=device)
 
     # ------------------------------------------------------------------ pieces
     def _stream(self):
@@ -192,7 +197,10 @@ class LlamaDecoder:
             else:
                 qkv = self._norm_then_linear(h, L["ln1"], L["W_pack"])
             attn = self._attention(qkv, past_len, li)
-            if tp:
+            if tp and self.xchg is not None:
+                L["o_proj"](attn, None, True, out=self.xchg.next_partial())
+                h = self.xchg.reduce(h, torch.empty_like(h))
+            elif tp:
                 h = h + self._allreduce(L["o_proj"](attn, None, True))
             else:
                 h = L["o_proj"](attn, None, True, residual=h)
@@ -205,7 +213,10 @@ class LlamaDecoder:
                     up = self._norm_then_linear(h, L["ln2"], L["up_proj"])
                 gate = L["gate_proj"].forward_without_preconditionFusedSilu(h, self.cache)
                 _lib.check(self.lib.mixq_mul_inplace(gate.data_ptr(), up.data_ptr(), gate.numel(), self._stream()), "mul")
-            if tp:
+            if tp and self.xchg is not None:
+                L["down_proj"](gate, None, True, out=self.xchg.next_partial())
+                h = self.xchg.reduce(h, torch.empty_like(h))
+            elif tp:
                 h = h + self._allreduce(L["down_proj"](gate, None, True))
             else:
                 h = L["down_proj"](gate, None, True, residual=h)

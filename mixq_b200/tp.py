@@ -10,6 +10,8 @@ Pure tensor slicing, device-agnostic (used on CPU by the gloo tests).
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 
 
@@ -41,3 +43,92 @@ def all_reduce_sum(t: torch.Tensor, group=None) -> torch.Tensor:
     if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1:
         torch.distributed.all_reduce(t, group=group)
     return t
+
+
+class _DeviceBuffer:
+    """Zero-copy torch view of raw device memory (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class PeerExchange:
+    """The exchange step of the row-parallel Linears over NVLink peer memory: ONE kernel per rank replaces
+    ncclAllReduce(sum, fp16 [M, hidden]) + the decoder's residual add (include/mixq.h: mixq_allreduce_residual).
+
+    Every rank owns two partial buffers (the row-parallel MixLinear writes straight into them, alternating) and eight flag
+    words, allocated with cudaMalloc and mapped into the other ranks of the node through CUDA IPC handles exchanged over the
+    process group.  Reads of the peers' partials travel over NVLink / NVSwitch inside the kernel; nothing goes through NCCL.
+    """
+
+    def __init__(self, rows: int, cols: int, rank: int, world: int, group=None, device="cuda"):
+        from . import _lib
+        import torch.distributed as dist
+        if not (2 <= world <= 8):
+            raise ValueError("PeerExchange needs 2..8 ranks on one node")
+        if (rows * cols) % 8:
+            raise ValueError("rows * cols must be a multiple of 8")
+        self.lib = _lib.load()
+        self._check = _lib.check
+        self.rows, self.cols, self.rank, self.world, self.device = rows, cols, rank, world, device
+        nbytes = rows * cols * 2
+        self._own = []
+        for size in (nbytes, nbytes, 256):
+            p = C.c_void_p()
+            self._check(self.lib.mixq_peer_alloc(size, C.byref(p)), "peer_alloc")
+            self._own.append(p.value)
+        handles = []
+        for p in self._own:
+            h = C.create_string_buffer(64)
+            self._check(self.lib.mixq_ipc_get_handle(p, h), "ipc_get_handle")
+            handles.append(h.raw)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, handles, group=group)
+        self._mapped = []      # peer mappings to close
+        ptrs = [[0, 0, 0] for _ in range(world)]
+        for r in range(world):
+            for j in range(3):
+                if r == rank:
+                    ptrs[r][j] = self._own[j]
+                else:
+                    q = C.c_void_p()
+                    self._check(self.lib.mixq_ipc_open_handle(gathered[r][j], C.byref(q)), f"ipc_open_handle(rank {r})")
+                    ptrs[r][j] = q.value
+                    self._mapped.append(q.value)
+        self._state = torch.zeros(2, dtype=torch.int32, device=device)      # epoch, done
+        self._args = _lib.AllReduceArgs()
+        a = self._args
+        for r in range(world):
+            a.partial0[r], a.partial1[r], a.flags[r] = ptrs[r][0], ptrs[r][1], ptrs[r][2]
+        a.epoch = self._state.data_ptr()
+        a.done = self._state.data_ptr() + 4
+        a.world, a.rank, a.n = world, rank, rows * cols
+        self._keep = [_DeviceBuffer(self._own[j], (rows, cols), "<f2") for j in range(2)]
+        self.partials = [torch.as_tensor(k, device=device) for k in self._keep]
+        self.buf = 0
+        dist.barrier(group=group)       # nobody signals before everybody has mapped everything
+
+    def next_partial(self) -> torch.Tensor:
+        """fp16 [rows, cols] buffer the row-parallel Linear of THIS exchange must write its partial output into."""
+        return self.partials[self.buf]
+
+    def reduce(self, residual, out: torch.Tensor) -> torch.Tensor:
+        """out = fp16(fp16(sum over ranks of the partials just written) + residual); flips to the other buffer."""
+        a = self._args
+        a.buf = self.buf
+        a.residual = 0 if residual is None else residual.data_ptr()
+        a.out = out.data_ptr()
+        self._check(self.lib.mixq_allreduce_residual(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                    "allreduce_residual")
+        self.buf ^= 1
+        return out
+
+    def close(self):
+        torch.cuda.synchronize()
+        for p in self._mapped:
+            self.lib.mixq_ipc_close_handle(p)
+        self._mapped = []
+        self.partials, self._keep = [], []
+        for p in self._own:
+            self.lib.mixq_peer_free(p)
+        self._own = []
