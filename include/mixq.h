@@ -180,7 +180,7 @@ int mixq_mul_inplace(void* a, const void* b, long long n, void* stream);
 /* ---- The exchange step of the row-parallel Linears (o_proj, down_proj) under tensor parallelism, over NVLink peer memory.
  * The reference has no multi-GPU code (models/base.py:196-225 is accelerate placement); this replaces ncclAllReduce + the
  * decoder's residual add by ONE kernel per rank: out = fp16( fp16(sum over ranks of partial, fp32, rank order) + residual ).
- * Set-up (once per process): every rank allocates two partial buffers and kMaxPeers flag words with mixq_peer_alloc,
+ * Set-up (once per process): every rank allocates two partial buffers (two-shot: and two result buffers) and 16 flag words with mixq_peer_alloc,
  * publishes their handles (mixq_ipc_get_handle, 64 bytes) to the other ranks of the node, and maps theirs
  * (mixq_ipc_open_handle).  Per exchange: the rank's Linear writes its partial into ITS buffer `buf`, then every rank calls
  * mixq_allreduce_residual with the same n and buf.  Callers ALTERNATE buf = 0, 1, 0, 1, ... over successive exchanges (a rank
@@ -190,7 +190,9 @@ int mixq_mul_inplace(void* a, const void* b, long long n, void* stream);
 typedef struct mixq_allreduce_args {
   const void* partial0[8]; /* [rank]: that rank's partial buffer 0, as mapped in this process (own rank: the local pointer) */
   const void* partial1[8]; /* [rank]: buffer index 1 */
-  void* flags[8];          /* [rank]: that rank's 8 flag words (uint32), as mapped in this process */
+  void* flags[8];          /* [rank]: that rank's 16 flag words (uint32), as mapped in this process */
+  void* result0[8];        /* two-shot (world >= 4 pays off): [rank]: that rank's result buffer 0 / 1, as mapped in this process; */
+  void* result1[8];        /*   every rank reduces 1/world of the vector and pushes it to all; out = own result buffer `buf`. NULL = one-shot */
   void* epoch;             /* local uint32 */
   void* done;              /* local uint32 */
   const void* residual;    /* local fp16 [n] or NULL */

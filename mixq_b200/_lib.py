@@ -63,6 +63,8 @@ class AllReduceArgs(C.Structure):
         ("partial0", C.c_void_p * 8),
         ("partial1", C.c_void_p * 8),
         ("flags", C.c_void_p * 8),
+        ("result0", C.c_void_p * 8),
+        ("result1", C.c_void_p * 8),
         ("epoch", C.c_void_p),
         ("done", C.c_void_p),
         ("residual", C.c_void_p),

@@ -738,7 +738,13 @@ int mixq_allreduce_residual(const mixq_allreduce_args* a, void* stream) {
     k.partial[p][0] = static_cast<const __half*>(a->partial0[p]);
     k.partial[p][1] = static_cast<const __half*>(a->partial1[p]);
     k.flags[p] = static_cast<uint32_t*>(a->flags[p]);
+    k.result[p][0] = static_cast<__half*>(a->result0[p]);
+    k.result[p][1] = static_cast<__half*>(a->result1[p]);
+    if ((a->result0[p] == nullptr) != (a->result0[0] == nullptr) || (a->result1[p] == nullptr) != (a->result0[0] == nullptr))
+      return fail(MIXQ_EINVAL, "two-shot needs the result buffers of every rank");
   }
+  if (a->result0[0] != nullptr && a->out != a->result0[a->rank] && a->out != a->result1[a->rank])
+    return fail(MIXQ_EINVAL, "two-shot: out must be this rank's result buffer of the exchange");
   k.epoch = static_cast<uint32_t*>(a->epoch);
   k.done = static_cast<uint32_t*>(a->done);
   k.residual = static_cast<const __half*>(a->residual);

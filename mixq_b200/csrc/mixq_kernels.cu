@@ -236,14 +236,34 @@ cudaError_t launch_rope_attn_decode(const __half* qkv, __half* k_cache, __half* 
 
 // ---------------------------------------------------------------- all-reduce (+ residual) over NVLink peer memory
 // The exchange step of the row-parallel Linears (o_proj, down_proj): every rank has written its fp16 partial [n] into its own
-// peer-mapped buffer; each rank then reads ALL partials (local HBM + peers over NVLink / NVSwitch), sums them in fp32 in rank
-// order (bit-identical on every rank), rounds to fp16 (what an fp16 all-reduce returns), adds the residual stream as a separate
-// fp16 op and writes h.  One launch replaces ncclAllReduce + the residual add.
-//   flags[r][p]: word in rank r's memory that rank p sets to the epoch it has reached ("my partial e is complete").
+// peer-mapped buffer.  out = fp16( fp16(sum over ranks of partial, fp32, rank order) + residual ) on every rank, bit-identical.
+//   one-shot (a.result == nullptr): each rank reads ALL partials (local HBM + peers over NVLink / NVSwitch) and computes the
+//     whole vector: (world - 1) * n * 2 bytes of NVLink reads per rank, one handshake.  Best for two ranks.
+//   two-shot: rank r reduces only elements [r * n / world, (r + 1) * n / world) and PUSHES that slice into the result buffer
+//     of every rank (st over NVLink); a second handshake tells everybody that all slices have landed.  NVLink bytes per
+//     rank: 2 * (world - 1) / world * n * 2 instead of (world - 1) * n * 2.  `out` is then the local result buffer itself.
+//   flags[r][2 * p + phase]: word in rank r's memory that rank p sets to the exchange count it has reached.
 //   *epoch: this rank's count of finished exchanges; every block reads it on entry, the last block to leave bumps it — so
-//   the kernel is replayable from a CUDA graph.  Callers alternate between two partial buffers: a rank overwrites the
-//   buffer of exchange e only after its exchange e + 1, which needed every peer's signal e + 1, which a peer sends only
+//   the kernel is replayable from a CUDA graph.  Callers alternate between two partial (and result) buffers: a rank overwrites
+//   the buffer of exchange e only after its exchange e + 1, which needed every peer's signal e + 1, which a peer sends only
 //   after its own exchange e (its reads of that buffer) has completed.
+__device__ __forceinline__ void peer_signal(const AllReduceArgs& a, int phase, uint32_t e) {
+  __threadfence_system();
+  for (int p = 0; p < a.world; ++p)
+    if (p != a.rank) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flags[p] + 2 * a.rank + phase), "r"(e) : "memory");
+}
+__device__ __forceinline__ void peer_wait(const AllReduceArgs& a, int phase, uint32_t e) {
+  const uint64_t t0 = globaltimer_ns();
+  for (int p = 0; p < a.world; ++p) {
+    if (p == a.rank) continue;
+    uint32_t v, spins = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a.flags[a.rank] + 2 * p + phase) : "memory");
+      if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > MIXQ_SPIN_TIMEOUT_NS) spin_timeout_trap(11 + phase, p, static_cast<int>(e));
+    } while (static_cast<int32_t>(v - e) < 0);
+  }
+}
+
 __global__ void __launch_bounds__(256) allreduce_residual_kernel(AllReduceArgs a) {
   pdl_launch_dependents();
   pdl_wait();                                   // my partial (previous kernel of the stream) is complete and visible
@@ -251,25 +271,18 @@ __global__ void __launch_bounds__(256) allreduce_residual_kernel(AllReduceArgs a
   if (threadIdx.x == 0) {
     const uint32_t e = *reinterpret_cast<volatile uint32_t*>(a.epoch) + 1;
     s_epoch = e;
-    if (blockIdx.x == 0) {
-      __threadfence_system();
-      for (int p = 0; p < a.world; ++p)
-        if (p != a.rank) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flags[p] + a.rank), "r"(e) : "memory");
-    }
-    const uint64_t t0 = globaltimer_ns();
-    for (int p = 0; p < a.world; ++p) {
-      if (p == a.rank) continue;
-      uint32_t v, spins = 0;
-      do {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a.flags[a.rank] + p) : "memory");
-        if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > MIXQ_SPIN_TIMEOUT_NS) spin_timeout_trap(11, p, static_cast<int>(e));
-      } while (static_cast<int32_t>(v - e) < 0);
-    }
+    if (blockIdx.x == 0) peer_signal(a, 0, e);  // "my partial e is complete"
+    peer_wait(a, 0, e);
   }
   __syncthreads();
   const int buf = a.buf;
+  const bool two_shot = a.result[a.rank][buf] != nullptr;
   const long long nv = a.n >> 3;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
+  // two-shot: this rank owns vectors [v0, v1)
+  const long long per = (nv + a.world - 1) / a.world;
+  const long long v0 = two_shot ? per * a.rank : 0;
+  const long long v1 = two_shot ? (v0 + per < nv ? v0 + per : nv) : nv;
+  for (long long i = v0 + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < v1;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     float acc[8];
 #pragma unroll
@@ -295,12 +308,20 @@ __global__ void __launch_bounds__(256) allreduce_residual_kernel(AllReduceArgs a
       }
       o.h2[j] = y2;
     }
-    *(reinterpret_cast<uint4*>(a.out) + i) = o.u;
+    if (two_shot) {
+      for (int p = 0; p < a.world; ++p) *(reinterpret_cast<uint4*>(a.result[p][buf]) + i) = o.u;   // push my slice to everybody
+    } else {
+      *(reinterpret_cast<uint4*>(a.out) + i) = o.u;
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    if (atomicAdd(a.done, 1u) == gridDim.x - 1) {   // last block out: everybody has read *epoch
+    __threadfence_system();
+    if (atomicAdd(a.done, 1u) == gridDim.x - 1) {   // last block out: everybody has read *epoch and pushed its share
+      if (two_shot) {
+        peer_signal(a, 1, s_epoch);                  // "my slice of exchange e is in every result buffer"
+        peer_wait(a, 1, s_epoch);                    // ... and everybody else's is in mine
+      }
       *a.done = 0;
       __threadfence();
       *reinterpret_cast<volatile uint32_t*>(a.epoch) = s_epoch;

@@ -20,7 +20,8 @@ __global__ void mul_inplace_kernel(__half2* a, const __half2* b, long long n2);
 constexpr int kMaxPeers = 8;
 struct AllReduceArgs {
   const __half* partial[kMaxPeers][2];   // [rank][buffer]: every rank's two partial buffers as mapped into THIS process
-  uint32_t* flags[kMaxPeers];            // [rank]: that rank's flag words (kMaxPeers of them), as mapped into this process
+  __half* result[kMaxPeers][2];          // two-shot only: [rank][buffer] result buffers as mapped into this process (else nullptr)
+  uint32_t* flags[kMaxPeers];            // [rank]: that rank's 2 * kMaxPeers flag words, as mapped into this process
   uint32_t* epoch;                       // local: exchanges finished so far
   uint32_t* done;                        // local: blocks finished in the current launch
   const __half* residual;                // local [n] or nullptr

@@ -55,6 +55,7 @@ CONFIGS = {
     "llama-2-70b": LlamaConfig("llama-2-70b", 8192, 28672, 80, 64, 8, 32000),
     # CPU-oracle-sized configuration for tests / smoke
     "tiny": LlamaConfig("tiny", 256, 512, 2, 4, 4, 512),
+    "tiny8": LlamaConfig("tiny8", 1024, 2048, 2, 8, 8, 512),   # shards over 8 ranks
 }
 
 
@@ -199,7 +200,7 @@ class LlamaDecoder:
             attn = self._attention(qkv, past_len, li)
             if tp and self.xchg is not None:
                 L["o_proj"](attn, None, True, out=self.xchg.next_partial())
-                h = self.xchg.reduce(h, torch.empty_like(h))
+                h = self.xchg.reduce(h)
             elif tp:
                 h = h + self._allreduce(L["o_proj"](attn, None, True))
             else:
@@ -215,7 +216,7 @@ class LlamaDecoder:
                 _lib.check(self.lib.mixq_mul_inplace(gate.data_ptr(), up.data_ptr(), gate.numel(), self._stream()), "mul")
             if tp and self.xchg is not None:
                 L["down_proj"](gate, None, True, out=self.xchg.next_partial())
-                h = self.xchg.reduce(h, torch.empty_like(h))
+                h = self.xchg.reduce(h)
             elif tp:
                 h = h + self._allreduce(L["down_proj"](gate, None, True))
             else:

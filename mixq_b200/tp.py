@@ -61,19 +61,26 @@ class PeerExchange:
     process group.  Reads of the peers' partials travel over NVLink / NVSwitch inside the kernel; nothing goes through NCCL.
     """
 
-    def __init__(self, rows: int, cols: int, rank: int, world: int, group=None, device="cuda"):
+    def __init__(self, rows: int, cols: int, rank: int, world: int, group=None, device="cuda", two_shot=None):
         from . import _lib
+        import os
         import torch.distributed as dist
         if not (2 <= world <= 8):
             raise ValueError("PeerExchange needs 2..8 ranks on one node")
         if (rows * cols) % 8:
             raise ValueError("rows * cols must be a multiple of 8")
+        if two_shot is None:
+            # one-shot reads (world - 1) * n from the peers, two-shot moves 2 * (world - 1) / world * n and shakes hands twice
+            env = os.environ.get("MIXQ_TP_TWO_SHOT")
+            two_shot = (world >= 4) if env is None else env == "1"
+        self.two_shot = bool(two_shot)
         self.lib = _lib.load()
         self._check = _lib.check
         self.rows, self.cols, self.rank, self.world, self.device = rows, cols, rank, world, device
         nbytes = rows * cols * 2
+        sizes = [nbytes, nbytes, 256] + ([nbytes, nbytes] if self.two_shot else [])   # partial 0/1, flags, result 0/1
         self._own = []
-        for size in (nbytes, nbytes, 256):
+        for size in sizes:
             p = C.c_void_p()
             self._check(self.lib.mixq_peer_alloc(size, C.byref(p)), "peer_alloc")
             self._own.append(p.value)
@@ -85,9 +92,9 @@ class PeerExchange:
         gathered = [None] * world
         dist.all_gather_object(gathered, handles, group=group)
         self._mapped = []      # peer mappings to close
-        ptrs = [[0, 0, 0] for _ in range(world)]
+        ptrs = [[0] * len(sizes) for _ in range(world)]
         for r in range(world):
-            for j in range(3):
+            for j in range(len(sizes)):
                 if r == rank:
                     ptrs[r][j] = self._own[j]
                 else:
@@ -100,11 +107,15 @@ class PeerExchange:
         a = self._args
         for r in range(world):
             a.partial0[r], a.partial1[r], a.flags[r] = ptrs[r][0], ptrs[r][1], ptrs[r][2]
+            if self.two_shot:
+                a.result0[r], a.result1[r] = ptrs[r][3], ptrs[r][4]
         a.epoch = self._state.data_ptr()
         a.done = self._state.data_ptr() + 4
         a.world, a.rank, a.n = world, rank, rows * cols
-        self._keep = [_DeviceBuffer(self._own[j], (rows, cols), "<f2") for j in range(2)]
-        self.partials = [torch.as_tensor(k, device=device) for k in self._keep]
+        nbuf = 4 if self.two_shot else 2
+        self._keep = [_DeviceBuffer(self._own[j if j < 2 else j + 1], (rows, cols), "<f2") for j in range(nbuf)]
+        views = [torch.as_tensor(k, device=device) for k in self._keep]
+        self.partials, self.results = views[:2], views[2:]
         self.buf = 0
         dist.barrier(group=group)       # nobody signals before everybody has mapped everything
 
@@ -112,11 +123,17 @@ class PeerExchange:
         """fp16 [rows, cols] buffer the row-parallel Linear of THIS exchange must write its partial output into."""
         return self.partials[self.buf]
 
-    def reduce(self, residual, out: torch.Tensor) -> torch.Tensor:
-        """out = fp16(fp16(sum over ranks of the partials just written) + residual); flips to the other buffer."""
+    def reduce(self, residual, out: torch.Tensor = None) -> torch.Tensor:
+        """fp16(fp16(sum over ranks of the partials just written) + residual); flips to the other buffer.  One-shot writes
+        `out` (allocated when None); two-shot returns this rank's result buffer of the exchange (valid until the exchange
+        after the next one)."""
         a = self._args
         a.buf = self.buf
         a.residual = 0 if residual is None else residual.data_ptr()
+        if self.two_shot:
+            out = self.results[self.buf]
+        elif out is None:
+            out = torch.empty((self.rows, self.cols), dtype=torch.float16, device=self.device)
         a.out = out.data_ptr()
         self._check(self.lib.mixq_allreduce_residual(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
                     "allreduce_residual")
@@ -128,7 +145,7 @@ class PeerExchange:
         for p in self._mapped:
             self.lib.mixq_ipc_close_handle(p)
         self._mapped = []
-        self.partials, self._keep = [], []
+        self.partials, self.results, self._keep = [], [], []
         for p in self._own:
             self.lib.mixq_peer_free(p)
         self._own = []
