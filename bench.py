@@ -9,7 +9,8 @@ independent [512,1] forward; "decode length 1024" there is the number of timed i
 weights with ~1 % forced outlier channels, synthetic tokens.  A "step" = one pass of the MixLinear hot path over one batch:
 the whole decode step (32 layers x 5 MixLinears + norms + attention glue + fp16 lm_head), replayed from one CUDA graph.
 
-N > 1 shards every Linear column-/row-wise over N ranks (one NCCL all-reduce per row-parallel Linear), total work fixed:
+N > 1 shards every Linear column-/row-wise over N ranks; the one exchange per row-parallel Linear is this library's
+all-reduce + residual kernel over NVLink peer memory (MIXQ_TP_EXCHANGE=nccl: NCCL all-reduce + add).  Total work fixed:
 "scaling": "strong".
 
 Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for how each field is obtained.
@@ -363,6 +364,8 @@ def run_mixq(args):
         "per_linear": per_kind, "linear_share_of_step": tot_t * len(model.layers) / (ms * 1e-3 / args.steps),
     }
 
+    model_xchg = model.xchg is not None
+    model_xchg_two_shot = bool(model.xchg.two_shot) if model_xchg else False
     if rank == 0:
         step_s = ms * 1e-3 / args.steps
         fl_step, by_step = model.algorithmic_work()
@@ -375,7 +378,9 @@ def run_mixq(args):
                        "layers": len(model.layers), "global_batch": B, "parallelism": f"tp{world}", "bit": args.bit,
                        "l2": "weights (>= 6 GB per step) exceed the 126 MB L2: inputs larger than L2, no flush",
                        "outliers_layer0": {k: m._n_ind for k, m in model.layers[0].items() if isinstance(m, MixLinear_GEMM)},
-                       "cuda_graph": True, "programmatic_dependent_launch": True},
+                       "cuda_graph": True, "programmatic_dependent_launch": True,
+                       "exchange": (None if world == 1 else ("peer-memory kernel, " + ("two-shot" if model_xchg_two_shot else "one-shot")
+                                                              if model_xchg else "nccl all-reduce + add"))},
             "e2e": {"value": B / (ms_e2e * 1e-3 / args.steps), "unit": "tokens/s", "h2d_bytes_per_step": B * 8,
                     "d2h_bytes_per_step": B * 8, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,

@@ -143,6 +143,39 @@ int main(void) {
     assert got == want
 
 
+def test_allreduce_args_struct_layout_and_validation():
+    """mixq_allreduce_args (the tensor-parallel exchange) as the C compiler sees it vs the ctypes mirror; bad arguments are
+    rejected before any CUDA call."""
+    src = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "mixq.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(mixq_allreduce_args), offsetof(mixq_allreduce_args, partial1),
+         offsetof(mixq_allreduce_args, flags), offsetof(mixq_allreduce_args, result1), offsetof(mixq_allreduce_args, epoch),
+         offsetof(mixq_allreduce_args, out), offsetof(mixq_allreduce_args, n), offsetof(mixq_allreduce_args, buf));
+  return 0;
+}'''
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "t.c")
+        open(c, "w").write(src)
+        exe = os.path.join(td, "t")
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        got = [int(v) for v in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    A = _lib.AllReduceArgs
+    want = [ctypes.sizeof(A), A.partial1.offset, A.flags.offset, A.result1.offset, A.epoch.offset, A.out.offset, A.n.offset,
+            A.buf.offset]
+    assert got == want
+    lib = _lib.load()
+    a = A()
+    a.world, a.rank, a.n = 1, 0, 64            # a single rank has nothing to exchange
+    assert lib.mixq_allreduce_residual(ctypes.byref(a), None) != 0
+    assert b"all-reduce" in lib.mixq_last_error()
+    a.world, a.n = 2, 12                        # n % 8 != 0
+    assert lib.mixq_allreduce_residual(ctypes.byref(a), None) != 0
+
+
 def test_llama_accounting_formulas():
     """SURVEY.md §8(d): per-step algorithmic work of Llama-2-7B at M=512 = 6.63 TFLOP / 8.77 GB."""
     M, H, I, L = 512, 4096, 11008, 32
