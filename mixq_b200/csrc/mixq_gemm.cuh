@@ -35,7 +35,7 @@ struct LinearParams {
   int bn;              // 2-CTA kernel: run-time tile width W (multiple of 32, <= 512)
   int nstages;         // 2-CTA kernel: pipeline stages that fit PIPE_BYTES at this W
   int stage_bytes;     // 2-CTA kernel: bytes between consecutive stages (>= k_atoms * (16 KB + W/2 * 128), multiple of 1024)
-  int ablate;          // tuning aid (MIXQ_DEBUG_ABLATE; results are garbage): 1 = no MMAs, 2 = no activation loads, 4 = no weight loads
+  int ablate;          // tuning aid (MIXQ_DEBUG_ABLATE; results are garbage): 1 = no MMAs, 2 = no activation loads, 4 = no weight loads, 8 = 16-column epilogue reads, 16 = single outlier pass buffer (8 and 16 keep results exact)
   int k_atoms;         // 2-CTA kernel: 128-byte k-atoms per pipeline stage and TMA op (1, or 2 with 3-D tm_a / tm_b / tm_b2)
   const uint8_t* q_w;  // raw weight pointer + row pitch in bytes (L2 prefetch of the weight stream)
   long long q_w_pitch;

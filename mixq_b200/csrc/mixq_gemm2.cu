@@ -82,7 +82,7 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
   if (has_o) {
     const int spare = 512 - SLOTS * W;               // host guarantees W <= 448 with outliers: spare >= 64
     if (spare < W) {
-      if (spare >= 128) { NB = 2; R = (spare >> 1) & ~31; }
+      if (spare >= 128 && !(p.ablate & 16)) { NB = 2; R = (spare >> 1) & ~31; }   // (tuning knob 16: one big buffer instead)
       else { NB = 1; R = spare & ~31; }
       P = (W + R - 1) / R;
       R = ((W + P - 1) / P + 31) & ~31;
