@@ -43,6 +43,19 @@ unsigned long long mixq_launch_count(void);
 /* Tuning/testing override of the GEMM tile width for calls that do not carry their own tile_n:
  * 0 = heuristic (default), 128 or 256. */
 int mixq_set_tile_n(int tile_n);
+/* How a MixLinear GEMM of this shape would be launched (pure host arithmetic; sms <= 0 = ask the current device):
+ * which kernel, tile width, k-atoms per TMA op and pipeline stage, pipeline depth, work split, TMEM plan. */
+typedef struct mixq_linear_plan {
+  int two_cta;        /* 1: mixq_linear2_kernel (CTA pairs, 256 x tile_w tiles); 0: mixq_linear_kernel (128 x tile_w) */
+  int tile_w;         /* output columns of a tile */
+  int k_atoms;        /* 128-byte k-atoms per TMA op / stage */
+  int stage_bytes, nstages;
+  int tiles, units, tiles_per_unit;   /* units = CTA pairs (two_cta) or CTAs; tiles_per_unit = the busiest unit */
+  int acc_slots;      /* int32 accumulators resident in TMEM (2: tile i + 1's MMAs overlap tile i's epilogue) */
+  int passes, pass_cols, pass_buffers;   /* epilogue passes per tile and the fp32 outlier accumulator buffers */
+  int tmem_cols;      /* TMEM columns in use (<= 512) */
+} mixq_linear_plan;
+int mixq_plan_linear(int M, int N, int K, int bit, int n_ind, int swiglu_pair, int tile_n, int sms, mixq_linear_plan* out);
 /* Programmatic dependent launch (default on; MIXQ_PDL=0 in the environment or on = 0 turns it off): every kernel of the
  * library is launched so that its CTAs may take an SM as soon as the previous kernel's CTA there has exited, set up, and
  * prefetch constants (the quantised weights) while the previous kernel drains; each kernel waits for its predecessors

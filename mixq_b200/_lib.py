@@ -76,6 +76,13 @@ class AllReduceArgs(C.Structure):
     ]
 
 
+class LinearPlan(C.Structure):
+    """Mirror of `mixq_linear_plan` (include/mixq.h)."""
+
+    _fields_ = [(n, C.c_int) for n in ("two_cta", "tile_w", "k_atoms", "stage_bytes", "nstages", "tiles", "units",
+                                         "tiles_per_unit", "acc_slots", "passes", "pass_cols", "pass_buffers", "tmem_cols")]
+
+
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 
 # name -> argtypes; every function returns int unless listed in _RESTYPES
@@ -103,6 +110,7 @@ SIGNATURES = {
     "mixq_allreduce_residual": [C.POINTER(AllReduceArgs), _vp],
     "mixq_set_tile_n": [_i],
     "mixq_set_pdl": [_i],
+    "mixq_plan_linear": [_i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(LinearPlan)],
     "mixq_set_trace_buffer": [_vp],
     "mixq_version": [],
     "mixq_launch_count": [],

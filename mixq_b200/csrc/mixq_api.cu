@@ -246,6 +246,72 @@ int pick_tile_n(int requested, int M, int N, int sms, bool tmem_outliers) {
 
 int pick_row_groups(RowQuantArgs* a, int grid, int warps_per_cta, long long smem_budget);
 
+// Launch plan of one MixLinear GEMM: which kernel, tile width, k-atoms per TMA op, pipeline depth, TMEM plan.  Pure host
+// arithmetic (exported as mixq_plan_linear so that the heuristics are testable without a GPU).
+struct GemmPlan {
+  int two_cta, tile_w, k_atoms, stage_bytes, nstages, tiles, tiles_per_unit, units;
+  TmemPlan tmem;
+};
+int plan_gemm(int M, int N, int K, int bit, int n_out, bool pair, int tile_req, int sms, GemmPlan* g) {
+  if (M < 1 || N < 8 || K < 16 || sms < 1) return fail(MIXQ_EINVAL, "M>=1, N>=8, K>=16 required");
+  const bool w4 = bit == 4;
+  // M > 128: CTA pairs (cta_group::2) own 256 x bn tiles — half the L2 -> SM bytes per MMA cycle (mixq_gemm2.cu)
+  bool two_cta = !w4 && M > 128 && sms >= 2;
+  const int npairs = sms / 2;
+  if (pair && (!two_cta || N % 16 != 0)) return fail(MIXQ_EINVAL, "SwiGLU pair needs bit 8, M > 128 and N % 16 == 0");
+  // pair: a tile of width W holds W/2 gate columns (staged by CTA 0) and the SAME W/2 up columns (staged by CTA 1)
+  int bn = two_cta ? pick_w2(tile_req, M, pair ? 2 * N : N, n_out, npairs) : pick_tile_n(tile_req, M, N, sms, n_out > 0);
+  // narrow tiles are paced by the TMA op count (one op ~340 clocks of the SM's TMA unit whatever its size): two k-atoms
+  // (256 bytes of K) per op and pipeline stage whenever at least three such stages fit
+  int k_atoms = (two_cta && K % 128 == 0 && K >= 256 && bn <= 256) ? 2 : 1;
+  if (const char* e = getenv("MIXQ_DEBUG_KATOMS")) { const int v = atoi(e); if (v == 1) k_atoms = 1; }
+  int stage2 = 0, nstages2 = 0;
+  for (;;) {
+    stage2 = k_atoms * (Gemm2Cfg::A_BYTES + (bn / 2) * 128);
+    if (const char* e = getenv("MIXQ_DEBUG_STAGE_BYTES")) { const int v = atoi(e); if (v >= stage2 && v % 1024 == 0) stage2 = v; }
+    nstages2 = Gemm2Cfg::PIPE_BYTES / stage2;
+    if (nstages2 > Gemm2Cfg::MAX_STAGES) nstages2 = Gemm2Cfg::MAX_STAGES;
+    if (const char* e = getenv("MIXQ_DEBUG_STAGES")) { const int v = atoi(e); if (v >= 2 && v < nstages2) nstages2 = v; }
+    // the outlier k-blocks of a tile stay resident in the ring during the epilogue passes: with the big stages they may not fit
+    if (k_atoms == 2 && (nstages2 < 3 || (n_out + 63) / 64 > nstages2 - 1)) { k_atoms = 1; continue; }
+    break;
+  }
+  // the outlier k-blocks of a tile stay resident in the ring during the epilogue passes: they must all fit
+  if (two_cta && (n_out + 63) / 64 > nstages2 - 1) {
+    if (pair) return fail(MIXQ_EINVAL, "SwiGLU pair: too many outlier columns for the resident outlier stages");
+    two_cta = false;
+    bn = pick_tile_n(tile_req, M, N, sms, n_out > 0);
+  }
+  g->two_cta = two_cta ? 1 : 0;
+  g->tile_w = bn;
+  g->k_atoms = two_cta ? k_atoms : 1;
+  if (two_cta) {
+    g->stage_bytes = stage2;
+    g->nstages = nstages2;
+    const int wout = pair ? bn / 2 : bn;
+    g->tiles = ((M + 255) / 256) * ((N + wout - 1) / wout);
+    g->units = npairs;
+    g->tiles_per_unit = (g->tiles + npairs - 1) / npairs;
+    bool single = false;
+    if (const char* e = getenv("MIXQ_DEBUG_ABLATE")) single = (atoi(e) & 16) != 0;
+    g->tmem = plan_tmem(bn, n_out > 0, g->tiles_per_unit, single);
+  } else {
+    g->stage_bytes = w4 ? (bn == 256 ? GemmCfg<256, true>::STAGE_BYTES : GemmCfg<128, true>::STAGE_BYTES)
+                        : (bn == 256 ? GemmCfg<256, false>::STAGE_BYTES : GemmCfg<128, false>::STAGE_BYTES);
+    g->nstages = w4 ? (bn == 256 ? GemmCfg<256, true>::STAGES : GemmCfg<128, true>::STAGES)
+                    : (bn == 256 ? GemmCfg<256, false>::STAGES : GemmCfg<128, false>::STAGES);
+    g->tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
+    g->units = sms;
+    g->tiles_per_unit = (g->tiles + sms - 1) / sms;
+    const int acc_cols = bn * (n_out > 0 ? 2 : 1);       // mixq_gemm.cu: s32 accumulator [+ f32 outlier accumulator]
+    g->tmem.slots = (2 * acc_cols <= 512) ? 2 : 1;
+    g->tmem.passes = 1;
+    g->tmem.pass_cols = bn;
+    g->tmem.buffers = 1;
+  }
+  return 0;
+}
+
 struct GemmCall {
   const void* q_x;
   const void* q_w;
@@ -282,36 +348,15 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
   if (c.n_out > 0 && (c.ld_ao % 8 != 0 || c.ld_wc % 8 != 0 || c.ld_ao < c.n_out || c.ld_wc < c.n_out))
     return fail(MIXQ_EINVAL, "outlier buffers need ld % 8 == 0 and ld >= n_ind");
   const bool w4 = (c.bit == 4);
-  // M > 128: CTA pairs (cta_group::2) own 256 x bn tiles — half the L2 -> SM bytes per MMA cycle (mixq_gemm2.cu)
-  bool two_cta = !w4 && c.M > 128 && di.sms >= 2;
-  const int npairs = di.sms / 2;
   const bool pair = c.q_w_up != nullptr;
-  if (pair && (!two_cta || c.bias != nullptr || !c.scale_col_up || (c.n_out > 0 && !c.weight_cache_up) || c.epilogue != EPI_DEQUANT_F16 ||
-               c.outl != nullptr || c.residual != nullptr || c.N % 16 != 0))
-    return fail(MIXQ_EINVAL, "SwiGLU pair needs bit 8, M > 128, N % 16 == 0, both scale/weight_cache sets, no bias/residual/addend");
-  // pair: a tile of width W holds W/2 gate columns (staged by CTA 0) and the SAME W/2 up columns (staged by CTA 1)
-  int bn = two_cta ? pick_w2(c.tile_n, c.M, pair ? 2 * c.N : c.N, c.n_out, npairs) : pick_tile_n(c.tile_n, c.M, c.N, di.sms, c.n_out > 0);
-  // narrow tiles are paced by the TMA op count (one op ~340 clocks of the SM's TMA unit whatever its size): two k-atoms
-  // (256 bytes of K) per op and pipeline stage whenever at least three such stages fit
-  int k_atoms = (two_cta && c.K % 128 == 0 && c.K >= 256 && bn <= 256) ? 2 : 1;
-  if (const char* e = getenv("MIXQ_DEBUG_KATOMS")) { const int v = atoi(e); if (v == 1) k_atoms = 1; }
-  int stage2 = 0, nstages2 = 0;
-  for (;;) {
-    stage2 = k_atoms * (Gemm2Cfg::A_BYTES + (bn / 2) * 128);
-    if (const char* e = getenv("MIXQ_DEBUG_STAGE_BYTES")) { const int v = atoi(e); if (v >= stage2 && v % 1024 == 0) stage2 = v; }
-    nstages2 = Gemm2Cfg::PIPE_BYTES / stage2;
-    if (nstages2 > Gemm2Cfg::MAX_STAGES) nstages2 = Gemm2Cfg::MAX_STAGES;
-    if (const char* e = getenv("MIXQ_DEBUG_STAGES")) { const int v = atoi(e); if (v >= 2 && v < nstages2) nstages2 = v; }
-    // the outlier k-blocks of a tile stay resident in the ring during the epilogue passes: with the big stages they may not fit
-    if (k_atoms == 2 && (nstages2 < 3 || (c.n_out + 63) / 64 > nstages2 - 1)) { k_atoms = 1; continue; }
-    break;
-  }
-  // the outlier k-blocks of a tile stay resident in the ring during the epilogue passes: they must all fit
-  if (two_cta && (c.n_out + 63) / 64 > nstages2 - 1) {
-    if (pair) return fail(MIXQ_EINVAL, "SwiGLU pair: too many outlier columns for the resident outlier stages");
-    two_cta = false;
-    bn = pick_tile_n(c.tile_n, c.M, c.N, di.sms, c.n_out > 0);
-  }
+  GemmPlan gp{};
+  if (int r = plan_gemm(c.M, c.N, c.K, c.bit, c.n_out, pair, c.tile_n, di.sms, &gp)) return r;
+  const bool two_cta = gp.two_cta != 0;
+  const int npairs = di.sms / 2;
+  if (pair && (c.bias != nullptr || !c.scale_col_up || (c.n_out > 0 && !c.weight_cache_up) || c.epilogue != EPI_DEQUANT_F16 ||
+               c.outl != nullptr || c.residual != nullptr))
+    return fail(MIXQ_EINVAL, "SwiGLU pair needs both scale/weight_cache sets and no bias/residual/addend");
+  const int bn = gp.tile_w, k_atoms = gp.k_atoms, stage2 = gp.stage_bytes, nstages2 = gp.nstages;
   const int b_rows = two_cta ? bn / 2 : bn;
 
   LinearParams p{};
@@ -513,6 +558,33 @@ int mixq_set_tile_n(int tile_n) {
   if (tile_n != 0 && (tile_n < 32 || tile_n > 512 || tile_n % 32 != 0))
     return fail(MIXQ_EINVAL, "tile_n must be 0 or a multiple of 32 up to 512 (the 1-CTA kernel honours 128 and 256 only)");
   g_tile_n.store(tile_n, std::memory_order_relaxed);
+  return 0;
+}
+
+int mixq_plan_linear(int M, int N, int K, int bit, int n_ind, int swiglu_pair, int tile_n, int sms, mixq_linear_plan* out) {
+  if (out == nullptr) return fail(MIXQ_EINVAL, "null plan");
+  if (bit != 8 && bit != 4) return fail(MIXQ_EINVAL, "bit must be 8 or 4");
+  if (K % 16 != 0 || N % 8 != 0) return fail(MIXQ_EINVAL, "K % 16 == 0 and N % 8 == 0 required");
+  if (sms <= 0) {
+    DeviceInfo di;
+    if (int r = device_info(&di)) return r;
+    sms = di.sms;
+  }
+  GemmPlan g{};
+  if (int r = plan_gemm(M, N, K, bit, n_ind, swiglu_pair != 0, tile_n, sms, &g)) return r;
+  out->two_cta = g.two_cta;
+  out->tile_w = g.tile_w;
+  out->k_atoms = g.k_atoms;
+  out->stage_bytes = g.stage_bytes;
+  out->nstages = g.nstages;
+  out->tiles = g.tiles;
+  out->units = g.units;
+  out->tiles_per_unit = g.tiles_per_unit;
+  out->acc_slots = g.tmem.slots;
+  out->passes = g.tmem.passes;
+  out->pass_cols = g.tmem.pass_cols;
+  out->pass_buffers = g.tmem.buffers;
+  out->tmem_cols = g.two_cta ? g.tmem.columns(g.tile_w, n_ind > 0) : g.tmem.slots * g.tile_w * (n_ind > 0 ? 2 : 1);
   return 0;
 }
 

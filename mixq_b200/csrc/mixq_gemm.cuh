@@ -71,4 +71,35 @@ struct Gemm2Cfg {
 };
 __global__ void mixq_linear2_kernel(const __grid_constant__ LinearParams p);
 
+// TMEM plan of the 2-CTA kernel (512 columns), ONE definition for the kernel and for the host-side planner
+// (mixq_plan_linear, tests/test_host_cpu.py).  SLOTS int32 accumulators of W columns: two when a pair has several tiles and
+// they fit, so that the MMAs of tile i + 1 run while the epilogue drains tile i.  What is left holds the fp32 accumulator of
+// the skinny outlier GEMM: all W columns at once when they fit (one pass), otherwise NB = 1 or 2 buffers of R columns that
+// the MMA warp refills while the epilogue drains the tile pass by pass (balanced: 352 -> 6 x 64, not 5 x 64 + 32).  Without
+// outliers a "pass" is the whole tile and the pass buffers ARE the accumulator slots.
+struct TmemPlan {
+  int slots;    // int32 accumulator slots (1 or 2)
+  int passes;   // P: epilogue passes per tile
+  int pass_cols;// R: accumulator columns per pass (both CTA halves together)
+  int buffers;  // NB: pass buffers / barrier pairs in use (1 or 2)
+  __host__ __device__ int columns(int W, bool has_o) const { return slots * W + (has_o ? buffers * pass_cols : 0); }
+};
+__host__ __device__ inline TmemPlan plan_tmem(int W, bool has_o, int tiles_of_pair, bool single_buffer) {
+  TmemPlan t;
+  t.slots = (tiles_of_pair > 1 && 2 * W + (has_o ? 64 : 0) <= 512) ? 2 : 1;
+  t.passes = 1;
+  t.pass_cols = W;
+  t.buffers = has_o ? 1 : t.slots;
+  if (has_o) {
+    const int spare = 512 - t.slots * W;             // the host guarantees W <= 448 with outliers: spare >= 64
+    if (spare < W) {
+      if (spare >= 128 && !single_buffer) { t.buffers = 2; t.pass_cols = (spare >> 1) & ~31; }
+      else { t.buffers = 1; t.pass_cols = spare & ~31; }
+      t.passes = (W + t.pass_cols - 1) / t.pass_cols;
+      t.pass_cols = ((W + t.passes - 1) / t.passes + 31) & ~31;
+    }
+  }
+  return t;
+}
+
 }  // namespace mixq

@@ -70,24 +70,11 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
   const bool has_o = nko > 0;
   const uint32_t atom_tx = 2u * static_cast<uint32_t>(Cfg::A_BYTES + bh * 128);    // both CTAs' bytes land on one barrier
   const uint32_t b_atom = static_cast<uint32_t>(bh) * 128u;                         // bytes between the k-atoms of a weight stage
-  // TMEM plan (512 columns).  SLOTS int32 accumulators of W columns: two when a pair has several tiles and they fit, so
-  // that the MMAs of tile i + 1 run while the epilogue drains tile i.  What is left holds the fp32 accumulator of the skinny
-  // outlier GEMM: all W columns at once when they fit (one pass), otherwise NB = 1 or 2 buffers of R columns that the MMA
-  // warp refills while the epilogue drains the tile pass by pass (balanced: 352 -> 6 x 64, not 5 x 64 + 32).  Without
-  // outliers a "pass" is the whole tile and the pass buffers ARE the accumulator slots.
-  // Passes are numbered globally (G = tile * P + c): pass G uses barrier pair / buffer G % NB in phase (G / NB) & 1.
+  // TMEM plan (plan_tmem, mixq_gemm.cuh).  Passes are numbered globally (G = tile * P + c): pass G uses barrier pair /
+  // buffer G % NB in phase (G / NB) & 1.
   const int my_tiles_geo = (pair < ntiles) ? (ntiles - 1 - pair) / npairs + 1 : 0;
-  const int SLOTS = (my_tiles_geo > 1 && 2 * W + (has_o ? 64 : 0) <= 512) ? 2 : 1;
-  int P = 1, R = W, NB = has_o ? 1 : SLOTS;
-  if (has_o) {
-    const int spare = 512 - SLOTS * W;               // host guarantees W <= 448 with outliers: spare >= 64
-    if (spare < W) {
-      if (spare >= 128 && !(p.ablate & 16)) { NB = 2; R = (spare >> 1) & ~31; }   // (tuning knob 16: one big buffer instead)
-      else { NB = 1; R = spare & ~31; }
-      P = (W + R - 1) / R;
-      R = ((W + P - 1) / P + 31) & ~31;
-    }
-  }
+  const TmemPlan tp = plan_tmem(W, has_o, my_tiles_geo, (p.ablate & 16) != 0);   // (tuning knob 16: one big pass buffer)
+  const int SLOTS = tp.slots, P = tp.passes, R = tp.pass_cols, NB = tp.buffers;
   const uint32_t outl_col0 = static_cast<uint32_t>(SLOTS * W);   // first TMEM column of the outlier buffers
 
   auto stage_a = [&](int s) { return smem + static_cast<size_t>(s) * stage_bytes; };

@@ -176,6 +176,76 @@ int main(void) {
     assert lib.mixq_allreduce_residual(ctypes.byref(a), None) != 0
 
 
+def _plan(M, N, K, bit=8, n=0, pair=0, tile=0, sms=148):
+    lib = _lib.load()
+    pl = _lib.LinearPlan()
+    rc = lib.mixq_plan_linear(M, N, K, bit, n, pair, tile, sms, ctypes.byref(pl))
+    return rc, pl
+
+
+def test_launch_plan_headline_shapes():
+    """The plans the Llama-2-7B batch-512 step runs with: tile widths, k-atoms, TMEM plan."""
+    rc, p = _plan(512, 12288, 4096, n=41)                       # W_pack: one 256 x 352 tile per CTA pair
+    assert rc == 0 and (p.two_cta, p.tile_w, p.k_atoms, p.tiles, p.tiles_per_unit) == (1, 352, 1, 70, 1)
+    assert (p.acc_slots, p.passes, p.pass_cols, p.pass_buffers, p.tmem_cols) == (1, 6, 64, 2, 480)
+    rc, p = _plan(512, 4096, 4096, n=41)                        # o_proj: narrow tile, two k-atoms per TMA op
+    assert rc == 0 and (p.two_cta, p.tile_w, p.k_atoms, p.nstages, p.passes, p.tmem_cols) == (1, 128, 2, 4, 1, 256)
+    rc, p = _plan(512, 4096, 11008, n=110)                      # down_proj: two resident outlier k-blocks still fit
+    assert rc == 0 and (p.tile_w, p.k_atoms, p.nstages) == (128, 2, 4)
+    rc, p = _plan(512, 11008, 4096, n=41, pair=1)               # SwiGLU pair: 2 x 11008 columns, two tiles per CTA pair
+    assert rc == 0 and (p.tile_w, p.k_atoms, p.tiles, p.tiles_per_unit, p.acc_slots) == (320, 1, 138, 2, 1)
+    assert (p.passes, p.pass_cols, p.pass_buffers) == (4, 96, 2)
+    rc, p = _plan(32, 4096, 4096, n=41)                         # C1: M <= 128 runs the 1-CTA kernel
+    assert rc == 0 and p.two_cta == 0 and p.tile_w in (128, 256) and p.units == 148
+    rc, p = _plan(512, 12288, 4096, bit=4, n=128)               # W4 runs the 1-CTA kernel as well
+    assert rc == 0 and p.two_cta == 0
+    rc, _ = _plan(64, 11008, 4096, pair=1)                      # the pair launch needs the 2-CTA kernel
+    assert rc != 0 and b"pair" in _lib.load().mixq_last_error()
+
+
+def test_launch_plan_invariants_over_all_configs():
+    """Every Linear shape of BASELINE.json's configs (7B / 8B / 70B, TP 1..8, batch 32..512, 0..200 outlier columns) gets a
+    plan that fits the hardware: TMEM <= 512 columns, pipeline <= 192 KB, resident outlier stages, passes cover the tile."""
+    models = {"7b": (4096, 11008, 32, 32), "8b": (4096, 14336, 32, 8), "70b": (8192, 28672, 64, 8)}
+    seen = 0
+    for H, I, heads, kv in models.values():
+        D = H // heads
+        for tp in (1, 2, 4, 8):
+            shapes = [((heads + 2 * kv) * D // tp, H, 0), (H, heads * D // tp, 0), (I // tp, H, 0), (I // tp, H, 1), (H, I // tp, 0)]
+            for N, K, pair in shapes:
+                if K % 16 or N % 16:
+                    continue
+                for M in (32, 128, 129, 256, 512):
+                    for n in (0, 41, 110, 128, 200):
+                        if n > K:
+                            continue
+                        rc, p = _plan(M, N, K, n=n, pair=pair)
+                        if pair and M <= 128:
+                            assert rc != 0
+                            continue
+                        if pair and rc != 0:            # too many outlier columns for the resident stages: documented limit
+                            assert n > 128
+                            continue
+                        assert rc == 0, (M, N, K, n, pair, _lib.load().mixq_last_error())
+                        seen += 1
+                        assert 1 <= p.tmem_cols <= 512, (M, N, K, n, pair, p.tmem_cols)
+                        assert p.tiles >= 1 and p.tiles_per_unit == -(-p.tiles // p.units)
+                        assert p.passes * p.pass_cols >= p.tile_w and p.pass_buffers in (1, 2)
+                        if p.two_cta:
+                            assert M > 128 and p.tile_w % 32 == 0 and 128 <= p.tile_w <= (448 if n else 512)
+                            assert p.stage_bytes == p.k_atoms * (16384 + p.tile_w // 2 * 128)
+                            assert 2 <= p.nstages <= 8 and p.nstages * p.stage_bytes <= 192 * 1024
+                            assert -(-n // 64) <= p.nstages - 1              # outlier k-blocks stay resident during the passes
+                            assert p.pass_cols % 32 == 0
+                            if p.k_atoms == 2:
+                                assert K % 128 == 0 and p.tile_w <= 256 and p.nstages >= 3
+                            if p.acc_slots == 2:
+                                assert p.tiles_per_unit > 1 and 2 * p.tile_w + (64 if n else 0) <= 512
+                        else:
+                            assert p.tile_w in (128, 256) and p.k_atoms == 1
+    assert seen > 500
+
+
 def test_llama_accounting_formulas():
     """per-step algorithmic work of Llama-2-7B at M=512 = 6.63 TFLOP / 8.77 GB."""
     M, H, I, L = 512, 4096, 11008, 32
