@@ -300,6 +300,20 @@ def mixgemm_sample(a, q_w, scale_col, ind):
     return dequantize(gemm_i8(q_x, q_w), xs, scale_col, outl=outl)
 
 
+def tp_exchange(partials, residual=None) -> np.ndarray:
+    """The tensor-parallel exchange of the row-parallel Linears (no counterpart in the reference, which is single-GPU:
+    models/base.py:196-225 only places layers): h = fp16( fp16(sum over ranks of partial) + residual ), the sum taken in fp32
+    in RANK ORDER (so every rank gets the same bits) and rounded to fp16 once — what an fp16 all-reduce returns — before the
+    decoder's residual add, a separate fp16 op.  mixq_b200/csrc/mixq_kernels.cu: allreduce_residual_kernel."""
+    acc = np.zeros(partials[0].shape, F32)
+    for part in partials:
+        acc = (acc + part.astype(F32)).astype(F32)
+    y = acc.astype(F16)
+    if residual is not None:
+        y = (y.astype(F32) + residual.astype(F32)).astype(F16)
+    return y
+
+
 def linear_fp32(x, weight, bias=None):
     """The un-quantised fp32 Linear MixLinear replaces: ground truth for the error budget."""
     y = np.asarray(x).astype(F32) @ np.asarray(weight).astype(F32).T

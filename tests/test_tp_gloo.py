@@ -41,12 +41,19 @@ def _run_layer(w, rank, world, allreduce):
     return outs, layer
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, peer_semantics=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from mixq_b200 import tp
+    from oracle import mixq_oracle as O
 
     def allreduce(a):
+        if peer_semantics:
+            # what the peer-memory exchange kernel does (mixq_allreduce_residual): every rank reads ALL partials and sums
+            # them in fp32 in rank order, one rounding to fp16; the residual add stays a separate fp16 op (decode_step)
+            parts = [torch.empty_like(torch.from_numpy(a)) for _ in range(world)]
+            dist.all_gather(parts, torch.from_numpy(np.ascontiguousarray(a)))
+            return O.tp_exchange([t.numpy() for t in parts])
         t = torch.from_numpy(a.astype(np.float32))   # fp16 partial sums, reduced; NCCL does this natively in fp16
         tp.all_reduce_sum(t)
         return t.numpy().astype(np.float16)
@@ -56,7 +63,8 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_tp2_matches_single_rank():
+@pytest.mark.parametrize("peer_semantics", [False, True])
+def test_tp2_matches_single_rank(peer_semantics):
     world = 2
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -64,7 +72,7 @@ def test_tp2_matches_single_rank():
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, peer_semantics)) for r in range(world)]
     for p in procs:
         p.start()
     got = {}
@@ -102,3 +110,24 @@ def test_shard_helpers():
         tp.shard_rows(w, 0, 3)
     q, k, v = torch.zeros(4, 2), torch.ones(2, 2), 2 * torch.ones(2, 2)
     assert tp.pack_qkv_shard(q, k, v, 1, 2)[:, 0].tolist() == [0, 0, 1, 2]
+
+
+def test_tp_exchange_oracle_properties():
+    """oracle.tp_exchange (the arithmetic of allreduce_residual_kernel): exact for two ranks, rank-order deterministic, and the
+    residual is a SEPARATE fp16 op (two roundings)."""
+    from oracle import mixq_oracle as O
+    rng = np.random.default_rng(0)
+    parts = [rng.standard_normal((16, 64)).astype(np.float16) for _ in range(8)]
+    res = rng.standard_normal((16, 64)).astype(np.float16)
+    two = O.tp_exchange(parts[:2])
+    assert np.array_equal(two, (parts[0].astype(np.float64) + parts[1].astype(np.float64)).astype(np.float16))
+    assert np.array_equal(O.tp_exchange(parts[:2]), O.tp_exchange(parts[1::-1]))        # a + b == b + a in fp32
+    y8 = O.tp_exchange(parts)
+    ref8 = np.zeros((16, 64), np.float32)
+    for p_ in parts:
+        ref8 = ref8 + p_.astype(np.float32)
+    assert np.array_equal(y8, ref8.astype(np.float16))
+    exact = sum(p_.astype(np.float64) for p_ in parts)
+    assert np.abs(y8.astype(np.float64) - exact).max() <= np.abs(exact).max() * 2 ** -10   # within fp16 rounding of the true sum
+    with_res = O.tp_exchange(parts, res)
+    assert np.array_equal(with_res, (y8.astype(np.float32) + res.astype(np.float32)).astype(np.float16))

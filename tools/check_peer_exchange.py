@@ -24,7 +24,7 @@ def main():
     ex = PeerExchange(M, H, rank, world, two_shot=two_shot)
     kernel_copy = os.environ.get("CHECK_MEMCPY") != "1"       # a kernel (not a memcpy node) fills the partial buffer
 
-    def reference(parts, res):
+    def reference(parts, res):                # == oracle.mixq_oracle.tp_exchange, restated in torch on the device
         acc = torch.zeros(M, H, dtype=torch.float32, device="cuda")
         for p_ in parts:                      # rank order, fp32 — what the kernel does (exact for 2 ranks, rounds beyond)
             acc += p_.float()
