@@ -41,7 +41,8 @@ int mixq_version(void);
 /* Number of kernels this library has launched on the calling process so far (bench.py's gpu_launches). */
 unsigned long long mixq_launch_count(void);
 /* Tuning/testing override of the GEMM tile width for calls that do not carry their own tile_n:
- * 0 = heuristic (default), 128 or 256. */
+ * 0 = heuristic (default); a multiple of 32 up to 512 for the 2-CTA kernel (M > 128, bit 8; capped at 448 with outlier
+ * columns), of which the 1-CTA kernel honours 128 and 256 only.  mixq_plan_linear reports what a shape resolves to. */
 int mixq_set_tile_n(int tile_n);
 /* How a MixLinear GEMM of this shape would be launched (pure host arithmetic; sms <= 0 = ask the current device):
  * which kernel, tile width, k-atoms per TMA op and pipeline stage, pipeline depth, work split, TMEM plan. */
