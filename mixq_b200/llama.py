@@ -265,6 +265,75 @@ class LlamaDecoder:
         self.graph.replay()
         return self._static_logits
 
+    # ------------------------------------------------------------------ checkpoints (the reference's on-disk layout)
+    def _split_qkv(self, w_pack: MixLinear_GEMM):
+        """W_pack -> (q_proj, k_proj, v_proj): the inverse of models/llama.py:98-166 (per-row scales make it lossless)."""
+        cfg, D = self.cfg, self.cfg.head_dim
+        sizes = [cfg.heads * D, cfg.kv_heads * D, cfg.kv_heads * D]
+        out, r0 = [], 0
+        fpn = getattr(w_pack, "fp_features_num", 128)
+        for n in sizes:
+            m = MixLinear_GEMM(w_pack.in_features, n, False, w_pack.q_weight.device, w_pack.bit, cache=self.cache,
+                               fp_features_num=fpn)
+            m.q_weight.copy_(w_pack.q_weight[r0:r0 + n])
+            m.scale_col.copy_(w_pack.scale_col[:, r0:r0 + n])
+            if w_pack.bit == 4:
+                m._wc_buf[:, :fpn] = w_pack._wc_buf[r0:r0 + n, :fpn]
+                m._ind_buf[:fpn] = w_pack._ind_buf[:fpn]
+                m._n_ind = fpn
+            out.append(m)
+            r0 += n
+        return out
+
+    def save_quantized(self, save_dir: str, safetensors: bool = False, shard_size="10GB"):
+        """Write this model in the layout of the reference's save_quantized (models/base.py:78-119; HF Llama module names),
+        so that `from_quantized` here — or the reference's own loader — reads it back.  Single rank only."""
+        from . import checkpoint as ck
+        if self.world != 1:
+            raise ValueError("save_quantized writes the un-sharded model: use world_size 1")
+        mods, extra = {}, {"model.embed_tokens.weight": self.embed, "model.norm.weight": self.norm_f, "lm_head.weight": self.lm_head}
+        for i, L in enumerate(self.layers):
+            p = f"model.layers.{i}."
+            q, k, v = self._split_qkv(L["W_pack"])
+            mods[p + "self_attn.q_proj"], mods[p + "self_attn.k_proj"], mods[p + "self_attn.v_proj"] = q, k, v
+            mods[p + "self_attn.o_proj"] = L["o_proj"]
+            mods[p + "mlp.gate_proj"], mods[p + "mlp.up_proj"], mods[p + "mlp.down_proj"] = L["gate_proj"], L["up_proj"], L["down_proj"]
+            extra[p + "input_layernorm.weight"] = L["ln1"]
+            extra[p + "post_attention_layernorm.weight"] = L["ln2"]
+        return ck.save_quantized(save_dir, mods, {"w_bit": self.bit, "version": "MIX", "q_group_size": 128}, extra=extra,
+                                 safetensors=safetensors, shard_size=shard_size)
+
+    @classmethod
+    def from_quantized(cls, save_dir: str, cfg: LlamaConfig, batch: int, device="cuda", safetensors: bool = False):
+        """models/base.py:162-229 for the decode harness: load a MixQ checkpoint directory (q/k/v fused into W_pack like
+        models/llama.py:98-166, o_proj / down_proj kept 8-bit in 4-bit models) instead of random-initialising."""
+        from . import checkpoint as ck
+        qc = ck.load_quant_config(save_dir)
+        self = cls.__new__(cls)
+        self.cfg, self.batch, self.bit, self.device = cfg, batch, int(qc["w_bit"]), device
+        self.rank, self.world, self.group = 0, 1, None
+        self.h_loc, self.kv_loc, self.i_loc = cfg.heads, cfg.kv_heads, cfg.intermediate
+        self.cache = MixLibCache(inputdim=batch, sigma=6, bit=self.bit, device=device)
+        mods, rest, _ = ck.load_quantized(save_dir, cache=self.cache, dev=device, safetensors=safetensors, fuse_layers=True)
+        n_layers = 1 + max(int(k.split(".")[2]) for k in mods)
+        self.n_layers = n_layers
+        self.layers = []
+        for i in range(n_layers):
+            p = f"model.layers.{i}."
+            self.layers.append({
+                "ln1": rest[p + "input_layernorm.weight"].to(device), "ln2": rest[p + "post_attention_layernorm.weight"].to(device),
+                "W_pack": mods[p + "self_attn.W_pack"], "o_proj": mods[p + "self_attn.o_proj"],
+                "gate_proj": mods[p + "mlp.gate_proj"], "up_proj": mods[p + "mlp.up_proj"], "down_proj": mods[p + "mlp.down_proj"]})
+        self.embed = rest["model.embed_tokens.weight"].to(device)
+        self.norm_f = rest["model.norm.weight"].to(device)
+        self.lm_head = rest["lm_head.weight"].to(device)
+        self.discovered = False
+        self.fuse_swiglu = (self.bit == 8 and batch > 128)
+        self.graph = self._static_tokens = self._static_logits = self.kv = None
+        self.lib = _lib.load()
+        self.xchg = None
+        return self
+
     # ------------------------------------------------------------------ accounting (SURVEY.md §8d)
     def linear_shapes(self):
         """(name, N, K, bit, n_outliers) of the five MixLinears of layer 0 as sharded on this rank."""

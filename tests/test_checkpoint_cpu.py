@@ -120,3 +120,27 @@ def test_layout_errors(tmp_path):
         ck.save_quantized(str(tmp_path), {"l": m}, {"w_bit": 4, "version": "QUIK"})
     with pytest.raises(FileNotFoundError):
         ck.load_state_dict(str(tmp_path / "nowhere"))
+
+
+@pytest.mark.parametrize("bit", [8, 4])
+def test_decoder_save_and_from_quantized_round_trip(tmp_path, bit):
+    """The decode harness writes the reference's layout (HF Llama module names, q/k/v separate) and reads it back with
+    q/k/v fused into W_pack: every tensor identical.  (Construction is device-agnostic; the step itself needs the GPU.)"""
+    from mixq_b200.llama import CONFIGS, LlamaDecoder
+    cfg = CONFIGS["tiny"]
+    m = LlamaDecoder(cfg, batch=8, bit=bit, device="cpu", seed=3)
+    files = m.save_quantized(str(tmp_path), safetensors=(bit == 4), shard_size="200KB")
+    assert any(f.endswith("quant_config.json") for f in files)
+    sd = ck.load_state_dict(str(tmp_path), safetensors=(bit == 4))
+    assert "model.layers.0.self_attn.q_proj.q_weight" in sd and "model.layers.1.mlp.down_proj.scale_col" in sd
+    assert sd["model.layers.0.self_attn.k_proj.q_weight"].shape[0] == cfg.kv_heads * cfg.head_dim
+    r = LlamaDecoder.from_quantized(str(tmp_path), cfg, batch=8, device="cpu", safetensors=(bit == 4))
+    assert r.bit == bit and r.n_layers == m.n_layers == cfg.layers
+    assert torch.equal(r.embed, m.embed) and torch.equal(r.lm_head, m.lm_head) and torch.equal(r.norm_f, m.norm_f)
+    for a, b in zip(m.layers, r.layers):
+        assert torch.equal(a["ln1"], b["ln1"]) and torch.equal(a["ln2"], b["ln2"])
+        for k in ("W_pack", "o_proj", "gate_proj", "up_proj", "down_proj"):
+            assert a[k].bit == b[k].bit and a[k].out_features == b[k].out_features, k
+            assert torch.equal(a[k].q_weight, b[k].q_weight) and torch.equal(a[k].scale_col, b[k].scale_col), k
+            if a[k].bit == 4:
+                assert torch.equal(a[k].ind, b[k].ind) and torch.equal(a[k].weight_cache, b[k].weight_cache), k
