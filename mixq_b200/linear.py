@@ -129,6 +129,35 @@ class MixLinear_GEMM(nn.Module):
             new[:, : self._wc_buf.shape[1]] = self._wc_buf
             self._wc_buf = new
 
+    # bit 4: the reference registers `weight_cache` [N, fp_features_num] and `ind` [fp_features_num] as buffers
+    # (linear.py:49-57), so they are state_dict keys that base.py's load_checkpoint_in_model sets by name.  Here they are
+    # views of the capacity buffers; the two hooks below keep the reference's keys, dtypes and shapes in state_dict().
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+        if self.bit == 4:
+            n = self.fp_features_num
+            destination[prefix + "weight_cache"] = self._wc_buf[:, :n].detach().clone()
+            destination[prefix + "ind"] = self._ind_buf[:n].detach().clone()
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        if self.bit == 4:
+            n = self.fp_features_num
+            wc, ind = state_dict.get(prefix + "weight_cache"), state_dict.get(prefix + "ind")
+            for key, val, shape in ((prefix + "weight_cache", wc, (self.out_features, n)), (prefix + "ind", ind, (n,))):
+                if val is None:
+                    if strict:
+                        missing_keys.append(key)
+                elif tuple(val.shape) != shape:
+                    error_msgs.append(f"size mismatch for {key}: checkpoint {tuple(val.shape)}, module {shape}")
+            if wc is not None and ind is not None and tuple(wc.shape) == (self.out_features, n) and tuple(ind.shape) == (n,):
+                self._reserve_wc(n)
+                self._wc_buf[:, :n] = wc.to(self._wc_buf.device, torch.float16)
+                self._ind_buf[:n] = ind.to(self._ind_buf.device, torch.int32)
+                self._n_ind = n
+            # the base class must not report the two keys as unexpected
+            state_dict = {k: v for k, v in state_dict.items() if k not in (prefix + "weight_cache", prefix + "ind")}
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+
     def _apply(self, fn, recurse=True):
         super()._apply(fn, recurse)
         self._ind_buf = fn(self._ind_buf)
@@ -199,6 +228,9 @@ class MixLinear_GEMM(nn.Module):
         q_x = cache.q_x_buffer(M, K)
         col_over = cache.col_over_buffer(K)
         cache.over_flag.zero_()
+        # a row with amax one fp16 ulp above sigma sets its column flags without raising over_flag (fp16(amax/qmax) ==
+        # fp16(sigma/qmax)): flags nobody compacted must not leak into the next module's discovery through the shared cache
+        col_over.zero_()
         lib = _lib.load()
         _lib.check(lib.mixq_find_row_scale_scan(_ptr(inputs), _ptr(cache.x_scale), _ptr(q_x), M, K, self.bit,
                                                 self._sigma_f, _ptr(col_over), _ptr(cache.over_flag),

@@ -254,3 +254,32 @@ def test_llama_accounting_formulas():
     by = sum(n * k + 2 * M * k + 2 * M * n + 2 * n for n, k in shapes) * L
     assert abs(fl / 1e12 - 6.63) < 0.01
     assert abs(by / 1e9 - 8.77) < 0.3
+
+
+@pytest.mark.parametrize("tag,bit,bias", [("w8", 8, False), ("w8_bias", 8, True), ("w4", 4, False)])
+def test_module_state_dict_matches_reference_manifest(tag, bit, bias):
+    """module.state_dict() has exactly the reference class's keys / dtypes / shapes (tests/golden/state_manifest.json,
+    recorded from /root/reference/mixquant/modules/linear.py:27-87) and load_state_dict round-trips — for bit 4 that
+    includes the registered `weight_cache` / `ind` buffers (what models/base.py's load_checkpoint_in_model sets by name)."""
+    import json
+    import os
+    man = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "state_manifest.json")))[tag]
+    K, N = man["in_features"], man["out_features"]
+    q = MixLinear_GEMM(K, N, bias, "cpu", bit, cache=_Cache())
+    sd = q.state_dict()
+    assert sorted(sd) == sorted(man["state"])
+    for k, (dt, shape) in man["state"].items():
+        assert str(sd[k].dtype) == "torch." + dt and list(sd[k].shape) == shape, k
+    g = torch.Generator().manual_seed(3)
+    src = {k: (torch.randint(0, 100, v.shape, generator=g).to(v.dtype)) for k, v in sd.items()}
+    q2 = MixLinear_GEMM(K, N, bias, "cpu", bit, cache=_Cache())
+    res = q2.load_state_dict(src, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    for k, v in q2.state_dict().items():
+        assert torch.equal(v, src[k]), k
+    if bit == 4:
+        assert torch.equal(q2.ind, src["ind"]) and torch.equal(q2.weight_cache, src["weight_cache"])
+        bad = dict(src)
+        del bad["ind"]
+        with pytest.raises(RuntimeError):
+            MixLinear_GEMM(K, N, bias, "cpu", bit, cache=_Cache()).load_state_dict(bad, strict=True)

@@ -1,6 +1,6 @@
 """Kernel-level MixLinear benchmark (the reference's examples/benchbitsand.py:515-566 convention: TFLOPS = 2*M*N*K / t).
 
-    python tools/bench_linear.py [--M 512] [--shapes 7b|8b|70b|NxK,...] [--modes norm,plain,skip] [--tile 0] [--bit 8]
+    python tools/bench_linear.py [--M 512] [--shapes 7b|8b|70b|NxK,...] [--modes norm,plain,skip,pairnorm,pairskip] [--tile 0] [--bit 8]
                                  [--copies 12] [--nout 41] [--reps 5] [--eager]
 
 Each (shape, mode) is timed as ONE CUDA graph holding `copies` launches on distinct weight copies (so the weights come
@@ -58,6 +58,13 @@ def main():
             ws = (torch.rand(N, generator=g, device=dev) * 1e-3 + 1e-4).half()
             wc = (torch.randn(N, cap, generator=g, device=dev) * 0.02).half()
             copies.append((qw, ws, wc))
+        pair_modes = [m for m in args.modes.split(",") if m.startswith("pair")]
+        ups = []
+        if pair_modes:   # SwiGLU pair: a second (up_proj) weight set per copy
+            for _ in range(args.copies):
+                ups.append((torch.randint(-127, 128, (N, K), generator=g, device=dev, dtype=torch.int8),
+                            (torch.rand(N, generator=g, device=dev) * 1e-3 + 1e-4).half(),
+                            (torch.randn(N, cap, generator=g, device=dev) * 0.02).half()))
         q_x = torch.zeros(M, K, dtype=torch.int8, device=dev)
         xs = torch.zeros(M, dtype=torch.float16, device=dev)
         ao = torch.zeros(M, cap, dtype=torch.float16, device=dev)
@@ -66,17 +73,21 @@ def main():
         x = x0.clone()
         for mode in args.modes.split(","):
             arglist = []
-            for qw, ws, wc in copies:
+            pair = mode.startswith("pair")     # pairnorm / pairplain / pairskip
+            sub = mode[4:] if pair else mode
+            for ci, (qw, ws, wc) in enumerate(copies):
                 a = _lib.LinearArgs()
+                if pair:
+                    a.q_weight_up, a.scale_col_up, a.weight_cache_up = ups[ci][0].data_ptr(), ups[ci][1].data_ptr(), ups[ci][2].data_ptr()
                 a.x = x.data_ptr(); a.M, a.N, a.K = M, N, K
-                a.norm_weight = nw.data_ptr() if mode == "norm" else 0
+                a.norm_weight = nw.data_ptr() if sub == "norm" else 0
                 a.norm_out = 0; a.eps = 1e-5
                 a.q_weight = qw.data_ptr(); a.scale_col = ws.data_ptr(); a.bit = args.bit
                 a.ind = cols.data_ptr(); a.n_ind = n
                 a.weight_cache = wc.data_ptr(); a.ld_wc = cap
                 a.q_x = q_x.data_ptr(); a.x_scale = xs.data_ptr(); a.act_outliers = ao.data_ptr(); a.ld_ao = cap
                 a.sigma = 6.0; a.y = y.data_ptr(); a.grid_sync = sync.data_ptr(); a.tile_n = args.tile
-                a.skip_prologue = 1 if mode == "skip" else 0
+                a.skip_prologue = 1 if sub == "skip" else 0
                 arglist.append(a)
 
             def run_all():
@@ -105,8 +116,9 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) * 1e3 / (args.reps * len(arglist))
-            fl = 2.0 * M * N * K
-            by = N * K * args.bit / 8 + 2 * M * K + 2 * M * N + 2 * N + 2 * n * N
+            nl = 2 if pair else 1
+            fl = 2.0 * M * N * K * nl
+            by = nl * (N * K * args.bit / 8 + 2 * N + 2 * n * N) + 2 * M * K + 2 * M * N
             print(json.dumps({"M": M, "N": N, "K": K, "bit": args.bit, "mode": mode, "n_out": n, "tile": args.tile,
                               "us": round(us, 2), "tflops": round(fl / us / 1e6, 1), "gbs": round(by / us / 1e3, 1)}), flush=True)
             del gr
