@@ -41,12 +41,24 @@ def parse():
 
 
 def peaks():
+    """Roofline denominators.  HBM / bf16: MEASURED_PEAKS.json (driver-written) else the profiling guide's fallback.  INT8 tensor
+    pipe: profiles/r02_int8_peak.json, measured on this pool's B200 by tools/int8_peak.py (torch._int_mm 8192^3 and this
+    library's own prologue-less kernel; burst = best single launch, sustained = 4 s back to back under the power cap)."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return dict(hbm_gbs=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
-                    source="measured")
-    return dict(hbm_gbs=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
+        pk = dict(hbm_gbs=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                  source="measured")
+    else:
+        pk = dict(hbm_gbs=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
+    q = os.path.join(ROOT, "profiles", "r02_int8_peak.json")
+    if os.path.exists(q):
+        d = json.load(open(q))
+        pk.update(int8_burst=d["int8_tops_burst"], int8_sustained=d["int8_tops_sustained"],
+                  int8_source="measured int8 (profiles/r02_int8_peak.json: torch._int_mm 8192^3 / own kernel without prologue)")
+    else:
+        pk.update(int8_burst=2.0 * pk["bf16"], int8_sustained=2.0 * pk["bf16_sustained"], int8_source="2 x bf16 (no int8 measurement found)")
+    return pk
 
 
 # ----------------------------------------------------------------------------------------------- CPU arms
@@ -206,6 +218,89 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
+# ----------------------------------------------------------------------------------------------- TP parity
+def tp_parity_check(args, cfg, model, tok0, logits_tp, rank, world):
+    """Before anything is timed at N > 1: the same seeded model at world_size 1 on rank 0 (steady state, same tokens).
+    TP logits must be within 1e-2 relative (north star) of the single-GPU logits and the column-parallel Linears (replicated
+    input) must have found exactly the single-GPU outlier index sets.  Models too large to rebuild whole beside the shard
+    (> 40 layers) are compared on their first 4 layers (same seeds => the same first layers)."""
+    import torch
+    import torch.distributed as dist
+    from mixq_b200.llama import LlamaDecoder
+    B = args.batch
+    n_par = model.n_layers if model.n_layers <= 40 else 4
+    tp_model, lt = model, logits_tp
+    if n_par != model.n_layers:     # every rank takes part: the truncated TP model has exchanges
+        tp_model = LlamaDecoder(cfg, batch=B, bit=args.bit, seed=0, outlier_frac=0.01, rank=rank, world_size=world, layers=n_par)
+        assert tp_model.discover(tok0)
+        tp_model._rank_barrier()
+        lt = tp_model.step(tok0)
+    torch.cuda.synchronize()
+    out = None
+    if rank == 0:
+        ref = LlamaDecoder(cfg, batch=B, bit=args.bit, seed=0, outlier_frac=0.01, rank=0, world_size=1, layers=n_par)
+        assert ref.discover(tok0)
+        lr = ref.step(tok0).float()
+        rel = float((lt.float() - lr).norm() / lr.norm())
+        col = ("W_pack", "up_proj", "gate_proj")
+        col_same = all(torch.equal(a[k].ind, b[k].ind) for a, b in zip(tp_model.layers, ref.layers) for k in col)
+        # row-parallel: this rank's shard of the single-GPU index set (informative: the shard sees its own x_scale)
+        hits = tot = 0
+        for a, b in zip(tp_model.layers, ref.layers):
+            for k in ("o_proj", "down_proj"):
+                ks = a[k].in_features
+                mine = set((b[k].ind[(b[k].ind >= rank * ks) & (b[k].ind < (rank + 1) * ks)] - rank * ks).tolist())
+                got = set(a[k].ind.tolist())
+                hits += len(mine & got)
+                tot += len(mine | got)
+        out = {"rel": rel, "tol": 1e-2, "ok": bool(rel <= 1e-2 and col_same), "column_parallel_outlier_sets_identical": bool(col_same),
+               "row_parallel_outlier_set_overlap": (hits / tot if tot else 1.0), "layers_compared": n_par,
+               "argmax_agreement": float((lt.argmax(-1) == lr.argmax(-1)).float().mean())}
+        del ref, lr
+        torch.cuda.empty_cache()
+    if tp_model is not model:
+        tp_model.close()
+        del tp_model
+    torch.cuda.synchronize()
+    dist.barrier()
+    return out
+
+
+def time_exchanges(model, n):
+    """Per-exchange device time of the peer-memory all-reduce + residual kernel alone: one CUDA graph of n exchanges on the
+    real buffers (every rank replays it at the same time)."""
+    import torch
+    h = torch.zeros((model.batch, model.cfg.hidden), dtype=torch.float16, device="cuda")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    model._rank_barrier()
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            model.xchg.next_partial()
+            model.xchg.reduce(h)
+    torch.cuda.current_stream().wait_stream(side)
+    model._rank_barrier()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n):
+            model.xchg.next_partial()
+            model.xchg.reduce(h)
+    model._rank_barrier()
+    g.replay()
+    model._rank_barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / (reps * n)
+    del g
+    model._rank_barrier()
+    return us
+
+
 # ----------------------------------------------------------------------------------------------- GPU arm
 def run_mixq(args):
     import torch
@@ -237,8 +332,10 @@ def run_mixq(args):
     ok = model.discover(tok0)
     assert ok, "outlier discovery did not converge after cache.stop calls"
     n0 = _lib.launch_count()
-    model.step(tok0)
+    model._rank_barrier()
+    logits_steady = model.step(tok0)
     launches_per_step = _lib.launch_count() - n0
+    tp_parity = tp_parity_check(args, cfg, model, tok0, logits_steady, rank, world) if world > 1 else None
     model.capture(tok0)
     dev_tokens = [t.cuda() for t in host_tokens]
     torch.cuda.synchronize()
@@ -254,13 +351,15 @@ def run_mixq(args):
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record()
     for i in range(args.steps):
         model.replay(dev_tokens[i % n_tok_sets])
-    e1.record()
+        evs[i + 1].record()
     barrier()
-    ms = e0.elapsed_time(e1)
+    ms = evs[0].elapsed_time(evs[-1])
+    per_step = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps))
+    ms_median = per_step[len(per_step) // 2]
     # ---- e2e: host tokens -> H2D -> step -> argmax -> D2H, every step, through the public call
     for i in range(2):
         model.replay(dev_tokens[0])
@@ -277,9 +376,9 @@ def run_mixq(args):
     sampler.stop_flag = True
     sampler.join(timeout=2)
     if world > 1:
-        t = torch.tensor([ms, ms_e2e], device="cuda")
+        t = torch.tensor([ms, ms_e2e, ms_median], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+        ms, ms_e2e, ms_median = float(t[0]), float(t[1]), float(t[2])
 
     # ---- roofline of the dominant kernel (mixq_linear2_kernel: every MixLinear launch of the step): per-launch CUDA-event
     # time of each of the step's Linear launches, taken over all layers' distinct weights
@@ -341,7 +440,11 @@ def run_mixq(args):
         tot_t += t_launch
         tot_fl += fl
         tot_by += by
-    int8_peak = 2.0 * pk["bf16_sustained"]
+    # burst figure for a region that ran at full clocks without the power cap, else the sustained one
+    clk = sampler.result()
+    at_full_clock = (clk["sm_mhz"] is not None and clk["sm_max_mhz"] and clk["sm_mhz"] >= 0.97 * clk["sm_max_mhz"]
+                     and "sw_power_cap" not in clk["reasons"])
+    int8_peak = pk["int8_burst"] if at_full_clock else pk["int8_sustained"]
     ach_tf, ach_gb = tot_fl / tot_t / 1e12, tot_by / tot_t / 1e9
     tensor_bound = (tot_fl / (int8_peak * 1e12)) >= (tot_by / (pk["hbm_gbs"] * 1e9))
     # DRAM bytes per launch from the committed `ncu --set full` capture of the same four launches (profiles/)
@@ -359,11 +462,19 @@ def run_mixq(args):
         "traffic": traffic, "traffic_source": traffic_src,
         "algorithmic_bytes_per_launch_avg": tot_by / len(kinds), "algorithmic_flops_per_launch_avg": tot_fl / len(kinds),
         "avg_launch_us": tot_t / len(kinds) * 1e6,
-        "peak_source": f"{pk['source']}: int8 tensor pipe taken as 2 x bf16_tflops_sustained ({pk['bf16_sustained']}); hbm_gbs {pk['hbm_gbs']}",
+        "peak_source": f"{pk['int8_source']}, {'burst' if at_full_clock else 'sustained'} figure (timed region at "
+                       f"{clk['sm_mhz']} MHz, reasons {clk['reasons']}); hbm_gbs {pk['hbm_gbs']} ({pk['source']})",
+        "int8_peaks": {"burst": pk["int8_burst"], "sustained": pk["int8_sustained"]},
         "other_bound": {"tflops": ach_tf, "frac_int8": ach_tf / int8_peak, "gbs": ach_gb, "frac_hbm": ach_gb / pk["hbm_gbs"]},
         "per_linear": per_kind, "linear_share_of_step": tot_t * len(model.layers) / (ms * 1e-3 / args.steps),
     }
 
+    exchange_us = None
+    if world > 1 and model.xchg is not None:
+        exchange_us = time_exchanges(model, 2 * len(model.layers))
+        t = torch.tensor([exchange_us], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        exchange_us = float(t[0])
     model_xchg = model.xchg is not None
     model_xchg_two_shot = bool(model.xchg.two_shot) if model_xchg else False
     if rank == 0:
@@ -371,7 +482,8 @@ def run_mixq(args):
         fl_step, by_step = model.algorithmic_work()
         line = {
             "metric": "llama_decode_tokens_per_s", "value": B / step_s, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": step_s * 1e3, "ms_per_step_median": ms_median,
+            "value_median": B / (ms_median * 1e-3), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "int8" if args.bit == 8 else "int4->int8", "data": "synthetic",
             "config": {"workload": f"{args.model} W{args.bit}A{args.bit}O16 decode step, batch {B}, q_len 1, empty KV cache "
                                    "(benchflops.py:96-128), ~1% forced outlier channels",
@@ -384,6 +496,10 @@ def run_mixq(args):
             "e2e": {"value": B / (ms_e2e * 1e-3 / args.steps), "unit": "tokens/s", "h2d_bytes_per_step": B * 8,
                     "d2h_bytes_per_step": B * 8, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,
+            "tp_parity": tp_parity,
+            "step_breakdown_us": {"linear_us": tot_t * len(model.layers) * 1e6,
+                                  "exchange_us": None if exchange_us is None else exchange_us * 2 * len(model.layers),
+                                  "per_exchange_us": exchange_us, "step_us": step_s * 1e6},
             "clocks": sampler.result(),
             "roofline": roofline,
             "step_work": {"linear_tflop": fl_step / 1e12, "linear_gb": by_step / 1e9,

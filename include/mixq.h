@@ -188,6 +188,16 @@ int mixq_linear_fused(const mixq_linear_args* args /* host */, void* stream);
 int mixq_rope_attention_decode(const void* qkv, void* k_cache, void* v_cache, int cache_cap, int past_len, void* out,
                                int M, int H, int Hkv, int D, float theta, void* stream);
 
+/* The same attention with the activation prologue of the Linear that consumes it (o_proj, called in unfused mode at
+ * fused/attn.py:263 => linear.py:187-193 ExtractOutliersAndSetToZeros + FindRowScale) folded in: one CTA owns one token row,
+ * so the row abs-max is known as soon as the row's heads are done.  Writes q_x int8 [M, H*D], x_scale fp16 [M] and
+ * act_outliers fp16 [M, ld_ao] (columns ind[0..n_ind)); `out` (fp16 [M, H*D], outlier columns zeroed like the reference
+ * leaves its tensor) is optional — NULL keeps no fp16 copy.  The consumer then runs mixq_linear_fused(skip_prologue = 1):
+ * the reference's "fused" call mode (fused/norm.py:24-33 is the other producer of this kind). */
+int mixq_rope_attention_decode_quant(const void* qkv, void* k_cache, void* v_cache, int cache_cap, int past_len, void* out,
+                                     int M, int H, int Hkv, int D, float theta, const int32_t* ind, int n_ind,
+                                     void* act_outliers, int ld_ao, void* q_x, void* x_scale, int bit, void* stream);
+
 /* elementwise gate *= up (mlp.py:64) kept for the decode harness */
 int mixq_mul_inplace(void* a, const void* b, long long n, void* stream);
 
@@ -221,6 +231,11 @@ int mixq_ipc_get_handle(const void* ptr, void* handle64);
 int mixq_ipc_open_handle(const void* handle64, void** ptr);
 int mixq_ipc_close_handle(void* ptr);
 int mixq_allreduce_residual(const mixq_allreduce_args* a, void* stream);
+/* How long (milliseconds, default 120 000; environment MIXQ_PEER_TIMEOUT_MS) an exchange waits for a silent peer before the
+ * kernel reports the stall (device printf + trap => a sticky CUDA error on the host).  Ranks drift apart by seconds around
+ * host-synchronising phases (outlier discovery, graph capture, rank-0-only work): callers should still put a process-group
+ * barrier between such a phase and the next exchange. */
+int mixq_set_peer_timeout_ms(long long ms);
 
 #ifdef __cplusplus
 }

@@ -101,6 +101,7 @@ SIGNATURES = {
     "mixq_compact_outlier_columns": [_vp, _i, _vp, _i, _vp, _vp],
     "mixq_linear_fused": [C.POINTER(LinearArgs), _vp],
     "mixq_rope_attention_decode": [_vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _f, _vp],
+    "mixq_rope_attention_decode_quant": [_vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _f, _vp, _i, _vp, _i, _vp, _vp, _i, _vp],
     "mixq_mul_inplace": [_vp, _vp, _ll, _vp],
     "mixq_peer_alloc": [C.c_ulonglong, C.POINTER(C.c_void_p)],
     "mixq_peer_free": [_vp],
@@ -108,6 +109,7 @@ SIGNATURES = {
     "mixq_ipc_open_handle": [C.c_char_p, C.POINTER(C.c_void_p)],
     "mixq_ipc_close_handle": [_vp],
     "mixq_allreduce_residual": [C.POINTER(AllReduceArgs), _vp],
+    "mixq_set_peer_timeout_ms": [_ll],
     "mixq_set_tile_n": [_i],
     "mixq_set_pdl": [_i],
     "mixq_plan_linear": [_i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(LinearPlan)],

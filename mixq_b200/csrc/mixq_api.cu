@@ -22,6 +22,14 @@ std::atomic<unsigned long long*> g_trace{nullptr};
 // Programmatic dependent launch (ptx.cuh: pdl_wait / pdl_launch_dependents): on unless MIXQ_PDL=0 or mixq_set_pdl(0).
 std::atomic<int> g_pdl{[] { const char* e = getenv("MIXQ_PDL"); return (e && e[0] == '0') ? 0 : 1; }()};
 bool pdl_on() { return g_pdl.load(std::memory_order_relaxed) != 0; }
+// How long the tensor-parallel exchange waits for a silent peer before it reports a stall (printf + trap).  Ranks legitimately
+// drift apart by seconds around host-synchronising phases (outlier discovery, graph capture, rank-0-only work), so the default
+// is generous; MIXQ_PEER_TIMEOUT_MS / mixq_set_peer_timeout_ms change it.
+std::atomic<unsigned long long> g_peer_timeout_ms{[] {
+  const char* e = getenv("MIXQ_PEER_TIMEOUT_MS");
+  const long long v = e ? atoll(e) : 0;
+  return static_cast<unsigned long long>(v > 0 ? v : 120000);
+}()};
 
 // Launch attributes shared by every kernel of the library.  A kernel with a grid barrier needs all of its CTAs
 // co-resident: a cooperative launch guarantees it; under PDL the grid is exactly one CTA per SM and the CTAs of the
@@ -593,6 +601,12 @@ int mixq_set_pdl(int on) {
   return 0;
 }
 
+int mixq_set_peer_timeout_ms(long long ms) {
+  if (ms <= 0) return fail(MIXQ_EINVAL, "peer timeout must be positive");
+  g_peer_timeout_ms.store(static_cast<unsigned long long>(ms), std::memory_order_relaxed);
+  return 0;
+}
+
 int mixq_set_trace_buffer(void* buf) {
   g_trace.store(static_cast<unsigned long long*>(buf), std::memory_order_relaxed);
   return 0;
@@ -771,6 +785,35 @@ int mixq_rope_attention_decode(const void* qkv, void* k_cache, void* v_cache, in
   return 0;
 }
 
+int mixq_rope_attention_decode_quant(const void* qkv, void* k_cache, void* v_cache, int cache_cap, int past_len, void* out,
+                                     int M, int H, int Hkv, int D, float theta, const int32_t* ind, int n_ind,
+                                     void* act_outliers, int ld_ao, void* q_x, void* x_scale, int bit, void* stream) {
+  if (!qkv || !q_x || !x_scale || M < 1 || H < 1 || Hkv < 1 || H % Hkv != 0 || (D != 64 && D != 128) || past_len < 0)
+    return fail(MIXQ_EINVAL, "bad attention arguments (head_dim must be 64 or 128)");
+  if (past_len > 0 && (!k_cache || !v_cache || cache_cap <= past_len))
+    return fail(MIXQ_EINVAL, "past_len > 0 needs k/v caches with capacity > past_len");
+  if (static_cast<long long>(H) * D * 2 > 96 * 1024) return fail(MIXQ_EINVAL, "attention row does not fit the shared-memory row buffer");
+  RowQuantArgs rq{};
+  if (int r = fill_rowquant(&rq, out, nullptr, nullptr, 0.f, ind, n_ind, act_outliers, ld_ao, q_x, x_scale, M, H * D, bit,
+                            0.f, nullptr, nullptr))
+    return r;
+  rq.group_warps = 4;   // the whole CTA (kAttnQuantWarps warps) owns the row
+  rq.ngroups = 1;
+  static thread_local int last_dev = -1;
+  int dev = 0;
+  MIXQ_CUDA(cudaGetDevice(&dev));
+  if (dev != last_dev) {
+    MIXQ_CUDA(cudaFuncSetAttribute(rope_attn_decode_quant_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    MIXQ_CUDA(cudaFuncSetAttribute(rope_attn_decode_quant_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    last_dev = dev;
+  }
+  MIXQ_CUDA(launch_rope_attn_decode(static_cast<const __half*>(qkv), static_cast<__half*>(k_cache), static_cast<__half*>(v_cache),
+                                    cache_cap, past_len, static_cast<__half*>(out), M, H, Hkv, D, theta, pdl_on(),
+                                    static_cast<cudaStream_t>(stream), &rq));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
 int mixq_peer_alloc(unsigned long long bytes, void** ptr) {
   if (!ptr || bytes == 0) return fail(MIXQ_EINVAL, "bad peer_alloc arguments");
   MIXQ_CUDA(cudaMalloc(ptr, bytes));            // its own allocation: the IPC handle maps exactly this buffer
@@ -825,6 +868,7 @@ int mixq_allreduce_residual(const mixq_allreduce_args* a, void* stream) {
   k.world = a->world;
   k.rank = a->rank;
   k.buf = a->buf & 1;
+  k.timeout_ns = g_peer_timeout_ms.load(std::memory_order_relaxed) * 1000000ull;
   DeviceInfo di;
   if (int r = device_info(&di)) return r;
   const int grid = grid_for(a->n / 8, 256, di.sms, 4);

@@ -122,29 +122,15 @@ __global__ void __launch_bounds__(1024) compact_cols_kernel(uint8_t* col_over, i
   if (threadIdx.x == 0) *n_new = base;
 }
 
-// RoPE + single-query attention for the decode harness (fused/attn.py:219-263): one warp per (token, head).
+// RoPE + single-query attention for the decode harness (fused/attn.py:219-263).
 // qkv row = [H*D | Hkv*D | Hkv*D]; the new key/value are appended at position past_len of the optional cache
 // [M, Hkv, cap, D]; out[M, H*D] = softmax(q.K^T * scale) . V.  HF rotate_half convention (pairs i, i + D/2).
-// Lane l owns the D/32 consecutive dims [l*E, l*E + E) (8-byte vector accesses); its rotation partner dims live in
-// lane l ^ 16.  Outside the quantised hot path (the reference calls flash-attn here); kept simple.
+// One warp per (token, head): lane l owns the D/32 consecutive dims [l*E, l*E + E) (8-byte vector accesses); its rotation
+// partner dims live in lane l ^ 16.  Outside the quantised hot path (the reference calls flash-attn here); kept simple.
 template <int D>
-__global__ void __launch_bounds__(256) rope_attn_decode_kernel(const __half* __restrict__ qkv, __half* k_cache,
-                                                               __half* v_cache, int cache_cap, int past_len,
-                                                               __half* __restrict__ out, int M, int H, int Hkv,
-                                                               float theta, float scale) {
-  constexpr int E = D / 32;   // 2 (D = 64) or 4 (D = 128) halves per lane
-  pdl_launch_dependents();
-  pdl_wait();
-  const int lane = threadIdx.x & 31;
-  const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  if (w >= static_cast<long long>(M) * H) return;
-  const int m = static_cast<int>(w / H), h = static_cast<int>(w % H);
-  const int hk = h / (H / Hkv);
-  const int ld = (H + 2 * Hkv) * D;
-  const __half* qp = qkv + static_cast<size_t>(m) * ld + h * D + lane * E;
-  const __half* kp = qkv + static_cast<size_t>(m) * ld + (H + hk) * D + lane * E;
-  const __half* vp = qkv + static_cast<size_t>(m) * ld + (H + Hkv + hk) * D + lane * E;
-  auto ldv = [](const __half* p_, float (&f)[E]) {
+struct AttnVec {
+  static constexpr int E = D / 32;   // 2 (D = 64) or 4 (D = 128) halves per lane
+  static __device__ __forceinline__ void ld(const __half* p_, float (&f)[E]) {
     if (E == 4) {
       const uint2 u = *reinterpret_cast<const uint2*>(p_);
       const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
@@ -153,8 +139,21 @@ __global__ void __launch_bounds__(256) rope_attn_decode_kernel(const __half* __r
       const float2 a = __half22float2(*reinterpret_cast<const __half2*>(p_));
       f[0] = a.x; f[1] = a.y;
     }
-  };
-  auto stv = [](__half* p_, const float (&f)[E]) {
+  }
+  // raw (packed fp16) form of the same vector: 2 registers (D = 128) or 1 (D = 64)
+  static __device__ __forceinline__ uint2 ldraw(const __half* p_) {
+    if (E == 4) return *reinterpret_cast<const uint2*>(p_);
+    return make_uint2(*reinterpret_cast<const uint32_t*>(p_), 0u);
+  }
+  static __device__ __forceinline__ void unpack(const uint2 u, float (&f)[E]) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    f[0] = a.x; f[1] = a.y;
+    if (E == 4) {
+      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+      f[E - 2] = b.x; f[E - 1] = b.y;
+    }
+  }
+  static __device__ __forceinline__ void st(__half* p_, const float (&f)[E]) {
     if (E == 4) {
       const __half2 a = __floats2half2_rn(f[0], f[1]), b = __floats2half2_rn(f[E - 2], f[E - 1]);
       *reinterpret_cast<uint2*>(p_) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
@@ -162,11 +161,19 @@ __global__ void __launch_bounds__(256) rope_attn_decode_kernel(const __half* __r
       const __half2 a = __floats2half2_rn(f[0], f[1]);
       *reinterpret_cast<uint32_t*>(p_) = *reinterpret_cast<const uint32_t*>(&a);
     }
-  };
-  float q[E], k[E], v[E], qr[E], kr[E];
-  ldv(qp, q);
-  ldv(kp, k);
-  ldv(vp, v);
+  }
+};
+
+// One (token m, head h) by one warp, q / k / v already in registers: RoPE on q and k, cache append, online-softmax
+// attention over past_len + 1 keys.
+template <int D>
+__device__ __forceinline__ void attn_head_compute(const float (&q)[D / 32], const float (&k)[D / 32], const float (&v)[D / 32],
+                                                  __half* k_cache, __half* v_cache, int cache_cap, int past_len, int m, int h,
+                                                  int H, int Hkv, float theta, float scale, int lane, float (&acc)[D / 32]) {
+  constexpr int E = D / 32;
+  using V = AttnVec<D>;
+  const int hk = h / (H / Hkv);
+  float qr[E], kr[E];
   const float sgn = (lane < 16) ? -1.f : 1.f;      // dims < D/2 take -x[d + D/2], the others +x[d - D/2]
 #pragma unroll
   for (int e = 0; e < E; ++e) {
@@ -182,10 +189,10 @@ __global__ void __launch_bounds__(256) rope_attn_decode_kernel(const __half* __r
     kr[e] = __half2float(__float2half_rn(k[e] * cs + sgn * ko * sn));
   }
   if (k_cache != nullptr && h % (H / Hkv) == 0) {
-    stv(k_cache + ((static_cast<size_t>(m) * Hkv + hk) * cache_cap + past_len) * D + lane * E, kr);
-    stv(v_cache + ((static_cast<size_t>(m) * Hkv + hk) * cache_cap + past_len) * D + lane * E, v);
+    V::st(k_cache + ((static_cast<size_t>(m) * Hkv + hk) * cache_cap + past_len) * D + lane * E, kr);
+    V::st(v_cache + ((static_cast<size_t>(m) * Hkv + hk) * cache_cap + past_len) * D + lane * E, v);
   }
-  float mx = -INFINITY, den = 0.f, acc[E];
+  float mx = -INFINITY, den = 0.f;
 #pragma unroll
   for (int e = 0; e < E; ++e) acc[e] = 0.f;
   for (int t = 0; t <= past_len; ++t) {
@@ -194,8 +201,8 @@ __global__ void __launch_bounds__(256) rope_attn_decode_kernel(const __half* __r
 #pragma unroll
       for (int e = 0; e < E; ++e) { kt[e] = kr[e]; vt[e] = v[e]; }
     } else {
-      ldv(k_cache + ((static_cast<size_t>(m) * Hkv + hk) * cache_cap + t) * D + lane * E, kt);
-      ldv(v_cache + ((static_cast<size_t>(m) * Hkv + hk) * cache_cap + t) * D + lane * E, vt);
+      V::ld(k_cache + ((static_cast<size_t>(m) * Hkv + hk) * cache_cap + t) * D + lane * E, kt);
+      V::ld(v_cache + ((static_cast<size_t>(m) * Hkv + hk) * cache_cap + t) * D + lane * E, vt);
     }
     float s = 0.f;
 #pragma unroll
@@ -212,23 +219,120 @@ __global__ void __launch_bounds__(256) rope_attn_decode_kernel(const __half* __r
   }
 #pragma unroll
   for (int e = 0; e < E; ++e) acc[e] = acc[e] / den;
-  stv(out + (static_cast<size_t>(m) * H + h) * D + lane * E, acc);
+}
+// this head's slices of the qkv row of token m -> registers
+template <int D>
+__device__ __forceinline__ void attn_head_load(const __half* __restrict__ qkv, int m, int h, int H, int Hkv, int lane,
+                                               float (&q)[D / 32], float (&k)[D / 32], float (&v)[D / 32]) {
+  constexpr int E = D / 32;
+  const int hk = h / (H / Hkv);
+  const int ld = (H + 2 * Hkv) * D;
+  const __half* row = qkv + static_cast<size_t>(m) * ld + lane * E;
+  AttnVec<D>::ld(row + h * D, q);
+  AttnVec<D>::ld(row + (H + hk) * D, k);
+  AttnVec<D>::ld(row + (H + Hkv + hk) * D, v);
+}
+template <int D>
+__device__ __forceinline__ void attn_head(const __half* __restrict__ qkv, __half* k_cache, __half* v_cache, int cache_cap,
+                                          int past_len, int m, int h, int H, int Hkv, float theta, float scale, int lane,
+                                          float (&acc)[D / 32]) {
+  float q[D / 32], k[D / 32], v[D / 32];
+  attn_head_load<D>(qkv, m, h, H, Hkv, lane, q, k, v);
+  attn_head_compute<D>(q, k, v, k_cache, v_cache, cache_cap, past_len, m, h, H, Hkv, theta, scale, lane, acc);
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) rope_attn_decode_kernel(const __half* __restrict__ qkv, __half* k_cache,
+                                                               __half* v_cache, int cache_cap, int past_len,
+                                                               __half* __restrict__ out, int M, int H, int Hkv,
+                                                               float theta, float scale) {
+  constexpr int E = D / 32;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (w >= static_cast<long long>(M) * H) return;
+  const int m = static_cast<int>(w / H), h = static_cast<int>(w % H);
+  float acc[E];
+  attn_head<D>(qkv, k_cache, v_cache, cache_cap, past_len, m, h, H, Hkv, theta, scale, lane, acc);
+  AttnVec<D>::st(out + (static_cast<size_t>(m) * H + h) * D + lane * E, acc);
+}
+
+// The same attention with the NEXT MixLinear's activation prologue folded in (o_proj: fused/attn.py:263 calls it in unfused
+// mode, i.e. ExtractOutliersAndSetToZeros + FindRowScale on the attention output, linear.py:187-193): one CTA owns one token
+// row, its 8 warps walk the row's heads, the fp16 row stays in shared memory, and process_row (rowquant.cuh) gathers / zeroes
+// the outlier columns, takes the row abs-max and quantises — o_proj then runs with skip_prologue, exactly like the reference's
+// "fused" call mode where a producer (norm.py:24-33) leaves q_xcache / x_scale / activation_outliers in the cache.
+// rq.x = optional fp16 [M, H*D] copy of the attention output (outlier columns zeroed, as the reference leaves its tensor).
+constexpr int kAttnQuantWarps = 4;   // 128 threads and <= 128 registers: >= 4 CTAs per SM, 512 token rows in ONE wave
+constexpr int kAttnQuantHPW = 8;     // heads a warp keeps in flight at once (q, k, v of all of them are loaded before any math)
+template <int D>
+__global__ void __launch_bounds__(kAttnQuantWarps * 32, 4)
+rope_attn_decode_quant_kernel(const __half* __restrict__ qkv, __half* k_cache, __half* v_cache, int cache_cap, int past_len,
+                              int H, int Hkv, float theta, float scale, const RowQuantArgs rq) {
+  constexpr int E = D / 32;
+  extern __shared__ __align__(128) uint8_t attn_row[];
+  __shared__ RowQuantSmem sm;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __half* row_s = reinterpret_cast<__half*>(attn_row);
+  for (int m = blockIdx.x; m < rq.M; m += gridDim.x) {
+    for (int base = 0; base < H; base += kAttnQuantWarps * kAttnQuantHPW) {
+      uint2 rq_[kAttnQuantHPW], rk_[kAttnQuantHPW], rv_[kAttnQuantHPW];   // packed fp16, all heads of this warp in flight
+      const int ld = (H + 2 * Hkv) * D;
+      const __half* row = qkv + static_cast<size_t>(m) * ld + lane * E;
+#pragma unroll
+      for (int j = 0; j < kAttnQuantHPW; ++j) {
+        const int h = base + warp + kAttnQuantWarps * j;
+        if (h < H) {
+          const int hk = h / (H / Hkv);
+          rq_[j] = AttnVec<D>::ldraw(row + h * D);
+          rk_[j] = AttnVec<D>::ldraw(row + (H + hk) * D);
+          rv_[j] = AttnVec<D>::ldraw(row + (H + Hkv + hk) * D);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kAttnQuantHPW; ++j) {
+        const int h = base + warp + kAttnQuantWarps * j;
+        if (h < H) {
+          float q[E], k[E], v[E], acc[E];
+          AttnVec<D>::unpack(rq_[j], q);
+          AttnVec<D>::unpack(rk_[j], k);
+          AttnVec<D>::unpack(rv_[j], v);
+          attn_head_compute<D>(q, k, v, k_cache, v_cache, cache_cap, past_len, m, h, H, Hkv, theta, scale, lane, acc);
+          AttnVec<D>::st(row_s + h * D + lane * E, acc);
+          if (rq.x != nullptr) AttnVec<D>::st(rq.x + static_cast<size_t>(m) * rq.K + h * D + lane * E, acc);
+        }
+      }
+    }
+    __syncthreads();
+    process_row(rq, m, 0, threadIdx.x, 0, &sm, row_s);
+    __syncthreads();
+  }
 }
 
 cudaError_t launch_rope_attn_decode(const __half* qkv, __half* k_cache, __half* v_cache, int cache_cap, int past_len,
-                                    __half* out, int M, int H, int Hkv, int D, float theta, bool pdl, cudaStream_t st) {
-  const long long warps = static_cast<long long>(M) * H;
-  const int grid = static_cast<int>((warps + 7) / 8);
+                                    __half* out, int M, int H, int Hkv, int D, float theta, bool pdl, cudaStream_t st,
+                                    const RowQuantArgs* rq) {
   const float scale = 1.0f / sqrtf(static_cast<float>(D));
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(rq != nullptr ? kAttnQuantWarps * 32 : 256);
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
+  if (rq != nullptr) {
+    cfg.gridDim = dim3(M);
+    cfg.dynamicSmemBytes = static_cast<size_t>(H) * D * 2;
+    if (D == 128)
+      return cudaLaunchKernelEx(&cfg, rope_attn_decode_quant_kernel<128>, qkv, k_cache, v_cache, cache_cap, past_len, H, Hkv, theta, scale, *rq);
+    return cudaLaunchKernelEx(&cfg, rope_attn_decode_quant_kernel<64>, qkv, k_cache, v_cache, cache_cap, past_len, H, Hkv, theta, scale, *rq);
+  }
+  const long long warps = static_cast<long long>(M) * H;
+  cfg.gridDim = dim3(static_cast<int>((warps + 7) / 8));
   if (D == 128)
     return cudaLaunchKernelEx(&cfg, rope_attn_decode_kernel<128>, qkv, k_cache, v_cache, cache_cap, past_len, out, M, H, Hkv, theta, scale);
   return cudaLaunchKernelEx(&cfg, rope_attn_decode_kernel<64>, qkv, k_cache, v_cache, cache_cap, past_len, out, M, H, Hkv, theta, scale);
@@ -259,7 +363,7 @@ __device__ __forceinline__ void peer_wait(const AllReduceArgs& a, int phase, uin
     uint32_t v, spins = 0;
     do {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a.flags[a.rank] + 2 * p + phase) : "memory");
-      if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > MIXQ_SPIN_TIMEOUT_NS) spin_timeout_trap(11 + phase, p, static_cast<int>(e));
+      if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > a.timeout_ns) spin_timeout_trap(11 + phase, p, static_cast<int>(e));
     } while (static_cast<int32_t>(v - e) < 0);
   }
 }

@@ -14,7 +14,11 @@ __global__ void gather_weight_cols_kernel(const void* q_w, const __half* scale_c
                                           __half* wc, int ld_wc, int col0, int N, int K, int bit);
 __global__ void compact_cols_kernel(uint8_t* col_over, int K, int32_t* ind_out, int max_new, int32_t* n_new);
 cudaError_t launch_rope_attn_decode(const __half* qkv, __half* k_cache, __half* v_cache, int cache_cap, int past_len,
-                                    __half* out, int M, int H, int Hkv, int D, float theta, bool pdl, cudaStream_t st);
+                                    __half* out, int M, int H, int Hkv, int D, float theta, bool pdl, cudaStream_t st,
+                                    const RowQuantArgs* rq = nullptr);   // rq: fold the next MixLinear's activation prologue in
+template <int D>
+__global__ void rope_attn_decode_quant_kernel(const __half* qkv, __half* k_cache, __half* v_cache, int cache_cap, int past_len,
+                                              int H, int Hkv, float theta, float scale, const RowQuantArgs rq);
 __global__ void mul_inplace_kernel(__half2* a, const __half2* b, long long n2);
 
 constexpr int kMaxPeers = 8;
@@ -28,6 +32,7 @@ struct AllReduceArgs {
   __half* out;                           // local [n]
   long long n;                           // elements, multiple of 8
   int world, rank, buf;
+  unsigned long long timeout_ns;         // a peer that stays silent this long is reported (printf + trap); mixq_set_peer_timeout_ms
 };
 __global__ void allreduce_residual_kernel(AllReduceArgs a);
 

@@ -203,7 +203,7 @@ __device__ __forceinline__ void process_row(const RowQuantArgs& a, int m, int gr
       const int c = a.ind[j];
       __half val = row_s[c];
       if (norm) val = __float2half_rn(__fmul_rn(__fmul_rn(__half2float(val), rstd), __half2float(a.norm_w[c])));
-      else xrow[c] = __float2half_rn(0.f);
+      else if (a.x != nullptr) xrow[c] = __float2half_rn(0.f);   // (a producer-fused caller may keep no fp16 copy at all)
       a.act_out[static_cast<size_t>(m) * a.ld_ao + j] = val;
       row_s[c] = __float2half_rn(0.f);
     }

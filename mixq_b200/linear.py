@@ -384,6 +384,29 @@ class MixLinear_GEMM(nn.Module):
         return y.reshape(cache.shape)
 
     @torch.no_grad()
+    def forward_quantized(self, M, cache=None, residual=None, out=None):
+        """The reference's fused call mode (linear.py:194-199: consume cache.q_xcache / x_scale / activation_outliers left by
+        a producer kernel) when the producer keeps no fp16 activation tensor at all — e.g. the attention kernel that
+        quantises its own output rows for o_proj (mixq_rope_attention_decode_quant).  Steady state only."""
+        if cache is None:
+            cache = self.cache
+        if self.add_outliers:
+            raise _lib.MixqError("forward_quantized is a steady-state path: run the discovery calls first")
+        self._require_cuda(cache.q_xcache, self.q_weight)
+        if out is None:
+            y = torch.empty((M, self.out_features), dtype=torch.float16, device=self.q_weight.device)
+        else:
+            if out.dtype != torch.float16 or not out.is_contiguous() or out.numel() != M * self.out_features:
+                raise _lib.MixqError("out must be a contiguous fp16 tensor of M * out_features elements")
+            y = out.view(M, self.out_features)
+        cache.shape = (M, self.out_features)
+        cache.ind = self.ind
+        ao, ld = self._cached_act_outliers(cache, M)
+        self._launch(cache, M, y, skip_prologue=True, residual=None if residual is None else residual.reshape(M, self.out_features),
+                     q_x=cache.q_xcache, act_outliers=ao, ld_ao=ld)
+        return y
+
+    @torch.no_grad()
     def forward_without_preconditionFusedSilu(self, x, cache):
         """linear.py:291-376 — gate_proj: no re-quantisation, consumes what up_proj left in the cache; SiLU epilogue."""
         inputs = x.reshape(-1, x.shape[-1])

@@ -146,6 +146,8 @@ class LlamaDecoder:
         self.discovered = False
         # one launch for up_proj + gate_proj + SiLU + gate*up (needs the 2-CTA kernel: M > 128, bit 8)
         self.fuse_swiglu = (bit == 8 and batch > 128)
+        # attention + o_proj's activation prologue in one launch (MIXQ_FUSE_ATTN_QUANT=1; off by default until it beats the separate launches)
+        self.fuse_attn_quant = os.environ.get("MIXQ_FUSE_ATTN_QUANT", "0") == "1"
         self.graph = None
         self._static_tokens = None
         self._static_logits = None
@@ -155,6 +157,19 @@ class LlamaDecoder:
         self.xchg = None
         if world_size > 1 and os.environ.get("MIXQ_TP_EXCHANGE", "peer") == "peer":
             self.xchg = PeerExchange(batch, H, rank, world_size, group=group, device=device)
+
+    def close(self):
+        """Release the peer-exchange buffers (CUDA-IPC mappings + cudaMalloc'd partial / result buffers) and the graph."""
+        self.graph = None
+        if getattr(self, "xchg", None) is not None:
+            self.xchg.close()
+            self.xchg = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     # ------------------------------------------------------------------ pieces
     def _stream(self):
@@ -174,6 +189,26 @@ class LlamaDecoder:
                                                        M, self.h_loc, self.kv_loc, cfg.head_dim, cfg.rope_theta,
                                                        self._stream()), "rope_attention_decode")
         return out
+
+    def _attention_quant(self, qkv, lin, past_len=0, layer_idx=0):
+        """Attention + the activation prologue of `lin` (o_proj) in ONE launch: the kernel owns whole token rows, so it
+        gathers lin's outlier columns, takes the row abs-max and quantises its own output (linear.py:187-193 on the
+        attention output); lin then runs in the reference's fused call mode (forward_quantized).  Steady state only."""
+        cfg, cache = self.cfg, self.cache
+        M, K = qkv.shape[0], self.h_loc * cfg.head_dim
+        kc = vc = None
+        cap = 0
+        if self.kv is not None:
+            kc, vc = self.kv[layer_idx]
+            cap = kc.shape[2]
+        n = lin._n_ind
+        ao, q_x = cache.ao_buffer(n), cache.q_x_buffer(M, K)
+        _lib.check(self.lib.mixq_rope_attention_decode_quant(
+            qkv.data_ptr(), 0 if kc is None else kc.data_ptr(), 0 if vc is None else vc.data_ptr(), cap, past_len, 0,
+            M, self.h_loc, self.kv_loc, cfg.head_dim, cfg.rope_theta, lin._ind_buf.data_ptr(), n, ao.data_ptr(), ao.shape[1],
+            q_x.data_ptr(), cache.x_scale.data_ptr(), lin.bit, self._stream()), "rope_attention_decode_quant")
+        cache.q_xcache = q_x
+        cache.activation_outliers = ao[:M, :n]
 
     def _allreduce(self, t):
         return all_reduce_sum(t, self.group) if self.world > 1 else t
@@ -197,14 +232,26 @@ class LlamaDecoder:
                 qkv = L["W_pack"].forward_norm_fused(h, L["ln1"], cfg.eps)
             else:
                 qkv = self._norm_then_linear(h, L["ln1"], L["W_pack"])
-            attn = self._attention(qkv, past_len, li)
-            if tp and self.xchg is not None:
-                L["o_proj"](attn, None, True, out=self.xchg.next_partial())
-                h = self.xchg.reduce(h)
-            elif tp:
-                h = h + self._allreduce(L["o_proj"](attn, None, True))
+            if steady and self.fuse_attn_quant:
+                # attention quantises its own output rows for o_proj: o_proj has no activation prologue left
+                self._attention_quant(qkv, L["o_proj"], past_len, li)
+                M = qkv.shape[0]
+                if tp and self.xchg is not None:
+                    L["o_proj"].forward_quantized(M, out=self.xchg.next_partial())
+                    h = self.xchg.reduce(h)
+                elif tp:
+                    h = h + self._allreduce(L["o_proj"].forward_quantized(M))
+                else:
+                    h = L["o_proj"].forward_quantized(M, residual=h)
             else:
-                h = L["o_proj"](attn, None, True, residual=h)
+                attn = self._attention(qkv, past_len, li)
+                if tp and self.xchg is not None:
+                    L["o_proj"](attn, None, True, out=self.xchg.next_partial())
+                    h = self.xchg.reduce(h)
+                elif tp:
+                    h = h + self._allreduce(L["o_proj"](attn, None, True))
+                else:
+                    h = L["o_proj"](attn, None, True, residual=h)
             if steady and self.fuse_swiglu:
                 gate = L["gate_proj"].forward_swiglu_fused(L["up_proj"], h, L["ln2"], cfg.eps)
             else:
@@ -238,14 +285,23 @@ class LlamaDecoder:
     def discover(self, tokens: torch.Tensor, calls: int | None = None):
         """The reference's first `cache.stop` forwards: online outlier discovery with host syncs."""
         for _ in range(self.cache.stop if calls is None else calls):
+            self._rank_barrier()      # discovery calls synchronise with the host: ranks drift apart between them
             self.step(tokens)
         # gate_proj never runs discovery itself: it follows up_proj's outlier set (linear.py:299-315)
         self.discovered = all(not L[k].add_outliers for L in self.layers for k in ("W_pack", "o_proj", "up_proj", "down_proj"))
         return self.discovered
 
+    def _rank_barrier(self):
+        """Process-group barrier before an exchange that follows a rank-asymmetric phase (host syncs, graph capture,
+        rank-0-only work): the peer-exchange kernel spins on its peers' flags and reports a stall after a timeout."""
+        if self.world > 1 and torch.distributed.is_initialized():
+            torch.cuda.synchronize()
+            torch.distributed.barrier(group=self.group)
+
     def capture(self, tokens: torch.Tensor):
         """Capture the steady-state step into a CUDA graph (tokens are copied into a static buffer per replay)."""
         assert self.discovered, "run discover() first"
+        self._rank_barrier()
         self._static_tokens = tokens.clone()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -254,9 +310,11 @@ class LlamaDecoder:
                 self.step(self._static_tokens)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        self._rank_barrier()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self._static_logits = self.step(self._static_tokens)
+        self._rank_barrier()
         return self.graph
 
     def replay(self, tokens: torch.Tensor | None = None) -> torch.Tensor:
@@ -329,6 +387,7 @@ class LlamaDecoder:
         self.lm_head = rest["lm_head.weight"].to(device)
         self.discovered = False
         self.fuse_swiglu = (self.bit == 8 and batch > 128)
+        self.fuse_attn_quant = os.environ.get("MIXQ_FUSE_ATTN_QUANT", "0") == "1"
         self.graph = self._static_tokens = self._static_logits = self.kv = None
         self.lib = _lib.load()
         self.xchg = None

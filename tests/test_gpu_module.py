@@ -233,6 +233,13 @@ def test_llama_swiglu_fused_step_matches_unfused():
     plain = m.step(tok).clone()
     assert _lib.launch_count() - n0 == 7 * cfg.layers + 1
     rel_close(host(fused), host(plain), "logits fused vs unfused", 2e-3)
+    # attention quantising its own output for o_proj (one launch) vs attention, then o_proj with its own prologue: same bits
+    m.fuse_swiglu = True
+    m.fuse_attn_quant = False
+    sep = m.step(tok).clone()
+    m.fuse_attn_quant = True
+    aq = m.step(tok).clone()
+    assert torch.equal(sep, aq), "attention-fused o_proj prologue must not change a bit"
 
 
 def test_attention_decode_with_kv_cache():
@@ -267,3 +274,53 @@ def test_attention_decode_with_kv_cache():
                                               10000.0, C.c_void_p(torch.cuda.current_stream().cuda_stream)), "attn0")
     v = qkv[:, (H + Hkv) * D:].reshape(M, Hkv, 1, D).repeat(H // Hkv, 2).reshape(M, H * D)
     bits_equal(host(out0), v, "attention over a single key == v")
+
+
+@pytest.mark.parametrize("M,H,Hkv,D,L,n,bit", [(5, 8, 2, 128, 7, 9, 8), (33, 32, 32, 128, 0, 41, 8), (4, 4, 1, 64, 3, 0, 8), (6, 8, 8, 128, 0, 5, 4)])
+def test_attention_quant_fused_matches_separate_prologue(M, H, Hkv, D, L, n, bit):
+    """mixq_rope_attention_decode_quant == mixq_rope_attention_decode followed by the oracle's ExtractOutliersAndSetToZeros +
+    FindRowScale (linear.py:187-193) on that attention output: q_x / x_scale / gathered outliers / zeroed fp16 copy bit-exact."""
+    from mixq_b200 import _lib
+    import ctypes as C
+    from oracle import mixq_oracle as O
+    lib = _lib.load()
+    rng = np.random.default_rng(M + H + n)
+    qkv = rng.standard_normal((M, (H + 2 * Hkv) * D)).astype(np.float16)
+    cols = np.sort(rng.permutation(H * D)[:n]).astype(np.int32)
+    vcols = (H + Hkv) * D   # make some value channels "massive" so that the gathered outlier columns are real outliers
+    qkv[:, vcols:] = (qkv[:, vcols:].astype(np.float32) * np.where(rng.random(Hkv * D) < 0.02, 30.0, 1.0)).astype(np.float16)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    cap = 16
+    mk = lambda: (torch.from_numpy(rng.standard_normal((M, Hkv, cap, D)).astype(np.float16)).cuda() if L else None)
+    kc, vc = mk(), mk()
+    kc2, vc2 = (kc.clone(), vc.clone()) if L else (None, None)
+    p = lambda t: 0 if t is None else t.data_ptr()
+    qkv_d = torch.from_numpy(qkv).cuda()
+    out = torch.zeros(M, H * D, dtype=torch.float16, device="cuda")
+    _lib.check(lib.mixq_rope_attention_decode(qkv_d.data_ptr(), p(kc), p(vc), cap if L else 0, L, out.data_ptr(), M, H, Hkv, D,
+                                              10000.0, st), "attn")
+    x = host(out).copy()
+    ao_ref = O.extract_outliers_and_set_to_zeros(cols, x) if n else None
+    q_ref, xs_ref = O.find_row_scale(x, bit)
+    capo = max(64, (n + 63) // 64 * 64)
+    ao = torch.zeros(M, capo, dtype=torch.float16, device="cuda")
+    q_x = torch.zeros(M, H * D, dtype=torch.int8, device="cuda")
+    xs = torch.zeros(M, dtype=torch.float16, device="cuda")
+    ind = torch.from_numpy(cols).cuda()
+    for keep_fp16 in (True, False):
+        out2 = torch.full((M, H * D), 7.0, dtype=torch.float16, device="cuda")
+        q_x.zero_(); xs.zero_(); ao.zero_()
+        _lib.check(lib.mixq_rope_attention_decode_quant(qkv_d.data_ptr(), p(kc2), p(vc2), cap if L else 0, L,
+                                                        out2.data_ptr() if keep_fp16 else 0, M, H, Hkv, D, 10000.0,
+                                                        ind.data_ptr() if n else 0, n, ao.data_ptr(), capo, q_x.data_ptr(),
+                                                        xs.data_ptr(), bit, st), "attn_quant")
+        torch.cuda.synchronize()
+        bits_equal(host(q_x), q_ref, "q_x")
+        bits_equal(host(xs), xs_ref.reshape(-1), "x_scale")
+        if n:
+            bits_equal(host(ao)[:, :n], ao_ref, "activation_outliers")
+        if keep_fp16:
+            bits_equal(host(out2), x, "fp16 copy with the outlier columns zeroed")
+    if L:
+        bits_equal(host(kc2), host(kc), "k cache append")
+        bits_equal(host(vc2), host(vc), "v cache append")
