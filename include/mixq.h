@@ -178,6 +178,12 @@ typedef struct mixq_linear_args {
   int skip_prologue;       /* 1: q_x / x_scale / act_outliers already valid (gate_proj, linear.py:291-376) */
   uint32_t* grid_sync;     /* one zero-initialised u32 in device memory, reused across launches */
   int tile_n;              /* 0 = auto; else a multiple of 32 up to 512 (the 1-CTA kernel, M <= 128 or W4, honours 128 / 256 only) */
+  /* tensor-parallel push: the reduce-scatter half of the row-parallel exchange fused into the GEMM epilogue.  peer_cols =
+   * N / world > 0: output column slice j = n / peer_cols goes to y_peer[j] (fp16 [M, peer_cols]: rank j's receive slot for THIS
+   * rank, a peer-mapped pointer for j != rank) instead of y; no bias / residual / addend / SwiGLU pair; peer_cols % 128 == 0
+   * (% 256 for M <= 128).  mixq_exchange_finish then reduces and broadcasts.  peer_cols = 0: off. */
+  void* y_peer[8];
+  int peer_cols;
 } mixq_linear_args;
 
 int mixq_linear_fused(const mixq_linear_args* args /* host */, void* stream);
@@ -197,6 +203,20 @@ int mixq_rope_attention_decode(const void* qkv, void* k_cache, void* v_cache, in
 int mixq_rope_attention_decode_quant(const void* qkv, void* k_cache, void* v_cache, int cache_cap, int past_len, void* out,
                                      int M, int H, int Hkv, int D, float theta, const int32_t* ind, int n_ind,
                                      void* act_outliers, int ld_ao, void* q_x, void* x_scale, int bit, void* stream);
+
+/* ---- QUIK MixedQLinear (mixquant/modules/qlinear.py:41-211; `quik` is an un-vendored third-party extension: parity
+ * unpinned, see oracle/quik_oracle.py).
+ * quik.asymmetric.quantize(x, int_indices, fp_indices, bits) (qlinear.py:117-120): per token row zero = min, scale =
+ * (max - min) / (2^bits - 1) over the int columns -> meta fp16 [2, M] (row 0 scales, row 1 zeros); q int8 [M, n_int] =
+ * rn((x - zero) / scale) - 2^(bits-1), one value per byte; fp_x fp16 [M, n_fp] = x[:, fp_indices].  Indices are int64
+ * (the reference registers them as torch.long buffers, qlinear.py:66-69). */
+int mixq_quik_quantize(const void* x, const int64_t* int_indices, int n_int, const int64_t* fp_indices, int n_fp, int bits,
+                       void* q, void* meta, void* fp_x, int M, int K, void* stream);
+/* The addend of quik.asymmetric.dequantize (qlinear.py:149-150): out fp16 [M,N] = (zero[m] + 2^(bits-1) scale[m]) * reduced_w[n]
+ * + fp_result[m,n] (fp_result may be NULL); the int GEMM (mixq_int4_fused_dequantize / mixq_int8_fused_dequantize with
+ * x_scale = meta row 0 and outl = this addend) completes y = acc * scale[m] * weights_scales[n] + addend. */
+int mixq_quik_addend(const void* meta, const void* reduced_w, const void* fp_result, int ld_fp, void* out, int M, int N,
+                     int bits, void* stream);
 
 /* elementwise gate *= up (mlp.py:64) kept for the decode harness */
 int mixq_mul_inplace(void* a, const void* b, long long n, void* stream);
@@ -231,6 +251,51 @@ int mixq_ipc_get_handle(const void* ptr, void* handle64);
 int mixq_ipc_open_handle(const void* handle64, void** ptr);
 int mixq_ipc_close_handle(void* ptr);
 int mixq_allreduce_residual(const mixq_allreduce_args* a, void* stream);
+/* The same exchange through an NVLink-SHARP (NVLS) multicast mapping: ONE symmetric allocation per rank (e.g. from
+ * torch.distributed._symmetric_memory: plumbing) holding partial 0 / 1, result 0 / 1 and 8 flag bytes at the same offsets on
+ * every rank, `local` = this rank's copy, `mc` = the multicast address of all copies.  Rank r reduces elements
+ * [r n / world, (r + 1) n / world) with multimem.ld_reduce (the switch adds the copies, fp32 accumulation), adds the residual
+ * slice as a separate fp16 rounding and multimem.st's the slice into every rank's result buffer; both handshakes are one
+ * multimem.red each.  The row-parallel Linear writes its partial into local + partial_off[buf]; the result of the exchange is
+ * local + result_off[buf] (valid until the exchange after the next one).  buf alternates 0, 1 as above; n % (8 * world) == 0. */
+typedef struct mixq_mc_allreduce_args {
+  void* mc;
+  void* local;
+  unsigned long long partial_off[2];
+  unsigned long long result_off[2];
+  unsigned long long flags_off;   /* 8 zero-initialised bytes (two uint32 counters), 16-byte aligned */
+  void* epoch;                    /* local uint32, zero-initialised */
+  void* done;                     /* local uint32, zero-initialised */
+  const void* residual;           /* local fp16 [n] or NULL */
+  long long n;
+  int world, rank, buf;
+} mixq_mc_allreduce_args;
+int mixq_allreduce_multicast(const mixq_mc_allreduce_args* a, void* stream);
+
+/* The FUSED row-parallel exchange: (1) the row-parallel MixLinear's epilogue pushes column slice j of its fp16 partial straight
+ * into rank j's receive slot (mixq_linear_args.y_peer / peer_cols: NVLink stores from the epilogue warps, overlapped with the
+ * GEMM's own tail); (2) mixq_exchange_finish shakes hands, reduces this rank's slice from its LOCAL slots (fp32, rank order, one
+ * rounding to fp16), adds the residual slice as a separate fp16 rounding and broadcasts the slice into every rank's result
+ * buffer (multimem.st through the switch when mc_result is set, else one store per peer), and shakes hands again.  Per rank
+ * 2 (world-1)/world n fp16 cross NVLink instead of (world-1) n, and only the small second half is exposed.
+ *   recv      : local fp16 [world][M, N/world] receive slots of THIS exchange (slot s = rank s's partial of my slice)
+ *   result[r] : rank r's result buffer fp16 [M, N] of this exchange as mapped here (own rank: the local pointer)
+ *   flags[r]  : rank r's two zero-initialised uint32 handshake counters as mapped here; mc_flags / mc_result: multicast
+ *               addresses of the same buffers, or NULL
+ * Callers alternate between two (recv, result) buffer sets exactly as for mixq_allreduce_residual. */
+typedef struct mixq_exchange_finish_args {
+  const void* recv;
+  void* result[8];
+  void* mc_result;
+  void* flags[8];
+  void* mc_flags;
+  void* epoch;             /* local uint32, zero-initialised */
+  void* done;              /* local uint32, zero-initialised */
+  const void* residual;    /* local fp16 [M, N] or NULL */
+  int M, N, world, rank;
+} mixq_exchange_finish_args;
+int mixq_exchange_finish(const mixq_exchange_finish_args* a, void* stream);
+
 /* How long (milliseconds, default 120 000; environment MIXQ_PEER_TIMEOUT_MS) an exchange waits for a silent peer before the
  * kernel reports the stall (device printf + trap => a sticky CUDA error on the host).  Ranks drift apart by seconds around
  * host-synchronising phases (outlier discovery, graph capture, rank-0-only work): callers should still put a process-group

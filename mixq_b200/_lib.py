@@ -53,6 +53,8 @@ class LinearArgs(C.Structure):
         ("skip_prologue", C.c_int),
         ("grid_sync", C.c_void_p),
         ("tile_n", C.c_int),
+        ("y_peer", C.c_void_p * 8),
+        ("peer_cols", C.c_int),
     ]
 
 
@@ -73,6 +75,44 @@ class AllReduceArgs(C.Structure):
         ("world", C.c_int),
         ("rank", C.c_int),
         ("buf", C.c_int),
+    ]
+
+
+class McAllReduceArgs(C.Structure):
+    """Mirror of `mixq_mc_allreduce_args` (include/mixq.h)."""
+
+    _fields_ = [
+        ("mc", C.c_void_p),
+        ("local", C.c_void_p),
+        ("partial_off", C.c_ulonglong * 2),
+        ("result_off", C.c_ulonglong * 2),
+        ("flags_off", C.c_ulonglong),
+        ("epoch", C.c_void_p),
+        ("done", C.c_void_p),
+        ("residual", C.c_void_p),
+        ("n", C.c_longlong),
+        ("world", C.c_int),
+        ("rank", C.c_int),
+        ("buf", C.c_int),
+    ]
+
+
+class ExchangeFinishArgs(C.Structure):
+    """Mirror of `mixq_exchange_finish_args` (include/mixq.h)."""
+
+    _fields_ = [
+        ("recv", C.c_void_p),
+        ("result", C.c_void_p * 8),
+        ("mc_result", C.c_void_p),
+        ("flags", C.c_void_p * 8),
+        ("mc_flags", C.c_void_p),
+        ("epoch", C.c_void_p),
+        ("done", C.c_void_p),
+        ("residual", C.c_void_p),
+        ("M", C.c_int),
+        ("N", C.c_int),
+        ("world", C.c_int),
+        ("rank", C.c_int),
     ]
 
 
@@ -102,6 +142,8 @@ SIGNATURES = {
     "mixq_linear_fused": [C.POINTER(LinearArgs), _vp],
     "mixq_rope_attention_decode": [_vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _f, _vp],
     "mixq_rope_attention_decode_quant": [_vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _f, _vp, _i, _vp, _i, _vp, _vp, _i, _vp],
+    "mixq_quik_quantize": [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
+    "mixq_quik_addend": [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp],
     "mixq_mul_inplace": [_vp, _vp, _ll, _vp],
     "mixq_peer_alloc": [C.c_ulonglong, C.POINTER(C.c_void_p)],
     "mixq_peer_free": [_vp],
@@ -109,6 +151,8 @@ SIGNATURES = {
     "mixq_ipc_open_handle": [C.c_char_p, C.POINTER(C.c_void_p)],
     "mixq_ipc_close_handle": [_vp],
     "mixq_allreduce_residual": [C.POINTER(AllReduceArgs), _vp],
+    "mixq_allreduce_multicast": [C.POINTER(McAllReduceArgs), _vp],
+    "mixq_exchange_finish": [C.POINTER(ExchangeFinishArgs), _vp],
     "mixq_set_peer_timeout_ms": [_ll],
     "mixq_set_tile_n": [_i],
     "mixq_set_pdl": [_i],

@@ -13,6 +13,19 @@ __device__ __forceinline__ __half2 hadd2_via_f32(__half2 a, __half2 b) {
   return __floats2half2_rn(__fadd_rn(af.x, bf.x), __fadd_rn(af.y, bf.y));
 }
 
+// Where the fp16 output columns [n, ...) of a tile go (all columns of a tile share the answer): `base + row * ld + n`.
+// Normally y [M,N]; with the tensor-parallel push the tile's column slice j = n / peer_cols is rank j's receive slot
+// [M, peer_cols] (the returned base is shifted by -j * peer_cols so that the global column index still addresses it).
+__device__ __forceinline__ __half* y_base(const LinearParams& p, int n, int& ld) {
+  if (p.peer_cols > 0) {
+    const int j = n / p.peer_cols;
+    ld = p.peer_cols;
+    return p.y_peer[j] - static_cast<ptrdiff_t>(j) * p.peer_cols;
+  }
+  ld = p.N;
+  return p.y;
+}
+
 // One 32-column slab of one accumulator row: TMEM -> registers -> dequant (+outliers, +bias, SiLU) -> global.
 // Every lane of the warp must call this (tcgen05.ld is warp-collective); row_ok masks the stores.
 template <bool HAS_O>
@@ -72,7 +85,9 @@ __device__ __forceinline__ void epilogue_chunk(const LinearParams& p, uint32_t t
         if (has_res) o2 = hadd2_via_f32(o2, *reinterpret_cast<const __half2*>(&rsw[j2]));
         ow[j2] = *reinterpret_cast<const uint32_t*>(&o2);
       }
-      *reinterpret_cast<uint4*>(p.y + static_cast<size_t>(row) * p.N + ng) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      int ldy;
+      __half* yb = y_base(p, n, ldy);
+      *reinterpret_cast<uint4*>(yb + static_cast<size_t>(row) * ldy + ng) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     }
   }
 }
@@ -140,7 +155,9 @@ __device__ __forceinline__ void epilogue_span(const LinearParams& p, uint32_t t_
           if (has_res) o2 = hadd2_via_f32(o2, *reinterpret_cast<const __half2*>(&rsw[j2]));
           ow[j2] = *reinterpret_cast<const uint32_t*>(&o2);
         }
-        *reinterpret_cast<uint4*>(p.y + static_cast<size_t>(row) * p.N + ng) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        int ldy;
+        __half* yb = y_base(p, n0, ldy);
+        *reinterpret_cast<uint4*>(yb + static_cast<size_t>(row) * ldy + ng) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
       }
     }
   }
@@ -346,7 +363,9 @@ __device__ __forceinline__ void epilogue_run_coalesced(const LinearParams& p, ui
     const int last = two ? g + 1 : g;
     if ((last & 3) == 3 || last == ngroups - 1) {   // block complete (or run finished): 64 columns out, coalesced
       __syncwarp();
-      epi_stage_out(stage_sa, p.y, p.N, m_base, n0 + (g & ~3) * 16, ((last & 3) + 1) * 2, p.M, p.N, lane);
+      int ldy;
+      __half* yb = y_base(p, n0, ldy);
+      epi_stage_out(stage_sa, yb, ldy, m_base, n0 + (g & ~3) * 16, ((last & 3) + 1) * 2, p.M, p.N, lane);
       __syncwarp();
     }
   }

@@ -344,6 +344,8 @@ struct GemmCall {
   int M, N, K, act, epilogue, tile_n;
   const RowQuantArgs* rq;  // non-null => fused prologue
   uint32_t* grid_sync;
+  void* const* y_peer = nullptr;   // tensor-parallel push (see mixq_linear_args.y_peer)
+  int peer_cols = 0;
 };
 
 int run_gemm(const GemmCall& c, cudaStream_t st) {
@@ -359,6 +361,20 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
   const bool pair = c.q_w_up != nullptr;
   GemmPlan gp{};
   if (int r = plan_gemm(c.M, c.N, c.K, c.bit, c.n_out, pair, c.tile_n, di.sms, &gp)) return r;
+  if (c.peer_cols > 0) {
+    // tensor-parallel push: a tile must not straddle two ranks' column slices
+    if (pair || c.bias || c.outl || c.residual || c.epilogue != EPI_DEQUANT_F16 || c.y_peer == nullptr)
+      return fail(MIXQ_EINVAL, "tensor-parallel push: no bias / residual / addend / SwiGLU pair, fp16 output only");
+    if (c.peer_cols % 128 != 0 || c.N % c.peer_cols != 0 || c.N / c.peer_cols > 8)
+      return fail(MIXQ_EINVAL, "tensor-parallel push: peer_cols must be a multiple of 128 dividing N into at most 8 slices");
+    if (c.peer_cols % gp.tile_w != 0) {
+      if (int r = plan_gemm(c.M, c.N, c.K, c.bit, c.n_out, pair, 128, di.sms, &gp)) return r;
+      if (c.peer_cols % gp.tile_w != 0) return fail(MIXQ_EINVAL, "tensor-parallel push: no tile width divides peer_cols");
+    }
+    for (int j = 0; j < c.N / c.peer_cols; ++j)
+      if (c.y_peer[j] == nullptr || (reinterpret_cast<uintptr_t>(c.y_peer[j]) & 15) != 0)
+        return fail(MIXQ_EINVAL, "tensor-parallel push: missing or misaligned y_peer pointer");
+  }
   const bool two_cta = gp.two_cta != 0;
   const int npairs = di.sms / 2;
   if (pair && (c.bias != nullptr || !c.scale_col_up || (c.n_out > 0 && !c.weight_cache_up) || c.epilogue != EPI_DEQUANT_F16 ||
@@ -436,6 +452,9 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
   p.residual = static_cast<const __half*>(c.residual);
   p.ld_res = c.ld_res;
   p.y = static_cast<__half*>(c.y);
+  p.peer_cols = c.peer_cols;
+  if (c.peer_cols > 0)
+    for (int j = 0; j < c.N / c.peer_cols; ++j) p.y_peer[j] = static_cast<__half*>(c.y_peer[j]);
   p.y_i32 = c.y_i32;
   p.M = c.M;
   p.N = c.N;
@@ -748,7 +767,7 @@ int mixq_compact_outlier_columns(uint8_t* col_over, int K, int32_t* ind_out, int
 
 int mixq_linear_fused(const mixq_linear_args* a, void* stream) {
   if (a == nullptr) return fail(MIXQ_EINVAL, "null args");
-  if (!a->q_weight || !a->scale_col || !a->q_x || !a->x_scale || !a->y) return fail(MIXQ_EINVAL, "null pointer");
+  if (!a->q_weight || !a->scale_col || !a->q_x || !a->x_scale || (!a->y && a->peer_cols <= 0)) return fail(MIXQ_EINVAL, "null pointer");
   if (a->n_ind > 0 && (!a->ind || !a->weight_cache || !a->act_outliers))
     return fail(MIXQ_EINVAL, "n_ind > 0 needs ind, weight_cache and act_outliers");
   RowQuantArgs rq{};
@@ -769,6 +788,8 @@ int mixq_linear_fused(const mixq_linear_args* a, void* stream) {
   if (a->residual && a->ld_res < a->N) return fail(MIXQ_EINVAL, "ld_res < N");
   c.rq = a->skip_prologue ? nullptr : &rq;
   c.grid_sync = a->grid_sync;
+  c.y_peer = a->y_peer;
+  c.peer_cols = a->peer_cols;
   return run_gemm(c, static_cast<cudaStream_t>(stream));
 }
 
@@ -792,7 +813,8 @@ int mixq_rope_attention_decode_quant(const void* qkv, void* k_cache, void* v_cac
     return fail(MIXQ_EINVAL, "bad attention arguments (head_dim must be 64 or 128)");
   if (past_len > 0 && (!k_cache || !v_cache || cache_cap <= past_len))
     return fail(MIXQ_EINVAL, "past_len > 0 needs k/v caches with capacity > past_len");
-  if (static_cast<long long>(H) * D * 2 > 96 * 1024) return fail(MIXQ_EINVAL, "attention row does not fit the shared-memory row buffer");
+  if (static_cast<long long>(2 * H + 2 * Hkv) * D * 2 > 96 * 1024)
+    return fail(MIXQ_EINVAL, "attention row does not fit the shared-memory row buffer");
   RowQuantArgs rq{};
   if (int r = fill_rowquant(&rq, out, nullptr, nullptr, 0.f, ind, n_ind, act_outliers, ld_ao, q_x, x_scale, M, H * D, bit,
                             0.f, nullptr, nullptr))
@@ -873,6 +895,95 @@ int mixq_allreduce_residual(const mixq_allreduce_args* a, void* stream) {
   if (int r = device_info(&di)) return r;
   const int grid = grid_for(a->n / 8, 256, di.sms, 4);
   MIXQ_CUDA(launch_small(allreduce_residual_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), k));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int mixq_allreduce_multicast(const mixq_mc_allreduce_args* a, void* stream) {
+  if (!a || a->world < 2 || a->world > kMaxPeers || a->rank < 0 || a->rank >= a->world || !a->mc || !a->local || !a->epoch ||
+      !a->done || a->n < 8 || (a->n % (8ll * a->world)) != 0)
+    return fail(MIXQ_EINVAL, "bad multicast all-reduce arguments (2 <= world <= 8, n % (8 * world) == 0)");
+  for (int b = 0; b < 2; ++b)
+    if ((a->partial_off[b] & 15) || (a->result_off[b] & 15)) return fail(MIXQ_EINVAL, "buffer offsets must be 16-byte aligned");
+  if (a->flags_off & 15) return fail(MIXQ_EINVAL, "flags offset must be 16-byte aligned");
+  McAllReduceArgs k{};
+  k.mc = static_cast<uint8_t*>(a->mc);
+  k.local = static_cast<uint8_t*>(a->local);
+  for (int b = 0; b < 2; ++b) {
+    k.partial_off[b] = a->partial_off[b];
+    k.result_off[b] = a->result_off[b];
+  }
+  k.flags_off = a->flags_off;
+  k.epoch = static_cast<uint32_t*>(a->epoch);
+  k.done = static_cast<uint32_t*>(a->done);
+  k.residual = static_cast<const __half*>(a->residual);
+  k.n = a->n;
+  k.world = a->world;
+  k.rank = a->rank;
+  k.buf = a->buf & 1;
+  k.timeout_ns = g_peer_timeout_ms.load(std::memory_order_relaxed) * 1000000ull;
+  DeviceInfo di;
+  if (int r = device_info(&di)) return r;
+  const int grid = grid_for(a->n / 8 / a->world, 256, di.sms, 2);
+  MIXQ_CUDA(launch_small(allreduce_multicast_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), k));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int mixq_exchange_finish(const mixq_exchange_finish_args* a, void* stream) {
+  if (!a || a->world < 2 || a->world > kMaxPeers || a->rank < 0 || a->rank >= a->world || !a->recv || !a->epoch || !a->done ||
+      a->M < 1 || a->N < 8 || a->N % (8 * a->world) != 0)
+    return fail(MIXQ_EINVAL, "bad exchange_finish arguments (2 <= world <= 8, N % (8 * world) == 0)");
+  XchgFinishArgs k{};
+  k.recv = static_cast<const __half*>(a->recv);
+  for (int p = 0; p < a->world; ++p) {
+    if (!a->flags[p] || (!a->mc_result && !a->result[p])) return fail(MIXQ_EINVAL, "missing peer pointer");
+    k.result[p] = static_cast<__half*>(a->result[p]);
+    k.flags[p] = static_cast<uint32_t*>(a->flags[p]);
+  }
+  k.mc_result = static_cast<__half*>(a->mc_result);
+  k.mc_flags = static_cast<uint32_t*>(a->mc_flags);
+  k.epoch = static_cast<uint32_t*>(a->epoch);
+  k.done = static_cast<uint32_t*>(a->done);
+  k.residual = static_cast<const __half*>(a->residual);
+  k.M = a->M;
+  k.N = a->N;
+  k.world = a->world;
+  k.rank = a->rank;
+  k.timeout_ns = g_peer_timeout_ms.load(std::memory_order_relaxed) * 1000000ull;
+  DeviceInfo di;
+  if (int r = device_info(&di)) return r;
+  const int grid = grid_for(static_cast<long long>(a->M) * (a->N / a->world / 8), 256, di.sms, 2);
+  MIXQ_CUDA(launch_small(exchange_finish_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), k));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int mixq_quik_quantize(const void* x, const int64_t* int_indices, int n_int, const int64_t* fp_indices, int n_fp, int bits,
+                       void* q, void* meta, void* fp_x, int M, int K, void* stream) {
+  if (!x || !int_indices || !q || !meta || M < 1 || n_int < 1 || n_int + n_fp > K || (bits != 4 && bits != 8) ||
+      (n_fp > 0 && (!fp_indices || !fp_x)))
+    return fail(MIXQ_EINVAL, "bad quik_quantize arguments");
+  DeviceInfo di;
+  if (int r = device_info(&di)) return r;
+  const int grid = M < di.sms * 8 ? M : di.sms * 8;
+  MIXQ_CUDA(launch_small(quik_quantize_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), static_cast<const __half*>(x),
+                         int_indices, n_int, fp_indices, n_fp, bits, static_cast<int8_t*>(q), static_cast<__half*>(meta),
+                         static_cast<__half*>(fp_x), M, K));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int mixq_quik_addend(const void* meta, const void* reduced_w, const void* fp_result, int ld_fp, void* out, int M, int N,
+                     int bits, void* stream) {
+  if (!meta || !reduced_w || !out || M < 1 || N < 8 || N % 8 != 0 || (bits != 4 && bits != 8) || (fp_result && ld_fp < N))
+    return fail(MIXQ_EINVAL, "bad quik_addend arguments");
+  DeviceInfo di;
+  if (int r = device_info(&di)) return r;
+  const int grid = grid_for(static_cast<long long>(M) * (N / 8), 256, di.sms);
+  MIXQ_CUDA(launch_small(quik_addend_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), static_cast<const __half*>(meta),
+                         static_cast<const __half*>(reduced_w), static_cast<const __half*>(fp_result), ld_fp,
+                         static_cast<__half*>(out), M, N, bits));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }

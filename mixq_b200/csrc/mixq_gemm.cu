@@ -270,6 +270,7 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
     }
   }
 
+  if (p.peer_cols > 0) __threadfence_system();   // tensor-parallel push: peer stores performed before the CTA retires
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {

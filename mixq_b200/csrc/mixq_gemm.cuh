@@ -25,6 +25,11 @@ struct LinearParams {
   const __half* residual;  // optional fp16 [M, ld_res]: y = fp16(y + residual) (decoder residual stream)
   int ld_res;
   __half* y;
+  // tensor-parallel push (row-parallel Linear, reduce-scatter fused into the epilogue): when peer_cols > 0 the output column
+  // slice j = n / peer_cols of every tile is stored straight into rank j's receive slot for this rank,
+  // y_peer[j][row * peer_cols + (n - j * peer_cols)] — peer memory over NVLink for j != rank — instead of y[row * N + n]
+  __half* y_peer[8];
+  int peer_cols;
   int32_t* y_i32;
   int M, N, K;
   int n_out;           // outlier columns multiplied on the tensor cores (0 = none)

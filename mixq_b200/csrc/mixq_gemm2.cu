@@ -390,6 +390,8 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
     }
     if (trace && warp == 4 && lane == 0) trace[5] = globaltimer_ns();
   }
+  // tensor-parallel push: this thread's stores into the peers' receive slots are performed system-wide before the CTA retires
+  if (p.peer_cols > 0) __threadfence_system();
 
   tc_fence_before();
   __syncthreads();

@@ -164,6 +164,13 @@ struct AttnVec {
   }
 };
 
+// cos / sin of the rotary angle of dimension pair i at position pos.  Out of line on purpose: powf + sincosf are ~1.5 k SASS
+// instructions when inlined per element, and none of it runs at position 0 (the benchflops regime).
+static __device__ __noinline__ void rope_angle(float theta, int i, int D, int pos, float* sn, float* cs) {
+  const float inv_freq = powf(theta, -2.0f * static_cast<float>(i) / static_cast<float>(D));
+  sincosf(static_cast<float>(pos) * inv_freq, sn, cs);
+}
+
 // One (token m, head h) by one warp, q / k / v already in registers: RoPE on q and k, cache append, online-softmax
 // attention over past_len + 1 keys.
 template <int D>
@@ -179,11 +186,7 @@ __device__ __forceinline__ void attn_head_compute(const float (&q)[D / 32], cons
   for (int e = 0; e < E; ++e) {
     const float qo = __shfl_xor_sync(0xffffffffu, q[e], 16), ko = __shfl_xor_sync(0xffffffffu, k[e], 16);
     float sn = 0.f, cs = 1.f;
-    if (past_len > 0) {
-      const int i = (lane * E + e) % (D / 2);
-      const float inv_freq = powf(theta, -2.0f * static_cast<float>(i) / static_cast<float>(D));
-      sincosf(static_cast<float>(past_len) * inv_freq, &sn, &cs);
-    }
+    if (past_len > 0) rope_angle(theta, (lane * E + e) % (D / 2), D, past_len, &sn, &cs);
     // round to fp16 like the reference's fp16 tensors do
     qr[e] = __half2float(__float2half_rn(q[e] * cs + sgn * qo * sn));
     kr[e] = __half2float(__float2half_rn(k[e] * cs + sgn * ko * sn));
@@ -264,50 +267,50 @@ __global__ void __launch_bounds__(256) rope_attn_decode_kernel(const __half* __r
 // the outlier columns, takes the row abs-max and quantises — o_proj then runs with skip_prologue, exactly like the reference's
 // "fused" call mode where a producer (norm.py:24-33) leaves q_xcache / x_scale / activation_outliers in the cache.
 // rq.x = optional fp16 [M, H*D] copy of the attention output (outlier columns zeroed, as the reference leaves its tensor).
-constexpr int kAttnQuantWarps = 4;   // 128 threads and <= 128 registers: >= 4 CTAs per SM, 512 token rows in ONE wave
-constexpr int kAttnQuantHPW = 8;     // heads a warp keeps in flight at once (q, k, v of all of them are loaded before any math)
+constexpr int kAttnQuantWarps = 4;   // 128 threads, small register footprint: many CTAs per SM, 512 token rows in ONE wave
+// The qkv row of the token comes into shared memory with ONE bulk-async copy and the heads are walked by a ROLLED loop: this
+// code runs once per CTA, so an unrolled per-head body is paced by cold instruction fetch (ncu: stall_no_inst 65 % for the
+// 8-heads-in-registers version, 12.8 k SASS instructions).
 template <int D>
 __global__ void __launch_bounds__(kAttnQuantWarps * 32, 4)
 rope_attn_decode_quant_kernel(const __half* __restrict__ qkv, __half* k_cache, __half* v_cache, int cache_cap, int past_len,
                               int H, int Hkv, float theta, float scale, const RowQuantArgs rq) {
   constexpr int E = D / 32;
-  extern __shared__ __align__(128) uint8_t attn_row[];
+  extern __shared__ __align__(128) uint8_t attn_smem[];
   __shared__ RowQuantSmem sm;
+  __shared__ uint64_t row_bar;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ld = (H + 2 * Hkv) * D;
+  __half* qkv_s = reinterpret_cast<__half*>(attn_smem);                 // [ld] this token's q | k | v
+  __half* row_s = qkv_s + ld;                                            // [H * D] attention output row
+  if (threadIdx.x == 0) {
+    mbar_init(&row_bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
   pdl_launch_dependents();
   pdl_wait();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __half* row_s = reinterpret_cast<__half*>(attn_row);
-  for (int m = blockIdx.x; m < rq.M; m += gridDim.x) {
-    for (int base = 0; base < H; base += kAttnQuantWarps * kAttnQuantHPW) {
-      uint2 rq_[kAttnQuantHPW], rk_[kAttnQuantHPW], rv_[kAttnQuantHPW];   // packed fp16, all heads of this warp in flight
-      const int ld = (H + 2 * Hkv) * D;
-      const __half* row = qkv + static_cast<size_t>(m) * ld + lane * E;
-#pragma unroll
-      for (int j = 0; j < kAttnQuantHPW; ++j) {
-        const int h = base + warp + kAttnQuantWarps * j;
-        if (h < H) {
-          const int hk = h / (H / Hkv);
-          rq_[j] = AttnVec<D>::ldraw(row + h * D);
-          rk_[j] = AttnVec<D>::ldraw(row + (H + hk) * D);
-          rv_[j] = AttnVec<D>::ldraw(row + (H + Hkv + hk) * D);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < kAttnQuantHPW; ++j) {
-        const int h = base + warp + kAttnQuantWarps * j;
-        if (h < H) {
-          float q[E], k[E], v[E], acc[E];
-          AttnVec<D>::unpack(rq_[j], q);
-          AttnVec<D>::unpack(rk_[j], k);
-          AttnVec<D>::unpack(rv_[j], v);
-          attn_head_compute<D>(q, k, v, k_cache, v_cache, cache_cap, past_len, m, h, H, Hkv, theta, scale, lane, acc);
-          AttnVec<D>::st(row_s + h * D + lane * E, acc);
-          if (rq.x != nullptr) AttnVec<D>::st(rq.x + static_cast<size_t>(m) * rq.K + h * D + lane * E, acc);
-        }
-      }
+  uint32_t phase = 0;
+  for (int m = blockIdx.x; m < rq.M; m += gridDim.x, phase ^= 1) {
+    if (threadIdx.x == 0) {
+      mbar_arrive_expect_tx(&row_bar, static_cast<uint32_t>(ld) * 2u);
+      bulk_load(qkv_s, qkv + static_cast<size_t>(m) * ld, static_cast<uint32_t>(ld) * 2u, &row_bar);
+    }
+    mbar_wait(&row_bar, phase, 8, m);
+#pragma unroll 1
+    for (int h = warp; h < H; h += kAttnQuantWarps) {
+      const int hk = h / (H / Hkv);
+      float q[E], k[E], v[E], acc[E];
+      AttnVec<D>::ld(qkv_s + h * D + lane * E, q);
+      AttnVec<D>::ld(qkv_s + (H + hk) * D + lane * E, k);
+      AttnVec<D>::ld(qkv_s + (H + Hkv + hk) * D + lane * E, v);
+      attn_head_compute<D>(q, k, v, k_cache, v_cache, cache_cap, past_len, m, h, H, Hkv, theta, scale, lane, acc);
+      AttnVec<D>::st(row_s + h * D + lane * E, acc);
+      if (rq.x != nullptr) AttnVec<D>::st(rq.x + static_cast<size_t>(m) * rq.K + h * D + lane * E, acc);
     }
     __syncthreads();
     process_row(rq, m, 0, threadIdx.x, 0, &sm, row_s);
+    fence_proxy_async_smem();   // the next row's bulk copy overwrites qkv_s, which generic-proxy loads have just read
     __syncthreads();
   }
 }
@@ -326,7 +329,7 @@ cudaError_t launch_rope_attn_decode(const __half* qkv, __half* k_cache, __half* 
   cfg.numAttrs = pdl ? 1 : 0;
   if (rq != nullptr) {
     cfg.gridDim = dim3(M);
-    cfg.dynamicSmemBytes = static_cast<size_t>(H) * D * 2;
+    cfg.dynamicSmemBytes = static_cast<size_t>(2 * H + 2 * Hkv) * D * 2;   // the token's qkv row + its attention output row
     if (D == 128)
       return cudaLaunchKernelEx(&cfg, rope_attn_decode_quant_kernel<128>, qkv, k_cache, v_cache, cache_cap, past_len, H, Hkv, theta, scale, *rq);
     return cudaLaunchKernelEx(&cfg, rope_attn_decode_quant_kernel<64>, qkv, k_cache, v_cache, cache_cap, past_len, H, Hkv, theta, scale, *rq);
@@ -430,6 +433,245 @@ __global__ void __launch_bounds__(256) allreduce_residual_kernel(AllReduceArgs a
       __threadfence();
       *reinterpret_cast<volatile uint32_t*>(a.epoch) = s_epoch;
     }
+  }
+}
+
+// ---------------------------------------------------------------- all-reduce (+ residual) through the NVSwitch (NVLS multicast)
+// Every rank maps ONE symmetric allocation (partial 0/1, result 0/1, flag words at the same offsets) and a multicast address
+// that reaches all copies at once.  Rank r owns elements [r * n / world, (r + 1) * n / world):
+//   multimem.ld_reduce(partial[buf] slice)  — the switch adds the world copies (fp32 accumulation) and returns fp16: one
+//                                              NVLink read of n / world elements per rank instead of (world - 1) * n / world;
+//   + residual (a separate fp16 rounding, as all-reduce followed by `h + y` gives);
+//   multimem.st(result[buf] slice)          — the switch writes the slice into every rank's result buffer.
+// Handshakes are ONE multimem.red each: flags[phase] of every rank += 1, a rank proceeds when its own word reaches
+// world * exchange count.  Phase 0: "my partial is complete"; phase 1: "my slice is in every result buffer".  The exchange
+// count lives on the device (graph replayable); callers alternate buf = 0, 1 exactly as for the peer kernel.
+__device__ __forceinline__ void mc_signal(const McAllReduceArgs& a, int phase) {
+  __threadfence_system();
+  asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(a.mc + a.flags_off + 4 * phase), "r"(1u) : "memory");
+}
+__device__ __forceinline__ void mc_wait(const McAllReduceArgs& a, int phase, uint32_t e) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a.local + a.flags_off) + phase;
+  const uint32_t target = e * static_cast<uint32_t>(a.world);
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t v, spins = 0;
+  do {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(w) : "memory");
+    if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > a.timeout_ns) spin_timeout_trap(21 + phase, static_cast<int>(v), static_cast<int>(target));
+  } while (static_cast<int32_t>(v - target) < 0);
+}
+
+__global__ void __launch_bounds__(256) allreduce_multicast_kernel(McAllReduceArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();                                   // my partial (previous kernel of the stream) is complete and visible
+  __shared__ uint32_t s_epoch;
+  if (threadIdx.x == 0) {
+    const uint32_t e = *reinterpret_cast<volatile uint32_t*>(a.epoch) + 1;
+    s_epoch = e;
+    if (blockIdx.x == 0) mc_signal(a, 0);
+    mc_wait(a, 0, e);
+  }
+  __syncthreads();
+  const int buf = a.buf;
+  const long long nv = a.n >> 3;                // 16-byte vectors
+  const long long per = nv / a.world;
+  const long long v0 = per * a.rank, v1 = v0 + per;
+  const uint8_t* src = a.mc + a.partial_off[buf];
+  uint8_t* dst = a.mc + a.result_off[buf];
+  for (long long i = v0 + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < v1;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    H8 y;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.f16x2 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(y.u.x), "=r"(y.u.y), "=r"(y.u.z), "=r"(y.u.w)
+                 : "l"(src + i * 16)
+                 : "memory");
+    if (a.residual != nullptr) {
+      H8 r;
+      r.u = *(reinterpret_cast<const uint4*>(a.residual) + i);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 yf = __half22float2(y.h2[j]), rf = __half22float2(r.h2[j]);
+        y.h2[j] = __floats2half2_rn(__fadd_rn(yf.x, rf.x), __fadd_rn(yf.y, rf.y));
+      }
+    }
+    asm volatile("multimem.st.relaxed.sys.global.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(dst + i * 16), "r"(y.u.x), "r"(y.u.y),
+                 "r"(y.u.z), "r"(y.u.w)
+                 : "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    if (atomicAdd(a.done, 1u) == gridDim.x - 1) {   // last block out: every block's slice stores have been issued and fenced
+      mc_signal(a, 1);                               // "my slice of exchange e is in every result buffer"
+      mc_wait(a, 1, s_epoch);                        // ... and everybody else's is in mine
+      *a.done = 0;
+      __threadfence();
+      *reinterpret_cast<volatile uint32_t*>(a.epoch) = s_epoch;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- fused exchange, second half (see XchgFinishArgs)
+// Handshake counters: word `phase` of EVERY rank is incremented once per exchange by every rank (one multimem.red through the
+// switch, or one red.release.sys per peer); a rank proceeds when its own word reaches world * exchange count.
+__device__ __forceinline__ void xf_signal(const XchgFinishArgs& a, int phase) {
+  __threadfence_system();
+  if (a.mc_flags != nullptr) {
+    asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(a.mc_flags + phase), "r"(1u) : "memory");
+  } else {
+    for (int p = 0; p < a.world; ++p)
+      asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(a.flags[p] + phase), "r"(1u) : "memory");
+  }
+}
+__device__ __forceinline__ void xf_wait(const XchgFinishArgs& a, int phase, uint32_t e) {
+  const uint32_t* w = a.flags[a.rank] + phase;
+  const uint32_t target = e * static_cast<uint32_t>(a.world);
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t v, spins = 0;
+  do {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(w) : "memory");
+    if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > a.timeout_ns) spin_timeout_trap(31 + phase, static_cast<int>(v), static_cast<int>(target));
+  } while (static_cast<int32_t>(v - target) < 0);
+}
+
+__global__ void __launch_bounds__(256) exchange_finish_kernel(XchgFinishArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();                                   // my GEMM (previous kernel of the stream) has pushed all of its tiles
+  __shared__ uint32_t s_epoch;
+  if (threadIdx.x == 0) {
+    const uint32_t e = *reinterpret_cast<volatile uint32_t*>(a.epoch) + 1;
+    s_epoch = e;
+    if (blockIdx.x == 0) xf_signal(a, 0);       // "my pushes of exchange e are complete"
+    xf_wait(a, 0, e);                           // ... and so are everybody's into my slots
+  }
+  __syncthreads();
+  const int Ns = a.N / a.world;
+  const int vpr = Ns >> 3;                      // 16-byte vectors per slot row
+  const long long nv = static_cast<long long>(a.M) * vpr;
+  const size_t slot = static_cast<size_t>(a.M) * Ns;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int row = static_cast<int>(i / vpr), c8 = static_cast<int>(i - static_cast<long long>(row) * vpr);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int s = 0; s < a.world; ++s) {
+      H8 v;
+      v.u = __ldcv(reinterpret_cast<const uint4*>(a.recv + s * slot + static_cast<size_t>(row) * Ns) + c8);   // written by peers: never from L1
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(v.h2[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+    const size_t off = static_cast<size_t>(row) * a.N + static_cast<size_t>(a.rank) * Ns + static_cast<size_t>(c8) * 8;
+    H8 r, o;
+    if (a.residual != nullptr) r.u = *reinterpret_cast<const uint4*>(a.residual + off);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __half2 y2 = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+      if (a.residual != nullptr) {
+        const float2 yf = __half22float2(y2), rf = __half22float2(r.h2[j]);
+        y2 = __floats2half2_rn(__fadd_rn(yf.x, rf.x), __fadd_rn(yf.y, rf.y));
+      }
+      o.h2[j] = y2;
+    }
+    if (a.mc_result != nullptr) {
+      asm volatile("multimem.st.relaxed.sys.global.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(a.mc_result + off), "r"(o.u.x), "r"(o.u.y),
+                   "r"(o.u.z), "r"(o.u.w)
+                   : "memory");
+    } else {
+      for (int p = 0; p < a.world; ++p) *reinterpret_cast<uint4*>(a.result[p] + off) = o.u;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    if (atomicAdd(a.done, 1u) == gridDim.x - 1) {   // last block out: every block's slice stores have been issued and fenced
+      xf_signal(a, 1);                               // "my slice of exchange e is in every result buffer"
+      xf_wait(a, 1, s_epoch);                        // ... and everybody else's is in mine
+      *a.done = 0;
+      __threadfence();
+      *reinterpret_cast<volatile uint32_t*>(a.epoch) = s_epoch;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- QUIK MixedQLinear (mixquant/modules/qlinear.py:82-152)
+// quik.asymmetric.quantize(x, int_indices, fp_indices, bits) (qlinear.py:117-120), one CTA per token row:
+//   zero = min over the int columns, scale = (max - min) / (2^bits - 1) (both stored as fp16: meta[0][m], meta[1][m]),
+//   q = rn((x - zero) / scale) - 2^(bits-1) in [-2^(b-1), 2^(b-1) - 1], one value per byte (the tcgen05 path has no int4 MMA);
+//   fp_x = x[:, fp_indices].  HBM-bound byte work: x is read twice (second pass from L1/L2), 1 byte written per element.
+__global__ void __launch_bounds__(256) quik_quantize_kernel(const __half* __restrict__ x, const int64_t* __restrict__ int_idx,
+                                                            int n_int, const int64_t* __restrict__ fp_idx, int n_fp, int bits,
+                                                            int8_t* __restrict__ q, __half* __restrict__ meta,
+                                                            __half* __restrict__ fp_x, int M, int K) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float s_mn[8], s_mx[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int m = blockIdx.x; m < M; m += gridDim.x) {
+    const __half* row = x + static_cast<size_t>(m) * K;
+    float mn = INFINITY, mx = -INFINITY;
+    for (int j = threadIdx.x; j < n_int; j += blockDim.x) {
+      const float v = __half2float(row[int_idx[j]]);
+      mn = fminf(mn, v);
+      mx = fmaxf(mx, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
+    __syncthreads();
+    mn = s_mn[0];
+    mx = s_mx[0];
+    for (int w = 1; w < (blockDim.x >> 5); ++w) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); }
+    const float levels = static_cast<float>((1 << bits) - 1);
+    const __half scale_h = __float2half_rn(__fdiv_rn(mx - mn, levels)), zero_h = __float2half_rn(mn);
+    const float scale = __half2float(scale_h), zero = __half2float(zero_h);
+    const float r = scale > 0.f ? __fdiv_rn(1.0f, scale) : 0.f;
+    const float half_range = static_cast<float>(1 << (bits - 1));
+    if (threadIdx.x == 0) {
+      meta[m] = scale_h;
+      meta[M + m] = zero_h;
+    }
+    int8_t* qrow = q + static_cast<size_t>(m) * n_int;
+    for (int j = threadIdx.x; j < n_int; j += blockDim.x) {
+      const float v = __half2float(row[int_idx[j]]);
+      float t = rintf(__fmul_rn(v - zero, r)) - half_range;
+      t = fminf(fmaxf(t, -half_range), half_range - 1.f);
+      qrow[j] = static_cast<int8_t>(t);
+    }
+    for (int j = threadIdx.x; j < n_fp; j += blockDim.x) fp_x[static_cast<size_t>(m) * n_fp + j] = row[fp_idx[j]];
+    __syncthreads();
+  }
+}
+// The addend of quik.asymmetric.dequantize (qlinear.py:149-150): out[m,n] = fp16((zero[m] + 2^(b-1) scale[m]) * reduced_w[n]
+// + fp_result[m,n]); the int GEMM's epilogue then adds it to acc * scale[m] * ws[n] (mixq_int4/int8_fused_dequantize).
+__global__ void quik_addend_kernel(const __half* __restrict__ meta, const __half* __restrict__ reduced_w,
+                                   const __half* __restrict__ fp_result, int ld_fp, __half* __restrict__ out, int M, int N, int bits) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int nv = N >> 3;
+  const long long total = static_cast<long long>(M) * nv;
+  const float half_range = static_cast<float>(1 << (bits - 1));
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(i / nv), n = static_cast<int>(i - static_cast<long long>(m) * nv) * 8;
+    const float shift = __fadd_rn(__half2float(meta[M + m]), __fmul_rn(half_range, __half2float(meta[m])));
+    H8 rw, fp, o;
+    rw.u = __ldg(reinterpret_cast<const uint4*>(reduced_w + n));
+    if (fp_result != nullptr) fp.u = *reinterpret_cast<const uint4*>(fp_result + static_cast<size_t>(m) * ld_fp + n);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = __fmul_rn(shift, __half2float(rw.h[j]));
+      if (fp_result != nullptr) v = __fadd_rn(v, __half2float(fp.h[j]));
+      o.h[j] = __float2half_rn(v);
+    }
+    *reinterpret_cast<uint4*>(out + static_cast<size_t>(m) * N + n) = o.u;
   }
 }
 

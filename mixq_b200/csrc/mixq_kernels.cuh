@@ -20,6 +20,11 @@ template <int D>
 __global__ void rope_attn_decode_quant_kernel(const __half* qkv, __half* k_cache, __half* v_cache, int cache_cap, int past_len,
                                               int H, int Hkv, float theta, float scale, const RowQuantArgs rq);
 __global__ void mul_inplace_kernel(__half2* a, const __half2* b, long long n2);
+// QUIK (mixquant/modules/qlinear.py): asymmetric per-token activation quantisation + the zero-point correction addend
+__global__ void quik_quantize_kernel(const __half* x, const int64_t* int_idx, int n_int, const int64_t* fp_idx, int n_fp, int bits,
+                                     int8_t* q, __half* meta, __half* fp_x, int M, int K);
+__global__ void quik_addend_kernel(const __half* meta, const __half* reduced_w, const __half* fp_result, int ld_fp, __half* out,
+                                   int M, int N, int bits);
 
 constexpr int kMaxPeers = 8;
 struct AllReduceArgs {
@@ -35,5 +40,38 @@ struct AllReduceArgs {
   unsigned long long timeout_ns;         // a peer that stays silent this long is reported (printf + trap); mixq_set_peer_timeout_ms
 };
 __global__ void allreduce_residual_kernel(AllReduceArgs a);
+
+// The same exchange through an NVLink-SHARP multicast mapping (NVSwitch reduces and broadcasts: multimem.ld_reduce / multimem.st).
+struct McAllReduceArgs {
+  uint8_t* mc;                 // multicast address of the symmetric allocation (every rank's copy at once)
+  uint8_t* local;              // this rank's copy of the same allocation
+  unsigned long long partial_off[2], result_off[2], flags_off;   // byte offsets inside the allocation (identical on all ranks)
+  uint32_t* epoch;             // local: exchanges finished so far
+  uint32_t* done;              // local: blocks finished in the current launch
+  const __half* residual;      // local [n] or nullptr
+  long long n;                 // elements, multiple of 8 * world
+  int world, rank, buf;
+  unsigned long long timeout_ns;
+};
+__global__ void allreduce_multicast_kernel(McAllReduceArgs a);
+
+
+// Second half of the fused row-parallel exchange.  The GEMM epilogues have PUSHED every rank's partial of column slice j into
+// rank j's receive slots (LinearParams::y_peer); this kernel shakes hands, reduces this rank's slice from its local slots
+// (fp32, rank order, one rounding to fp16), adds the residual slice as a separate fp16 op and broadcasts the slice into every
+// rank's result buffer — through the switch (multimem.st) when a multicast mapping exists, else with one store per peer.
+struct XchgFinishArgs {
+  const __half* recv;          // local: [world][M, Ns] receive slots of this exchange (slot s = rank s's partial of MY slice)
+  __half* result[kMaxPeers];   // every rank's result buffer [M, N] of this exchange as mapped here (own rank: local)
+  __half* mc_result;           // multicast address of the result buffer, or nullptr
+  uint32_t* flags[kMaxPeers];  // every rank's two handshake counters as mapped here (own rank: local)
+  uint32_t* mc_flags;          // multicast address of the counters, or nullptr
+  uint32_t* epoch;             // local: exchanges finished so far
+  uint32_t* done;              // local: blocks finished in the current launch
+  const __half* residual;      // local [M, N] or nullptr
+  int M, N, world, rank;
+  unsigned long long timeout_ns;
+};
+__global__ void exchange_finish_kernel(XchgFinishArgs a);
 
 }  // namespace mixq

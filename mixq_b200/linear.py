@@ -256,7 +256,7 @@ class MixLinear_GEMM(nn.Module):
                                                   self.in_features, self.bit, self._stream()), "gather_weight_columns")
 
     def _launch(self, cache, M, y, *, x=None, skip_prologue=False, act=ACT_NONE, norm_weight=None, eps=0.0,
-                norm_out=None, residual=None, q_x=None, act_outliers=None, ld_ao=None, up=None):
+                norm_out=None, residual=None, q_x=None, act_outliers=None, ld_ao=None, up=None, push=None):
         """One mixq_linear_fused launch."""
         a = self._args
         n = self._n_ind
@@ -292,6 +292,13 @@ class MixLinear_GEMM(nn.Module):
         a.residual = _ptr(residual)
         a.ld_res = 0 if residual is None else residual.stride(0)
         a.y = _ptr(y)
+        # tensor-parallel push: column slice j of y goes straight into rank j's receive slot (tp.PushExchange.push_targets())
+        if push is None:
+            a.peer_cols = 0
+        else:
+            ptrs, a.peer_cols = push
+            for j, pj in enumerate(ptrs):
+                a.y_peer[j] = pj
         a.act = act
         a.skip_prologue = 1 if skip_prologue else 0
         a.grid_sync = _ptr(cache.grid_sync)
@@ -313,7 +320,7 @@ class MixLinear_GEMM(nn.Module):
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
-    def forward(self, x, cache=None, unfused=False, residual=None, out=None):
+    def forward(self, x, cache=None, unfused=False, residual=None, out=None, push=None):
         """linear.py:165-289.  unfused=True: x holds raw fp16 activations (their outlier columns are zeroed IN
         PLACE, as the reference does); unfused=False: the preceding FasterTransformerRMSNorm already left
         q_xcache / x_scale / activation_outliers in the cache.  `residual` (extension): y = fp16(y + residual);
@@ -326,7 +333,13 @@ class MixLinear_GEMM(nn.Module):
         if unfused and inputs.data_ptr() != x.data_ptr():
             raise _lib.MixqError("unfused MixLinear needs a contiguous activation tensor (columns are zeroed in place)")
         M = inputs.shape[0]
-        if out is None:
+        if push is not None:
+            # `push` (extension): (slot pointers, slice width) from tp.PushExchange — the fp16 output is scattered straight
+            # into the ranks' receive slots by the epilogue; nothing is returned
+            if residual is not None or out is not None or self.bias is not None:
+                raise _lib.MixqError("push excludes residual / out / bias (the exchange's finish kernel adds the residual)")
+            y = None
+        elif out is None:
             y = torch.empty((M, self.out_features), dtype=torch.float16, device=inputs.device)
         else:
             if out.dtype != torch.float16 or not out.is_contiguous() or out.numel() != M * self.out_features:
@@ -338,13 +351,13 @@ class MixLinear_GEMM(nn.Module):
             cache.ind = self.ind
             if unfused:
                 # steady state: gather+zero, absmax, quantise, both GEMMs, epilogue — one launch
-                self._launch(cache, M, y, x=inputs, residual=res2)
+                self._launch(cache, M, y, x=inputs, residual=res2, push=push)
                 cache.q_xcache = cache.q_x_buffer(M, self.in_features)
                 cache.activation_outliers = cache.ao_buffer(self._n_ind)[:M, : self._n_ind]
             else:
                 ao, ld = self._cached_act_outliers(cache, M)
-                self._launch(cache, M, y, skip_prologue=True, residual=res2, q_x=cache.q_xcache, act_outliers=ao, ld_ao=ld)
-            return y.reshape(cache.shape)
+                self._launch(cache, M, y, skip_prologue=True, residual=res2, q_x=cache.q_xcache, act_outliers=ao, ld_ao=ld, push=push)
+            return None if y is None else y.reshape(cache.shape)
 
         # ---- online outlier discovery (first cache.stop calls): linear.py:187-226
         lib = _lib.load()
@@ -380,11 +393,11 @@ class MixLinear_GEMM(nn.Module):
         if self.cnt >= self.cache.stop or self._n_ind > 128:
             self.add_outliers = False
         cache.activation_outliers = ao[:M, : self._n_ind]
-        self._launch(cache, M, y, skip_prologue=True, residual=res2)
-        return y.reshape(cache.shape)
+        self._launch(cache, M, y, skip_prologue=True, residual=res2, push=push)
+        return None if y is None else y.reshape(cache.shape)
 
     @torch.no_grad()
-    def forward_quantized(self, M, cache=None, residual=None, out=None):
+    def forward_quantized(self, M, cache=None, residual=None, out=None, push=None):
         """The reference's fused call mode (linear.py:194-199: consume cache.q_xcache / x_scale / activation_outliers left by
         a producer kernel) when the producer keeps no fp16 activation tensor at all — e.g. the attention kernel that
         quantises its own output rows for o_proj (mixq_rope_attention_decode_quant).  Steady state only."""
@@ -393,7 +406,9 @@ class MixLinear_GEMM(nn.Module):
         if self.add_outliers:
             raise _lib.MixqError("forward_quantized is a steady-state path: run the discovery calls first")
         self._require_cuda(cache.q_xcache, self.q_weight)
-        if out is None:
+        if push is not None:
+            y = None
+        elif out is None:
             y = torch.empty((M, self.out_features), dtype=torch.float16, device=self.q_weight.device)
         else:
             if out.dtype != torch.float16 or not out.is_contiguous() or out.numel() != M * self.out_features:
@@ -403,7 +418,7 @@ class MixLinear_GEMM(nn.Module):
         cache.ind = self.ind
         ao, ld = self._cached_act_outliers(cache, M)
         self._launch(cache, M, y, skip_prologue=True, residual=None if residual is None else residual.reshape(M, self.out_features),
-                     q_x=cache.q_xcache, act_outliers=ao, ld_ao=ld)
+                     q_x=cache.q_xcache, act_outliers=ao, ld_ao=ld, push=push)
         return y
 
     @torch.no_grad()

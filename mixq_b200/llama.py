@@ -29,7 +29,7 @@ import torch
 from . import _lib
 from .cache import MixLibCache
 from .linear import MixLinear_GEMM
-from .tp import PeerExchange, all_reduce_sum, pack_qkv_shard, shard_cols, shard_rows
+from .tp import all_reduce_sum, make_exchange, pack_qkv_shard, shard_cols, shard_rows
 
 
 @dataclass
@@ -146,17 +146,19 @@ class LlamaDecoder:
         self.discovered = False
         # one launch for up_proj + gate_proj + SiLU + gate*up (needs the 2-CTA kernel: M > 128, bit 8)
         self.fuse_swiglu = (bit == 8 and batch > 128)
-        # attention + o_proj's activation prologue in one launch (MIXQ_FUSE_ATTN_QUANT=1; off by default until it beats the separate launches)
-        self.fuse_attn_quant = os.environ.get("MIXQ_FUSE_ATTN_QUANT", "0") == "1"
+        # attention + o_proj's activation prologue in one launch (MIXQ_FUSE_ATTN_QUANT=0: separate launches)
+        self.fuse_attn_quant = os.environ.get("MIXQ_FUSE_ATTN_QUANT", "1") != "0"
         self.graph = None
         self._static_tokens = None
         self._static_logits = None
         self.kv = None
         self.lib = _lib.load()
-        # row-parallel exchange: one peer-memory kernel (all-reduce + residual) unless MIXQ_TP_EXCHANGE=nccl
+        # row-parallel exchange: ONE kernel of this library (all-reduce + residual) — through the NVSwitch (NVLS multicast) when
+        # MIXQ_TP_EXCHANGE = auto (= push: reduce-scatter fused into the GEMM epilogue + finish kernel) | push-nomc | multicast | peer | nccl
         self.xchg = None
-        if world_size > 1 and os.environ.get("MIXQ_TP_EXCHANGE", "peer") == "peer":
-            self.xchg = PeerExchange(batch, H, rank, world_size, group=group, device=device)
+        kind = os.environ.get("MIXQ_TP_EXCHANGE", "auto")
+        if world_size > 1 and kind != "nccl":
+            self.xchg = make_exchange(batch, H, rank, world_size, group=group, device=device, kind=kind)
 
     def close(self):
         """Release the peer-exchange buffers (CUDA-IPC mappings + cudaMalloc'd partial / result buffers) and the graph."""
@@ -237,7 +239,10 @@ class LlamaDecoder:
                 self._attention_quant(qkv, L["o_proj"], past_len, li)
                 M = qkv.shape[0]
                 if tp and self.xchg is not None:
-                    L["o_proj"].forward_quantized(M, out=self.xchg.next_partial())
+                    if getattr(self.xchg, "fused", False):
+                        L["o_proj"].forward_quantized(M, push=self.xchg.push_targets())
+                    else:
+                        L["o_proj"].forward_quantized(M, out=self.xchg.next_partial())
                     h = self.xchg.reduce(h)
                 elif tp:
                     h = h + self._allreduce(L["o_proj"].forward_quantized(M))
@@ -246,7 +251,10 @@ class LlamaDecoder:
             else:
                 attn = self._attention(qkv, past_len, li)
                 if tp and self.xchg is not None:
-                    L["o_proj"](attn, None, True, out=self.xchg.next_partial())
+                    if getattr(self.xchg, "fused", False):
+                        L["o_proj"](attn, None, True, push=self.xchg.push_targets())
+                    else:
+                        L["o_proj"](attn, None, True, out=self.xchg.next_partial())
                     h = self.xchg.reduce(h)
                 elif tp:
                     h = h + self._allreduce(L["o_proj"](attn, None, True))
@@ -262,12 +270,17 @@ class LlamaDecoder:
                 gate = L["gate_proj"].forward_without_preconditionFusedSilu(h, self.cache)
                 _lib.check(self.lib.mixq_mul_inplace(gate.data_ptr(), up.data_ptr(), gate.numel(), self._stream()), "mul")
             if tp and self.xchg is not None:
-                L["down_proj"](gate, None, True, out=self.xchg.next_partial())
+                if getattr(self.xchg, "fused", False):
+                    L["down_proj"](gate, None, True, push=self.xchg.push_targets())
+                else:
+                    L["down_proj"](gate, None, True, out=self.xchg.next_partial())
                 h = self.xchg.reduce(h)
             elif tp:
                 h = h + self._allreduce(L["down_proj"](gate, None, True))
             else:
                 h = L["down_proj"](gate, None, True, residual=h)
+            if li == 0 and getattr(self, "probe_layer0", False):
+                self.hidden_after_layer0 = h.clone()     # parity probe (bench.py tp_parity): the residual stream after layer 0
         hn = torch.empty_like(h)
         _lib.check(self.lib.mixq_rmsnorm(h.data_ptr(), self.norm_f.data_ptr(), hn.data_ptr(), cfg.eps, h.shape[0],
                                          cfg.hidden, self._stream()), "final norm")
@@ -358,8 +371,20 @@ class LlamaDecoder:
             mods[p + "mlp.gate_proj"], mods[p + "mlp.up_proj"], mods[p + "mlp.down_proj"] = L["gate_proj"], L["up_proj"], L["down_proj"]
             extra[p + "input_layernorm.weight"] = L["ln1"]
             extra[p + "post_attention_layernorm.weight"] = L["ln2"]
-        return ck.save_quantized(save_dir, mods, {"w_bit": self.bit, "version": "MIX", "q_group_size": 128}, extra=extra,
-                                 safetensors=safetensors, shard_size=shard_size)
+        files = list(ck.save_quantized(save_dir, mods, {"w_bit": self.bit, "version": "MIX", "q_group_size": 128}, extra=extra,
+                                       safetensors=safetensors, shard_size=shard_size))
+        # the HF config.json the reference's loader (base.py:_load_config -> AutoConfig.from_pretrained) and
+        # mixq_b200.auto.AutoForCausalLM.from_quantized read the architecture from
+        import json
+        cfg = self.cfg
+        hf = {"architectures": ["LlamaForCausalLM"], "model_type": "llama", "hidden_size": cfg.hidden,
+              "intermediate_size": cfg.intermediate, "num_hidden_layers": self.n_layers, "num_attention_heads": cfg.heads,
+              "num_key_value_heads": cfg.kv_heads, "vocab_size": cfg.vocab, "rms_norm_eps": cfg.eps, "rope_theta": cfg.rope_theta,
+              "hidden_act": "silu", "max_position_embeddings": 4096, "torch_dtype": "float16", "tie_word_embeddings": False}
+        path = os.path.join(save_dir, "config.json")
+        with open(path, "w") as f:
+            json.dump(hf, f, indent=2)
+        return files + [path]
 
     @classmethod
     def from_quantized(cls, save_dir: str, cfg: LlamaConfig, batch: int, device="cuda", safetensors: bool = False):
@@ -387,7 +412,7 @@ class LlamaDecoder:
         self.lm_head = rest["lm_head.weight"].to(device)
         self.discovered = False
         self.fuse_swiglu = (self.bit == 8 and batch > 128)
-        self.fuse_attn_quant = os.environ.get("MIXQ_FUSE_ATTN_QUANT", "0") == "1"
+        self.fuse_attn_quant = os.environ.get("MIXQ_FUSE_ATTN_QUANT", "1") != "0"
         self.graph = self._static_tokens = self._static_logits = self.kv = None
         self.lib = _lib.load()
         self.xchg = None

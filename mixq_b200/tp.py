@@ -149,3 +149,219 @@ class PeerExchange:
         for p in self._own:
             self.lib.mixq_peer_free(p)
         self._own = []
+
+
+class MulticastExchange:
+    """The exchange step through the NVSwitch: NVLink-SHARP multicast (multimem.ld_reduce / multimem.st / multimem.red) in ONE
+    kernel of this library per rank (include/mixq.h: mixq_allreduce_multicast).  Same interface as PeerExchange.
+
+    Plumbing only comes from torch: `torch.distributed._symmetric_memory` allocates one symmetric buffer per rank and hands
+    back this rank's pointer and the multicast address; the data plane is this library's kernel.  Raises RuntimeError when
+    the platform offers no multicast mapping (callers then fall back to PeerExchange).
+    """
+
+    two_shot = True   # reduce-scatter + all-gather through the switch
+
+    def __init__(self, rows: int, cols: int, rank: int, world: int, group=None, device="cuda"):
+        from . import _lib
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        if not (2 <= world <= 8):
+            raise ValueError("MulticastExchange needs 2..8 ranks on one node")
+        n = rows * cols
+        if n % (8 * world):
+            raise ValueError("rows * cols must be a multiple of 8 * world")
+        self.lib, self._check = _lib.load(), _lib.check
+        self.rows, self.cols, self.rank, self.world, self.device = rows, cols, rank, world, device
+        nbytes = n * 2
+        total = 4 * nbytes + 256           # partial 0/1, result 0/1, flag words
+        grp = dist.group.WORLD if group is None else group
+        try:
+            symm.enable_symm_mem_for_group(grp.group_name)
+        except Exception:
+            pass
+        self._buf = symm.empty(total // 2, dtype=torch.float16, device=torch.device(device) if not isinstance(device, torch.device) else device)
+        self._buf.zero_()
+        torch.cuda.synchronize()
+        self._hdl = symm.rendezvous(self._buf, grp)
+        mc = int(getattr(self._hdl, "multicast_ptr", 0) or 0)
+        if mc == 0:
+            raise RuntimeError("no NVLS multicast mapping on this platform")
+        self._state = torch.zeros(2, dtype=torch.int32, device=device)      # epoch, done
+        a = self._args = _lib.McAllReduceArgs()
+        a.mc, a.local = mc, self._buf.data_ptr()
+        a.partial_off[0], a.partial_off[1] = 0, nbytes
+        a.result_off[0], a.result_off[1] = 2 * nbytes, 3 * nbytes
+        a.flags_off = 4 * nbytes
+        a.epoch = self._state.data_ptr()
+        a.done = self._state.data_ptr() + 4
+        a.n, a.world, a.rank = n, world, rank
+        views = [self._buf[j * n:(j + 1) * n].view(rows, cols) for j in range(4)]
+        self.partials, self.results = views[:2], views[2:]
+        self.buf = 0
+        dist.barrier(group=group)       # nobody signals before everybody has mapped everything
+
+    def next_partial(self) -> torch.Tensor:
+        return self.partials[self.buf]
+
+    def reduce(self, residual, out: torch.Tensor = None) -> torch.Tensor:
+        a = self._args
+        a.buf = self.buf
+        a.residual = 0 if residual is None else residual.data_ptr()
+        self._check(self.lib.mixq_allreduce_multicast(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                    "allreduce_multicast")
+        out = self.results[self.buf]
+        self.buf ^= 1
+        return out
+
+    def close(self):
+        torch.cuda.synchronize()
+        self.partials, self.results = [], []
+        self._hdl = None
+        self._buf = None
+
+
+def _symmetric_alloc(total_bytes: int, rank: int, world: int, group=None, device="cuda"):
+    """One zero-initialised allocation of `total_bytes` per rank, mapped into every rank of the node.
+    Returns (local_ptr, [ptr of rank r's copy as mapped here], multicast_ptr or 0, keepalive, close()).
+    torch.distributed._symmetric_memory when it works (it also yields an NVLS multicast address on NVSwitch systems),
+    else cudaMalloc + CUDA-IPC handles exchanged over the process group.  Plumbing only."""
+    import torch.distributed as dist
+    from . import _lib
+    lib = _lib.load()
+    try:
+        import torch.distributed._symmetric_memory as symm
+        grp = dist.group.WORLD if group is None else group
+        dev = torch.device(device) if not isinstance(device, torch.device) else device
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        buf = symm.empty((total_bytes + 1) // 2, dtype=torch.float16, device=dev)
+        buf.zero_()
+        torch.cuda.synchronize()
+        hdl = symm.rendezvous(buf, grp)
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        assert ptrs[rank] == buf.data_ptr()
+        return buf.data_ptr(), ptrs, mc, (buf, hdl), (lambda: None)
+    except Exception as e:
+        import sys
+        if rank == 0:
+            print(f"mixq: torch symmetric memory unavailable ({type(e).__name__}: {e}); using CUDA-IPC peer mappings", file=sys.stderr)
+    p = C.c_void_p()
+    _lib.check(lib.mixq_peer_alloc(total_bytes, C.byref(p)), "peer_alloc")
+    h = C.create_string_buffer(64)
+    _lib.check(lib.mixq_ipc_get_handle(p, h), "ipc_get_handle")
+    gathered = [None] * world
+    dist.all_gather_object(gathered, h.raw, group=group)
+    ptrs, mapped = [0] * world, []
+    for r in range(world):
+        if r == rank:
+            ptrs[r] = p.value
+        else:
+            q = C.c_void_p()
+            _lib.check(lib.mixq_ipc_open_handle(gathered[r], C.byref(q)), f"ipc_open_handle(rank {r})")
+            ptrs[r] = q.value
+            mapped.append(q.value)
+
+    def close():
+        for q in mapped:
+            lib.mixq_ipc_close_handle(q)
+        lib.mixq_peer_free(p.value)
+    return p.value, ptrs, 0, None, close
+
+
+class PushExchange:
+    """The FUSED row-parallel exchange (include/mixq.h: mixq_linear_args.y_peer + mixq_exchange_finish).
+
+    Reduce-scatter half: the row-parallel MixLinear's epilogue warps store column slice j of this rank's partial straight into
+    rank j's receive slot over NVLink (`push_targets()` hands the slot pointers to MixLinear_GEMM.forward(..., push=)), so the
+    transfer rides under the GEMM's own tail.  All-gather half: `reduce(residual)` launches the small finish kernel — handshake,
+    local fp32 reduction of this rank's slice in rank order (+ residual, a separate fp16 rounding), broadcast of the slice into
+    every rank's result buffer (multimem.st through the NVSwitch when a multicast mapping exists), handshake.
+    Bit-identical on all ranks and equal to oracle.mixq_oracle.tp_exchange (rank-order fp32 sum)."""
+
+    fused = True
+    two_shot = True
+
+    def __init__(self, rows: int, cols: int, rank: int, world: int, group=None, device="cuda", multicast: bool = True):
+        from . import _lib
+        import torch.distributed as dist
+        if not (2 <= world <= 8):
+            raise ValueError("PushExchange needs 2..8 ranks on one node")
+        if cols % world or (cols // world) % 128:
+            raise ValueError("hidden size / world must be a multiple of 128 (a GEMM tile may not straddle two ranks' slices)")
+        self.lib, self._check = _lib.load(), _lib.check
+        self.rows, self.cols, self.rank, self.world, self.device = rows, cols, rank, world, device
+        self.ns = cols // world
+        nb = rows * cols * 2
+        self._nb = nb
+        local, ptrs, mc, self._keep, self._close = _symmetric_alloc(4 * nb + 256, rank, world, group, device)
+        if not multicast:
+            mc = 0
+        self.multicast = mc != 0
+        self._local, self._ptrs, self._mc = local, ptrs, mc
+        self._state = torch.zeros(2, dtype=torch.int32, device=device)      # epoch, done
+        self._fin = []
+        self._targets = []
+        slot = rows * self.ns * 2
+        for b in range(2):
+            a = _lib.ExchangeFinishArgs()
+            a.recv = local + b * nb
+            for r in range(world):
+                a.result[r] = ptrs[r] + 2 * nb + b * nb
+                a.flags[r] = ptrs[r] + 4 * nb
+            a.mc_result = (mc + 2 * nb + b * nb) if mc else 0
+            a.mc_flags = (mc + 4 * nb) if mc else 0
+            a.epoch = self._state.data_ptr()
+            a.done = self._state.data_ptr() + 4
+            a.M, a.N, a.world, a.rank = rows, cols, world, rank
+            self._fin.append(a)
+            self._targets.append([ptrs[j] + b * nb + rank * slot for j in range(world)])
+        self._views = [_DeviceBuffer(local + 2 * nb + b * nb, (rows, cols), "<f2") for b in range(2)]
+        self.results = [torch.as_tensor(v, device=device) for v in self._views]
+        self.buf = 0
+        torch.cuda.synchronize()
+        dist.barrier(group=group)       # nobody pushes or signals before everybody has mapped everything
+
+    def push_targets(self):
+        """(slot pointers, slice width) for MixLinear_GEMM.forward(..., push=) of THIS exchange."""
+        return self._targets[self.buf], self.ns
+
+    def reduce(self, residual, out: torch.Tensor = None) -> torch.Tensor:
+        a = self._fin[self.buf]
+        a.residual = 0 if residual is None else residual.data_ptr()
+        self._check(self.lib.mixq_exchange_finish(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                    "exchange_finish")
+        out = self.results[self.buf]
+        self.buf ^= 1
+        return out
+
+    def close(self):
+        torch.cuda.synchronize()
+        self.results, self._views = [], []
+        self._close()
+        self._close = lambda: None
+        self._keep = None
+
+
+def make_exchange(rows: int, cols: int, rank: int, world: int, group=None, device="cuda", kind: str = "auto"):
+    """kind: "push" (reduce-scatter fused into the GEMM epilogue + finish kernel; the default), "push-nomc" (the same without
+    the multicast broadcast), "multicast" (NVLS all-reduce kernel), "peer" (CUDA-IPC peer-memory all-reduce kernel),
+    "auto" = push."""
+    if kind in ("auto", "push", "push-nomc"):
+        try:
+            return PushExchange(rows, cols, rank, world, group=group, device=device, multicast=(kind != "push-nomc"))
+        except ValueError:          # slice width not a multiple of the GEMM tile: every rank falls back alike
+            if kind != "auto":
+                raise
+        kind = "multicast"
+    if kind in ("multicast", "auto"):
+        try:
+            return MulticastExchange(rows, cols, rank, world, group=group, device=device)
+        except Exception as e:      # every rank fails the same way: the decision is collective-consistent
+            if kind == "multicast":
+                raise
+            import sys
+            if rank == 0:
+                print(f"mixq: NVLS multicast exchange unavailable ({type(e).__name__}: {e}); using the peer-memory exchange", file=sys.stderr)
+    return PeerExchange(rows, cols, rank, world, group=group, device=device)

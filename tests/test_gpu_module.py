@@ -324,3 +324,54 @@ def test_attention_quant_fused_matches_separate_prologue(M, H, Hkv, D, L, n, bit
     if L:
         bits_equal(host(kc2), host(kc), "k cache append")
         bits_equal(host(vc2), host(vc), "v cache append")
+
+
+@pytest.mark.parametrize("bit", [8, 4])
+def test_auto_from_quantized_model_surface(bit, tmp_path):
+    """basic_quant_mix.py -> AutoForCausalLM.from_quantized -> benchflops.py with the reference's names (auto.py:42-53,
+    base.py:162-229, llama.py:9-22, attn.py:206-278): a checkpoint directory written in the reference's layout is loaded into
+    QuantAttentionFused / MixLlamaMLP / FasterTransformerRMSNorm modules; `model(input_ids, use_cache=True).logits` must agree
+    with the decode harness (itself pinned to the oracle above) through the discovery calls and in steady state."""
+    import json
+    from mixq_b200 import AutoForCausalLM, MixLibCache
+    from mixq_b200.attn import QuantAttentionFused
+    from mixq_b200.llama import CONFIGS, LlamaDecoder
+    cfg = CONFIGS["tiny"]
+    B = 24
+    m = LlamaDecoder(cfg, batch=B, bit=bit, seed=3, outlier_frac=0.02)
+    d = str(tmp_path / "ckpt")
+    m.save_quantized(d)
+    assert json.load(open(f"{d}/quant_config.json"))["w_bit"] == bit and json.load(open(f"{d}/config.json"))["model_type"] == "llama"
+    model = AutoForCausalLM.from_quantized(d, "", fuse_layers=True, mix=True, cache=MixLibCache(inputdim=B, bit=bit), batch_size=B)
+    assert isinstance(model.layers[0].self_attn, QuantAttentionFused) and model.layers[0].self_attn.cache_batch_size == B
+    tok = torch.randint(0, cfg.vocab, (B, 1), generator=torch.Generator().manual_seed(0)).cuda()
+    for call in range(4):
+        la = m.step(tok)
+        if call == 1:
+            m.discovered = True
+        out = model(tok, use_cache=True)              # benchflops.py:124: no past_key_values -> an empty KV cache every call
+        assert tuple(out.logits.shape) == (B, 1, cfg.vocab) and out[0] is out.logits
+        for L, Lm in zip(m.layers, model.layers):
+            bits_equal(host(L["W_pack"].ind), host(Lm.self_attn.W_pack.ind), f"call {call} W_pack outlier set")
+            bits_equal(host(L["down_proj"].ind), host(Lm.mlp.down_proj_.ind), f"call {call} down_proj outlier set")
+        rel_close(host(out.logits[:, 0]), host(la), f"call {call} logits", 2e-3)
+    # KV cache: three tokens one by one on the module-owned cache (own decode kernel) == the three tokens as one prefill (SDPA)
+    seq = torch.randint(0, cfg.vocab, (B, 3), generator=torch.Generator().manual_seed(1)).cuda()
+    big = AutoForCausalLM.from_quantized(d, "", fuse_layers=True, mix=True, cache=MixLibCache(inputdim=3 * B, bit=bit), batch_size=B)
+    for La, Lb in zip(model.layers, big.layers):      # the same discovered outlier state on both
+        for a, b in ((La.self_attn.W_pack, Lb.self_attn.W_pack), (La.self_attn.o_proj, Lb.self_attn.o_proj),
+                     (La.mlp.up_proj_, Lb.mlp.up_proj_), (La.mlp.gate_proj_, Lb.mlp.gate_proj_), (La.mlp.down_proj_, Lb.mlp.down_proj_)):
+            assert not a.add_outliers or a is La.mlp.gate_proj_
+            if a._n_ind:
+                b.weight_cache = a.weight_cache
+                b.ind = a.ind
+            b.add_outliers = a.add_outliers
+            b.forward_without_precondition_len = a.forward_without_precondition_len
+    out = model(seq[:, :1], use_cache=True)
+    for t in (1, 2):
+        out = model(seq[:, t:t + 1], use_cache=True, past_key_values=out.past_key_values)
+    assert model.layers[0].self_attn.start_pos == 3
+    pre = big(seq, use_cache=True)
+    rel_close(host(out.logits[:, -1]), host(pre.logits[:, -1]), "decode with KV cache vs prefill", 2e-2)
+    g = model.generate(seq[:, :1], max_new_tokens=3)
+    assert tuple(g.shape) == (B, 4)

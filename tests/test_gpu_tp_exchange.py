@@ -15,6 +15,9 @@ def test_peer_exchange_two_ranks():
         pytest.skip("needs 2 GPUs on one node (run under `gpurun --gpus 2`)")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                         "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "check_peer_exchange.py")],
-                       capture_output=True, text=True, timeout=600)
+                       capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "push exchange ok" in r.stdout and "push decoder ok" in r.stdout
+    assert "push-nomc exchange ok" in r.stdout
     assert "peer exchange ok" in r.stdout
+    assert "multicast exchange ok" in r.stdout or "multicast exchange unavailable" in r.stdout
