@@ -37,6 +37,9 @@ def parse():
     ap.add_argument("--bit", type=int, default=8, choices=[4, 8])
     ap.add_argument("--layers", type=int, default=None, help="debug: fewer layers (the number is reported, never default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kv-len", type=int, default=-1,
+                    help="KV-cache variant of the metric: every sequence already holds this many tokens (-1: the largest power of "
+                         "two minus one, up to 1023, whose cache fits beside the model at N=1; 0: off)")
     return ap.parse_args()
 
 
@@ -483,6 +486,46 @@ def run_mixq(args):
         "per_linear": per_kind, "linear_share_of_step": tot_t * len(model.layers) / (ms * 1e-3 / args.steps),
     }
 
+    # ---- the KV-cache variant ("also report a variant with a real growing KV cache"): the same step with
+    # every sequence at position kv_len, attention over the cache through the library path the reference uses (flash-attn there,
+    # torch SDPA here).  benchflops itself never carries a cache (benchflops.py:124), so this is reported beside the headline.
+    kv_variant = None
+    if world == 1 and args.kv_len != 0:
+        per_tok = 2 * B * cfg.kv_heads * cfg.head_dim * 2 * len(model.layers)          # bytes per cached position
+        free = torch.cuda.mem_get_info()[0] - (8 << 30)
+        L = args.kv_len
+        if L < 0:
+            L = 1023
+            while L > 0 and (L + 1) * per_tok > free:
+                L = (L + 1) // 2 - 1
+        if L > 0 and (L + 1) * per_tok <= free:
+            model.graph = None
+            model.alloc_kv(L + 1)
+            model.kv_library_attention = True
+            for kc, vc in model.kv:
+                kc.normal_(0, 1)
+                vc.normal_(0, 1)
+            model.capture(tok0, past_len=L)
+            for i in range(2):
+                model.replay(dev_tokens[i])
+            torch.cuda.synchronize()
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ksteps = max(3, min(args.steps, 10))
+            k0.record()
+            for i in range(ksteps):
+                model.replay(dev_tokens[i % n_tok_sets])
+            k1.record()
+            torch.cuda.synchronize()
+            kms = k0.elapsed_time(k1) / ksteps
+            kv_variant = {"past_len": L, "tokens_per_s": B / (kms * 1e-3), "ms_per_step": kms, "steps": ksteps,
+                          "kv_cache_gb": (L + 1) * per_tok / 1e9,
+                          "note": "same step with every sequence at position past_len; attention over the KV cache = torch SDPA "
+                                  "(library, as the reference's flash-attn); HBM floor for reading the cache once: "
+                                  f"{(L + 1) * per_tok / (pk['hbm_gbs'] * 1e9) * 1e3:.2f} ms"}
+            model.graph = None
+            model.kv = None
+            model.kv_library_attention = False
+            torch.cuda.empty_cache()
     exchange_us = None
     if world > 1 and model.xchg is not None:
         exchange_us = time_exchanges(model, 2 * len(model.layers))
@@ -511,6 +554,7 @@ def run_mixq(args):
                     "d2h_bytes_per_step": B * 8, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,
             "tp_parity": tp_parity,
+            "kv_variant": kv_variant,
             "step_breakdown_us": {"linear_us": tot_t * len(model.layers) * 1e6,
                                   "exchange_us": None if exchange_us is None else exchange_us * 2 * len(model.layers),
                                   "per_exchange_us": exchange_us, "step_us": step_s * 1e6},

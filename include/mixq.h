@@ -62,6 +62,15 @@ int mixq_plan_linear(int M, int N, int K, int bit, int n_ind, int swiglu_pair, i
  * prefetch constants (the quantised weights) while the previous kernel drains; each kernel waits for its predecessors
  * (griddepcontrol.wait) before touching any activation tensor.  Results are identical either way. */
 int mixq_set_pdl(int on);
+/* How the launches that contain a grid barrier (mixq_linear_fused with its activation prologue) guarantee that all their CTAs
+ * are resident at once (environment MIXQ_GRID_BARRIER = pdl | coop | split):
+ *   0 "pdl"   default: programmatic dependent launch, one CTA per SM; co-residency holds because the process owns the GPU
+ *             (the previous kernel's CTAs leave without waiting for anybody).  The library checks with
+ *             cudaOccupancyMaxActiveClusters that the grid fits the device and refuses the launch otherwise.
+ *   1 "coop"  cudaLaunchAttributeCooperative on those launches (no PDL overlap for them): the driver enforces co-residency.
+ *   2 "split" two launches — activation prologue (row quantiser), then the GEMM with skip_prologue — and no grid barrier:
+ *             for processes that share the GPU with other streams, MPS clients or profilers.  Results are bit-identical. */
+int mixq_set_grid_barrier_mode(int mode);
 
 /* Tuning aid: device buffer of 148*8 uint64 that every subsequent mixq_linear_fused / GEMM launch fills with
  * %globaltimer stamps per CTA (start, prologue done, grid barrier passed, first MMA, last MMA, epilogue done).
@@ -184,6 +193,10 @@ typedef struct mixq_linear_args {
    * (% 256 for M <= 128).  mixq_exchange_finish then reduces and broadcasts.  peer_cols = 0: off. */
   void* y_peer[8];
   int peer_cols;
+  /* one-shot variant for small worlds: peer_bcast = number of destinations > 0 (peer_cols = 0): every tile is stored, whole, into
+   * each of y_peer[0 .. peer_bcast) (fp16 [M,N] receive slots, one per rank incl. this one); mixq_exchange_finish(one_shot = 1)
+   * then reduces all of them locally with a single handshake. */
+  int peer_bcast;
 } mixq_linear_args;
 
 int mixq_linear_fused(const mixq_linear_args* args /* host */, void* stream);
@@ -217,6 +230,11 @@ int mixq_quik_quantize(const void* x, const int64_t* int_indices, int n_int, con
  * x_scale = meta row 0 and outl = this addend) completes y = acc * scale[m] * weights_scales[n] + addend. */
 int mixq_quik_addend(const void* meta, const void* reduced_w, const void* fp_result, int ld_fp, void* out, int M, int N,
                      int bits, void* stream);
+
+/* Tuning aid: `iters` flag round trips between two ranks inside ONE launch (rank 0 writes rank 1's word, rank 1 answers);
+ * *out_ns (device uint64) = elapsed nanoseconds.  mine / peer: this rank's word and the other rank's word as mapped here;
+ * mc: multicast address of the word (then both sides use multimem.red) or NULL. */
+int mixq_debug_pingpong(void* mine, void* peer, void* mc, int iters, int rank, void* out_ns, void* stream);
 
 /* elementwise gate *= up (mlp.py:64) kept for the decode harness */
 int mixq_mul_inplace(void* a, const void* b, long long n, void* stream);
@@ -279,6 +297,7 @@ int mixq_allreduce_multicast(const mixq_mc_allreduce_args* a, void* stream);
  * buffer (multimem.st through the switch when mc_result is set, else one store per peer), and shakes hands again.  Per rank
  * 2 (world-1)/world n fp16 cross NVLink instead of (world-1) n, and only the small second half is exposed.
  *   recv      : local fp16 [world][M, N/world] receive slots of THIS exchange (slot s = rank s's partial of my slice)
+ *               (one_shot: [world][M, N], every rank's full partial)
  *   result[r] : rank r's result buffer fp16 [M, N] of this exchange as mapped here (own rank: the local pointer)
  *   flags[r]  : rank r's two zero-initialised uint32 handshake counters as mapped here; mc_flags / mc_result: multicast
  *               addresses of the same buffers, or NULL
@@ -293,6 +312,8 @@ typedef struct mixq_exchange_finish_args {
   void* done;              /* local uint32, zero-initialised */
   const void* residual;    /* local fp16 [M, N] or NULL */
   int M, N, world, rank;
+  int one_shot;            /* 1: recv = [world][M, N] FULL partials (peer_bcast push): reduce everything locally, one handshake,
+                            *    result[rank] only (no broadcast, result / mc_result of the peers unused) */
 } mixq_exchange_finish_args;
 int mixq_exchange_finish(const mixq_exchange_finish_args* a, void* stream);
 

@@ -55,6 +55,7 @@ class LinearArgs(C.Structure):
         ("tile_n", C.c_int),
         ("y_peer", C.c_void_p * 8),
         ("peer_cols", C.c_int),
+        ("peer_bcast", C.c_int),
     ]
 
 
@@ -113,6 +114,7 @@ class ExchangeFinishArgs(C.Structure):
         ("N", C.c_int),
         ("world", C.c_int),
         ("rank", C.c_int),
+        ("one_shot", C.c_int),
     ]
 
 
@@ -144,6 +146,7 @@ SIGNATURES = {
     "mixq_rope_attention_decode_quant": [_vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _f, _vp, _i, _vp, _i, _vp, _vp, _i, _vp],
     "mixq_quik_quantize": [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
     "mixq_quik_addend": [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp],
+    "mixq_debug_pingpong": [_vp, _vp, _vp, _i, _i, _vp, _vp],
     "mixq_mul_inplace": [_vp, _vp, _ll, _vp],
     "mixq_peer_alloc": [C.c_ulonglong, C.POINTER(C.c_void_p)],
     "mixq_peer_free": [_vp],
@@ -156,6 +159,7 @@ SIGNATURES = {
     "mixq_set_peer_timeout_ms": [_ll],
     "mixq_set_tile_n": [_i],
     "mixq_set_pdl": [_i],
+    "mixq_set_grid_barrier_mode": [_i],
     "mixq_plan_linear": [_i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(LinearPlan)],
     "mixq_set_trace_buffer": [_vp],
     "mixq_version": [],

@@ -26,6 +26,18 @@ __device__ __forceinline__ __half* y_base(const LinearParams& p, int n, int& ld)
   return p.y;
 }
 
+// f(base, ld) for every destination of the tile that holds output column n.
+template <class F>
+__device__ __forceinline__ void for_each_ydest(const LinearParams& p, int n, F f) {
+  if (p.peer_bcast > 0) {
+    for (int d = 0; d < p.peer_bcast; ++d) f(p.y_peer[d], p.N);
+  } else {
+    int ld;
+    __half* b = y_base(p, n, ld);
+    f(b, ld);
+  }
+}
+
 // One 32-column slab of one accumulator row: TMEM -> registers -> dequant (+outliers, +bias, SiLU) -> global.
 // Every lane of the warp must call this (tcgen05.ld is warp-collective); row_ok masks the stores.
 template <bool HAS_O>
@@ -85,9 +97,8 @@ __device__ __forceinline__ void epilogue_chunk(const LinearParams& p, uint32_t t
         if (has_res) o2 = hadd2_via_f32(o2, *reinterpret_cast<const __half2*>(&rsw[j2]));
         ow[j2] = *reinterpret_cast<const uint32_t*>(&o2);
       }
-      int ldy;
-      __half* yb = y_base(p, n, ldy);
-      *reinterpret_cast<uint4*>(yb + static_cast<size_t>(row) * ldy + ng) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      const uint4 ov = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      for_each_ydest(p, n, [&](__half* yb, int ldy) { *reinterpret_cast<uint4*>(yb + static_cast<size_t>(row) * ldy + ng) = ov; });
     }
   }
 }
@@ -155,9 +166,8 @@ __device__ __forceinline__ void epilogue_span(const LinearParams& p, uint32_t t_
           if (has_res) o2 = hadd2_via_f32(o2, *reinterpret_cast<const __half2*>(&rsw[j2]));
           ow[j2] = *reinterpret_cast<const uint32_t*>(&o2);
         }
-        int ldy;
-        __half* yb = y_base(p, n0, ldy);
-        *reinterpret_cast<uint4*>(yb + static_cast<size_t>(row) * ldy + ng) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        const uint4 ov = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        for_each_ydest(p, n0, [&](__half* yb, int ldy) { *reinterpret_cast<uint4*>(yb + static_cast<size_t>(row) * ldy + ng) = ov; });
       }
     }
   }
@@ -349,6 +359,14 @@ __device__ __forceinline__ void epilogue_run_coalesced(const LinearParams& p, ui
       tmem_ld_wait();
       epilogue_group16<false, MODE, 0, 32>(p, acc, acc, xs, scale_sa + g * 32, row_sa, sw, (g & 3) * 2, row, row_ok, n0 + g * 16);
       epilogue_group16<false, MODE, 16, 32>(p, acc, acc, xs, scale_sa + (g + 1) * 32, row_sa, sw, ((g + 1) & 3) * 2, row, row_ok, n0 + (g + 1) * 16);
+    } else if (HAS_O && two && !(p.ablate & 8)) {
+      // with outliers too: both accumulators 32 columns per tcgen05.ld / wait (half the exposed TMEM round trips of a pass)
+      uint32_t acc[32], oacc[32];
+      tmem_ld_32x32(t_int + g * 16, acc);
+      tmem_ld_32x32(t_outl + g * 16, oacc);
+      tmem_ld_wait();
+      epilogue_group16<true, MODE, 0, 32>(p, acc, oacc, xs, scale_sa + g * 32, row_sa, sw, (g & 3) * 2, row, row_ok, n0 + g * 16);
+      epilogue_group16<true, MODE, 16, 32>(p, acc, oacc, xs, scale_sa + (g + 1) * 32, row_sa, sw, ((g + 1) & 3) * 2, row, row_ok, n0 + (g + 1) * 16);
     } else {
 #pragma unroll 1
       for (int h = 0; h < (two ? 2 : 1); ++h) {
@@ -363,9 +381,9 @@ __device__ __forceinline__ void epilogue_run_coalesced(const LinearParams& p, ui
     const int last = two ? g + 1 : g;
     if ((last & 3) == 3 || last == ngroups - 1) {   // block complete (or run finished): 64 columns out, coalesced
       __syncwarp();
-      int ldy;
-      __half* yb = y_base(p, n0, ldy);
-      epi_stage_out(stage_sa, yb, ldy, m_base, n0 + (g & ~3) * 16, ((last & 3) + 1) * 2, p.M, p.N, lane);
+      for_each_ydest(p, n0, [&](__half* yb, int ldy) {
+        epi_stage_out(stage_sa, yb, ldy, m_base, n0 + (g & ~3) * 16, ((last & 3) + 1) * 2, p.M, p.N, lane);
+      });
       __syncwarp();
     }
   }
@@ -374,74 +392,57 @@ __device__ __forceinline__ void epilogue_run_coalesced(const LinearParams& p, ui
 }  // namespace mixq
 
 // ================================================================ SwiGLU pair epilogue (2-CTA kernel, pair mode)
-// In pair mode CTA 0 of the pair stages gate_proj's weight rows and CTA 1 up_proj's rows for the SAME output columns, so
-// in every CTA the accumulator's first column half is gate and the second half is up: epilogue warp (q, 0) holds gate,
-// warp (q, 1) holds up for the same 32 rows.  The reference (fused/mlp.py:61-64) does
+// In pair mode CTA 0 of the pair stages gate_proj's weight rows and CTA 1 up_proj's rows for the SAME output columns, so in
+// every CTA each MMA column chunk holds gate columns in its first half and the matching up columns in its second half.  The
+// reference (fused/mlp.py:61-64) does
 //     up = up_proj(x);  gate = gate_proj.forward_without_preconditionFusedSilu(x);  gate *= up        (all fp16 tensors)
-// so y = fp16( fp16(silu(v_gate)) * fp16(v_up) ).  The gate warp publishes its fp16 values through its staging tile,
-// the up warp multiplies and stores; the two warps meet at a 64-thread named barrier twice per 64-column block.
+// so y = fp16( fp16(silu(v_gate)) * fp16(v_up) ).  Each epilogue warp takes every other 32-column block of the run and reads
+// BOTH accumulators for it, so gate and up meet in registers: no cross-warp exchange, no named barriers (the first version had
+// a gate warp publishing through shared memory to an up warp — 40 % of its time was the two barriers per block, ncu r02).
 namespace mixq {
 
-template <bool HAS_O, int ROLE>   // ROLE 0 = gate warp, 1 = up warp
-__device__ __forceinline__ void epilogue_run_swiglu(const LinearParams& p, uint32_t my_sa, uint32_t gate_sa, int bar_id,
-                                                    uint32_t t_int, uint32_t t_outl, int m_base, int n0, int ncols, float xs,
-                                                    uint32_t scale_sa, int lane) {
+template <bool HAS_O>
+__device__ __forceinline__ void epilogue_run_swiglu(const LinearParams& p, uint32_t my_sa, uint32_t t_g, uint32_t t_u, uint32_t t_og,
+                                                    uint32_t t_ou, int m_base, int n0, int ncols, float xs, uint32_t sc_g_sa,
+                                                    uint32_t sc_u_sa, int lane, int half) {
   const uint32_t sw = lane & 7;
   const uint32_t my_row = my_sa + lane * 128;
-  const uint32_t gate_row = gate_sa + lane * 128;
 #pragma unroll 1
-  for (int b = 0; b < ncols; b += 64) {
-    const int bc = (ncols - b < 64) ? (ncols - b) : 64;
+  for (int c0 = half * 32; c0 < ncols; c0 += 64) {
+    const int bc = (ncols - c0 < 32) ? (ncols - c0) : 32;     // 16 or 32 columns
 #pragma unroll 1
     for (int c = 0; c < bc; c += 16) {
-      uint32_t acc[16];
-      uint32_t oacc[16];
-      tmem_ld_32x16(t_int + b + c, acc);
-      if (HAS_O) tmem_ld_32x16(t_outl + b + c, oacc);
+      uint32_t g[16], u[16], og[16], ou[16];
+      tmem_ld_32x16(t_g + c0 + c, g);
+      tmem_ld_32x16(t_u + c0 + c, u);
+      if (HAS_O) {
+        tmem_ld_32x16(t_og + c0 + c, og);
+        tmem_ld_32x16(t_ou + c0 + c, ou);
+      }
       tmem_ld_wait();
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        const uint4 wsu = lds128(scale_sa + (b + c + g * 8) * 2);
-        const uint32_t wsw[4] = {wsu.x, wsu.y, wsu.z, wsu.w};
+      for (int gi = 0; gi < 2; ++gi) {
+        const uint4 wg4 = lds128(sc_g_sa + (c0 + c + gi * 8) * 2);
+        const uint4 wu4 = lds128(sc_u_sa + (c0 + c + gi * 8) * 2);
+        const uint32_t wg[4] = {wg4.x, wg4.y, wg4.z, wg4.w};
+        const uint32_t wu[4] = {wu4.x, wu4.y, wu4.z, wu4.w};
         uint32_t ow[4];
 #pragma unroll
         for (int j2 = 0; j2 < 4; ++j2) {
-          const int cc = g * 8 + j2 * 2;
-          float2 v = dequant2<HAS_O>(acc[cc], acc[cc + 1], oacc[cc], oacc[cc + 1], xs, wsw[j2]);
-          if (ROLE == 0) {
-            v.x = silu_f(v.x);
-            v.y = silu_f(v.y);
-          }
-          const __half2 o2 = __floats2half2_rn(v.x, v.y);
-          ow[j2] = *reinterpret_cast<const uint32_t*>(&o2);
+          const int cc = gi * 8 + j2 * 2;
+          float2 vg = dequant2<HAS_O>(g[cc], g[cc + 1], og[cc], og[cc + 1], xs, wg[j2]);
+          const float2 vu = dequant2<HAS_O>(u[cc], u[cc + 1], ou[cc], ou[cc + 1], xs, wu[j2]);
+          vg.x = silu_f(vg.x);
+          vg.y = silu_f(vg.y);
+          const __half2 pr = __hmul2(__floats2half2_rn(vg.x, vg.y), __floats2half2_rn(vu.x, vu.y));
+          ow[j2] = *reinterpret_cast<const uint32_t*>(&pr);
         }
-        sts128(my_row + ((((c >> 3) + g) ^ sw) << 4), make_uint4(ow[0], ow[1], ow[2], ow[3]));
+        sts128(my_row + ((static_cast<uint32_t>((c >> 3) + gi) ^ sw) << 4), make_uint4(ow[0], ow[1], ow[2], ow[3]));
       }
     }
-    named_bar_sync(bar_id, 64);            // gate tile published
-    if (ROLE == 1) {
-#pragma unroll 1
-      for (int ch = 0; ch < (bc >> 3); ++ch) {
-        const uint32_t off = (static_cast<uint32_t>(ch) ^ sw) << 4;
-        const uint4 gu = lds128(gate_row + off);
-        const uint4 uu = lds128(my_row + off);
-        const uint32_t gw[4] = {gu.x, gu.y, gu.z, gu.w};
-        const uint32_t uw[4] = {uu.x, uu.y, uu.z, uu.w};
-        uint32_t ow[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const __half2 pr = __hmul2(*reinterpret_cast<const __half2*>(&gw[j]), *reinterpret_cast<const __half2*>(&uw[j]));
-          ow[j] = *reinterpret_cast<const uint32_t*>(&pr);
-        }
-        sts128(my_row + off, make_uint4(ow[0], ow[1], ow[2], ow[3]));
-      }
-    }
-    named_bar_sync(bar_id, 64);            // gate tile consumed: its warp may overwrite it
-    if (ROLE == 1) {
-      __syncwarp();
-      epi_stage_out(my_sa, p.y, p.N, m_base, n0 + b, bc >> 3, p.M, p.N, lane);
-      __syncwarp();
-    }
+    __syncwarp();
+    epi_stage_out(my_sa, p.y, p.N, m_base, n0 + c0, bc >> 3, p.M, p.N, lane);
+    __syncwarp();
   }
 }
 

@@ -31,6 +31,23 @@ std::atomic<unsigned long long> g_peer_timeout_ms{[] {
   return static_cast<unsigned long long>(v > 0 ? v : 120000);
 }()};
 
+// How the kernels with a grid barrier (fused activation prologue) are launched — mixq_set_grid_barrier_mode / MIXQ_GRID_BARRIER:
+//   0 "pdl"   (default) programmatic dependent launch, one CTA per SM: co-residency follows from the GPU being ours (every CTA of
+//             the previous kernel leaves without waiting for anybody).  For a process that owns the GPU (the benchmark, a serving
+//             worker with one stream of work).
+//   1 "coop"  cudaLaunchAttributeCooperative instead of PDL on those launches: the driver guarantees co-residency (and refuses the
+//             launch otherwise); the kernel boundary is no longer overlapped.
+//   2 "split" no grid barrier at all: the activation prologue runs as its own launch (rowquant_kernel), then the GEMM with
+//             skip_prologue — bit-identical results; for processes that share the GPU with other streams / MPS clients.
+std::atomic<int> g_barrier_mode{[] {
+  const char* e = getenv("MIXQ_GRID_BARRIER");
+  if (e == nullptr) return 0;
+  if (!strcmp(e, "coop")) return 1;
+  if (!strcmp(e, "split")) return 2;
+  return 0;
+}()};
+int barrier_mode() { return g_barrier_mode.load(std::memory_order_relaxed); }
+
 // Launch attributes shared by every kernel of the library.  A kernel with a grid barrier needs all of its CTAs
 // co-resident: a cooperative launch guarantees it; under PDL the grid is exactly one CTA per SM and the CTAs of the
 // previous kernel leave without waiting for anybody, so ours all become resident as those exit.
@@ -38,6 +55,7 @@ struct LaunchAttrs {
   cudaLaunchAttribute a[2];
   int n = 0;
   LaunchAttrs(bool cooperative, bool pdl) {
+    if (cooperative && barrier_mode() == 1) pdl = false;
     if (pdl) {
       a[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       a[n].val.programmaticStreamSerializationAllowed = 1;
@@ -184,12 +202,32 @@ int launch_linear(const LinearParams& p, int grid, bool cooperative, cudaStream_
 int launch_linear2(const LinearParams& p, int grid, bool cooperative, cudaStream_t st) {
   using Cfg = Gemm2Cfg;
   static thread_local int last_dev = -1;
+  static thread_local int max_clusters = 0;
   int dev = 0;
   MIXQ_CUDA(cudaGetDevice(&dev));
   if (dev != last_dev) {
     MIXQ_CUDA(cudaFuncSetAttribute(mixq_linear2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    // the grid barrier needs every CTA pair resident at once: ask the driver how many clusters of this kernel fit the device
+    cudaLaunchConfig_t q{};
+    q.gridDim = dim3(2);
+    q.blockDim = dim3(Cfg::NUM_THREADS);
+    q.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = 2;
+    qa[0].val.clusterDim.y = qa[0].val.clusterDim.z = 1;
+    q.attrs = qa;
+    q.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, mixq_linear2_kernel, &q) != cudaSuccess) {
+      (void)cudaGetLastError();
+      max_clusters = 0;   // unknown: do not block the launch on a failed query
+    }
     last_dev = dev;
   }
+  if (cooperative && max_clusters > 0 && grid / 2 > max_clusters)
+    return fail(MIXQ_EINVAL, "fused prologue: the device cannot hold all " + std::to_string(grid / 2) +
+                                 " CTA pairs of the grid barrier at once (max " + std::to_string(max_clusters) +
+                                 "); use mixq_set_grid_barrier_mode(2)");
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(Cfg::NUM_THREADS);
@@ -264,18 +302,19 @@ int plan_gemm(int M, int N, int K, int bit, int n_out, bool pair, int tile_req, 
   if (M < 1 || N < 8 || K < 16 || sms < 1) return fail(MIXQ_EINVAL, "M>=1, N>=8, K>=16 required");
   const bool w4 = bit == 4;
   // M > 128: CTA pairs (cta_group::2) own 256 x bn tiles — half the L2 -> SM bytes per MMA cycle (mixq_gemm2.cu)
-  bool two_cta = !w4 && M > 128 && sms >= 2;
+  bool two_cta = M > 128 && sms >= 2;   // W4 too: the epilogue warps unpack the nibbles during the mainloop (mixq_gemm2.cu)
   const int npairs = sms / 2;
-  if (pair && (!two_cta || N % 16 != 0)) return fail(MIXQ_EINVAL, "SwiGLU pair needs bit 8, M > 128 and N % 16 == 0");
+  if (pair && (!two_cta || N % 16 != 0)) return fail(MIXQ_EINVAL, "SwiGLU pair needs M > 128 and N % 16 == 0");
   // pair: a tile of width W holds W/2 gate columns (staged by CTA 0) and the SAME W/2 up columns (staged by CTA 1)
   int bn = two_cta ? pick_w2(tile_req, M, pair ? 2 * N : N, n_out, npairs) : pick_tile_n(tile_req, M, N, sms, n_out > 0);
   // narrow tiles are paced by the TMA op count (one op ~340 clocks of the SM's TMA unit whatever its size): two k-atoms
   // (256 bytes of K) per op and pipeline stage whenever at least three such stages fit
-  int k_atoms = (two_cta && K % 128 == 0 && K >= 256 && bn <= 256) ? 2 : 1;
+  int k_atoms = (two_cta && !w4 && K % 128 == 0 && K >= 256 && bn <= 256) ? 2 : 1;
   if (const char* e = getenv("MIXQ_DEBUG_KATOMS")) { const int v = atoi(e); if (v == 1) k_atoms = 1; }
   int stage2 = 0, nstages2 = 0;
   for (;;) {
-    stage2 = k_atoms * (Gemm2Cfg::A_BYTES + (bn / 2) * 128);
+    stage2 = k_atoms * (Gemm2Cfg::A_BYTES + (bn / 2) * 128) + (w4 ? (bn / 2) * 64 : 0);   // W4: + the packed landing rows
+    stage2 = (stage2 + 1023) / 1024 * 1024;
     if (const char* e = getenv("MIXQ_DEBUG_STAGE_BYTES")) { const int v = atoi(e); if (v >= stage2 && v % 1024 == 0) stage2 = v; }
     nstages2 = Gemm2Cfg::PIPE_BYTES / stage2;
     if (nstages2 > Gemm2Cfg::MAX_STAGES) nstages2 = Gemm2Cfg::MAX_STAGES;
@@ -302,7 +341,7 @@ int plan_gemm(int M, int N, int K, int bit, int n_out, bool pair, int tile_req, 
     g->tiles_per_unit = (g->tiles + npairs - 1) / npairs;
     bool single = false;
     if (const char* e = getenv("MIXQ_DEBUG_ABLATE")) single = (atoi(e) & 16) != 0;
-    g->tmem = plan_tmem(bn, n_out > 0, g->tiles_per_unit, single);
+    g->tmem = plan_tmem(bn, n_out > 0, w4 ? 1 : g->tiles_per_unit, single);
   } else {
     g->stage_bytes = w4 ? (bn == 256 ? GemmCfg<256, true>::STAGE_BYTES : GemmCfg<128, true>::STAGE_BYTES)
                         : (bn == 256 ? GemmCfg<256, false>::STAGE_BYTES : GemmCfg<128, false>::STAGE_BYTES);
@@ -346,6 +385,7 @@ struct GemmCall {
   uint32_t* grid_sync;
   void* const* y_peer = nullptr;   // tensor-parallel push (see mixq_linear_args.y_peer)
   int peer_cols = 0;
+  int peer_bcast = 0;
 };
 
 int run_gemm(const GemmCall& c, cudaStream_t st) {
@@ -375,6 +415,13 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
       if (c.y_peer[j] == nullptr || (reinterpret_cast<uintptr_t>(c.y_peer[j]) & 15) != 0)
         return fail(MIXQ_EINVAL, "tensor-parallel push: missing or misaligned y_peer pointer");
   }
+  if (c.peer_bcast > 0) {
+    if (c.peer_cols > 0 || c.peer_bcast > 8 || pair || c.bias || c.outl || c.residual || c.epilogue != EPI_DEQUANT_F16 || c.y_peer == nullptr)
+      return fail(MIXQ_EINVAL, "tensor-parallel broadcast push: 1..8 destinations, no bias / residual / addend / SwiGLU pair");
+    for (int j = 0; j < c.peer_bcast; ++j)
+      if (c.y_peer[j] == nullptr || (reinterpret_cast<uintptr_t>(c.y_peer[j]) & 15) != 0)
+        return fail(MIXQ_EINVAL, "tensor-parallel push: missing or misaligned y_peer pointer");
+  }
   const bool two_cta = gp.two_cta != 0;
   const int npairs = di.sms / 2;
   if (pair && (c.bias != nullptr || !c.scale_col_up || (c.n_out > 0 && !c.weight_cache_up) || c.epilogue != EPI_DEQUANT_F16 ||
@@ -394,7 +441,7 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
   }
   if (ka2) {
   } else if (w4) {
-    if (int r = make_map(&p.tm_b, c.q_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, c.K / 2, c.N, c.K / 2, 64, bn,
+    if (int r = make_map(&p.tm_b, c.q_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, c.K / 2, c.N, c.K / 2, 64, b_rows,
                          CU_TENSOR_MAP_SWIZZLE_NONE))
       return r;
   } else {
@@ -413,6 +460,10 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
   if (pair) {
     if (ka2) {
       if (int r = make_map_katoms(&p.tm_b2, c.q_w_up, c.K, c.N, b_rows, 2)) return r;
+    } else if (w4) {
+      if (int r = make_map(&p.tm_b2, c.q_w_up, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, c.K / 2, c.N, c.K / 2, 64, b_rows,
+                           CU_TENSOR_MAP_SWIZZLE_NONE))
+        return r;
     } else if (int r = make_map(&p.tm_b2, c.q_w_up, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, c.K, c.N, c.K, 128, b_rows,
                                 CU_TENSOR_MAP_SWIZZLE_128B)) {
       return r;
@@ -453,8 +504,10 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
   p.ld_res = c.ld_res;
   p.y = static_cast<__half*>(c.y);
   p.peer_cols = c.peer_cols;
+  p.peer_bcast = c.peer_bcast;
   if (c.peer_cols > 0)
     for (int j = 0; j < c.N / c.peer_cols; ++j) p.y_peer[j] = static_cast<__half*>(c.y_peer[j]);
+  for (int j = 0; j < c.peer_bcast; ++j) p.y_peer[j] = static_cast<__half*>(c.y_peer[j]);
   p.y_i32 = c.y_i32;
   p.M = c.M;
   p.N = c.N;
@@ -469,6 +522,7 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
   p.nstages = nstages2;
   p.stage_bytes = stage2;
   p.k_atoms = ka2 ? 2 : 1;
+  p.w4 = (w4 && two_cta) ? 1 : 0;
   if (const char* e = getenv("MIXQ_DEBUG_ABLATE")) p.ablate = atoi(e);
   p.q_w = static_cast<const uint8_t*>(c.q_w);
   p.q_w_pitch = w4 ? c.K / 2 : c.K;
@@ -612,6 +666,12 @@ int mixq_plan_linear(int M, int N, int K, int bit, int n_ind, int swiglu_pair, i
   out->pass_cols = g.tmem.pass_cols;
   out->pass_buffers = g.tmem.buffers;
   out->tmem_cols = g.two_cta ? g.tmem.columns(g.tile_w, n_ind > 0) : g.tmem.slots * g.tile_w * (n_ind > 0 ? 2 : 1);
+  return 0;
+}
+
+int mixq_set_grid_barrier_mode(int mode) {
+  if (mode < 0 || mode > 2) return fail(MIXQ_EINVAL, "grid barrier mode: 0 = pdl, 1 = cooperative, 2 = split (two launches)");
+  g_barrier_mode.store(mode, std::memory_order_relaxed);
   return 0;
 }
 
@@ -767,7 +827,8 @@ int mixq_compact_outlier_columns(uint8_t* col_over, int K, int32_t* ind_out, int
 
 int mixq_linear_fused(const mixq_linear_args* a, void* stream) {
   if (a == nullptr) return fail(MIXQ_EINVAL, "null args");
-  if (!a->q_weight || !a->scale_col || !a->q_x || !a->x_scale || (!a->y && a->peer_cols <= 0)) return fail(MIXQ_EINVAL, "null pointer");
+  if (!a->q_weight || !a->scale_col || !a->q_x || !a->x_scale || (!a->y && a->peer_cols <= 0 && a->peer_bcast <= 0))
+    return fail(MIXQ_EINVAL, "null pointer");
   if (a->n_ind > 0 && (!a->ind || !a->weight_cache || !a->act_outliers))
     return fail(MIXQ_EINVAL, "n_ind > 0 needs ind, weight_cache and act_outliers");
   RowQuantArgs rq{};
@@ -787,9 +848,15 @@ int mixq_linear_fused(const mixq_linear_args* a, void* stream) {
   c.q_w_up = a->q_weight_up; c.scale_col_up = a->scale_col_up; c.weight_cache_up = a->weight_cache_up;
   if (a->residual && a->ld_res < a->N) return fail(MIXQ_EINVAL, "ld_res < N");
   c.rq = a->skip_prologue ? nullptr : &rq;
+  if (c.rq != nullptr && barrier_mode() == 2) {
+    // "split": the activation prologue as its own launch, then the GEMM without a grid barrier (bit-identical)
+    if (int r = launch_rowquant(rq, static_cast<cudaStream_t>(stream))) return r;
+    c.rq = nullptr;
+  }
   c.grid_sync = a->grid_sync;
   c.y_peer = a->y_peer;
   c.peer_cols = a->peer_cols;
+  c.peer_bcast = a->peer_bcast;
   return run_gemm(c, static_cast<cudaStream_t>(stream));
 }
 
@@ -937,7 +1004,7 @@ int mixq_exchange_finish(const mixq_exchange_finish_args* a, void* stream) {
   XchgFinishArgs k{};
   k.recv = static_cast<const __half*>(a->recv);
   for (int p = 0; p < a->world; ++p) {
-    if (!a->flags[p] || (!a->mc_result && !a->result[p])) return fail(MIXQ_EINVAL, "missing peer pointer");
+    if (!a->flags[p] || (!a->mc_result && !a->result[p] && !(a->one_shot && p != a->rank))) return fail(MIXQ_EINVAL, "missing peer pointer");
     k.result[p] = static_cast<__half*>(a->result[p]);
     k.flags[p] = static_cast<uint32_t*>(a->flags[p]);
   }
@@ -950,10 +1017,14 @@ int mixq_exchange_finish(const mixq_exchange_finish_args* a, void* stream) {
   k.N = a->N;
   k.world = a->world;
   k.rank = a->rank;
+  k.one_shot = a->one_shot ? 1 : 0;
   k.timeout_ns = g_peer_timeout_ms.load(std::memory_order_relaxed) * 1000000ull;
+  static const int xf_ablate = [] { const char* e = getenv("MIXQ_DEBUG_XF"); return e ? atoi(e) : 0; }();
+  k.ablate = xf_ablate;
+  k.trace = g_trace.load(std::memory_order_relaxed);
   DeviceInfo di;
   if (int r = device_info(&di)) return r;
-  const int grid = grid_for(static_cast<long long>(a->M) * (a->N / a->world / 8), 256, di.sms, 2);
+  const int grid = grid_for(static_cast<long long>(a->M) * (a->N / (a->one_shot ? 1 : a->world) / 8), 256, di.sms, 2);
   MIXQ_CUDA(launch_small(exchange_finish_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), k));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
@@ -985,6 +1056,14 @@ int mixq_quik_addend(const void* meta, const void* reduced_w, const void* fp_res
                          static_cast<const __half*>(reduced_w), static_cast<const __half*>(fp_result), ld_fp,
                          static_cast<__half*>(out), M, N, bits));
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int mixq_debug_pingpong(void* mine, void* peer, void* mc, int iters, int rank, void* out_ns, void* stream) {
+  pingpong_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<uint32_t*>(mine), static_cast<uint32_t*>(peer),
+                                                                    static_cast<uint32_t*>(mc), iters, rank,
+                                                                    static_cast<unsigned long long*>(out_ns));
+  MIXQ_CUDA(cudaGetLastError());
   return 0;
 }
 

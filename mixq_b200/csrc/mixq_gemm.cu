@@ -251,8 +251,8 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
               uint32_t o[8];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const uint32_t lo = __vsub4((w[j] & 0x0F0F0F0Fu) ^ 0x08080808u, 0x08080808u);
-                const uint32_t hi = __vsub4(((w[j] >> 4) & 0x0F0F0F0Fu) ^ 0x08080808u, 0x08080808u);
+                const uint32_t lo = nib_lo_s8x4(w[j]);
+                const uint32_t hi = nib_hi_s8x4(w[j]);
                 o[2 * j] = __byte_perm(lo, hi, 0x5140);
                 o[2 * j + 1] = __byte_perm(lo, hi, 0x7362);
               }
@@ -270,7 +270,6 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
     }
   }
 
-  if (p.peer_cols > 0) __threadfence_system();   // tensor-parallel push: peer stores performed before the CTA retires
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {

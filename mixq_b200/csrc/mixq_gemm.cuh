@@ -30,6 +30,8 @@ struct LinearParams {
   // y_peer[j][row * peer_cols + (n - j * peer_cols)] — peer memory over NVLink for j != rank — instead of y[row * N + n]
   __half* y_peer[8];
   int peer_cols;
+  int peer_bcast;      // > 0: every tile goes, whole, to each of y_peer[0 .. peer_bcast) (fp16 [M,N] receive slots): the one-shot
+                       // exchange for small worlds — no second phase, (world - 1) * M * N fp16 over NVLink per rank
   int32_t* y_i32;
   int M, N, K;
   int n_out;           // outlier columns multiplied on the tensor cores (0 = none)
@@ -42,6 +44,8 @@ struct LinearParams {
   int stage_bytes;     // 2-CTA kernel: bytes between consecutive stages (>= k_atoms * (16 KB + W/2 * 128), multiple of 1024)
   int ablate;          // tuning aid (MIXQ_DEBUG_ABLATE; results are garbage): 1 = no MMAs, 2 = no activation loads, 4 = no weight loads, 8 = 16-column epilogue reads, 16 = single outlier pass buffer (8 and 16 keep results exact)
   int k_atoms;         // 2-CTA kernel: 128-byte k-atoms per pipeline stage and TMA op (1, or 2 with 3-D tm_a / tm_b / tm_b2)
+  int w4;              // 2-CTA kernel: weights are packed nibbles (tm_b / tm_b2: uint8 [N, K/2], box 64 B x W/2 rows, no swizzle);
+                       // the epilogue warps unpack each stage's 64-byte rows into the SWIZZLE_128B int8 tile during the mainloop
   const uint8_t* q_w;  // raw weight pointer + row pitch in bytes (L2 prefetch of the weight stream)
   long long q_w_pitch;
   unsigned long long* trace;  // optional [gridDim.x * 8] globaltimer stamps (mixq_set_trace_buffer), debug/tuning only

@@ -41,6 +41,10 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
   uint64_t* bar_tfull = bar_empty + MAXS;                                      // [0]: one phase per epilogue pass; per CTA
   uint64_t* bar_tempty = bar_tfull + 2;                                        // [0]: pass consumed by both CTAs' epilogues; leader
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+  // W4 only (they live in the slack of the RowQuantSmem block): the packed weight rows of a stage land on the CTA's OWN
+  // bar_bfull; bar_ready (leader) counts the unpack warps of both CTAs that have expanded the stage to int8
+  uint64_t* bar_bfull = reinterpret_cast<uint64_t*>(smem + Cfg::PIPE_BYTES + 256 + 384);
+  uint64_t* bar_ready = bar_bfull + MAXS;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -68,17 +72,22 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
   const int NT = (p.N + wout - 1) / wout;
   const int ntiles = MP * NT;
   const bool has_o = nko > 0;
-  const uint32_t atom_tx = 2u * static_cast<uint32_t>(Cfg::A_BYTES + bh * 128);    // both CTAs' bytes land on one barrier
+  const bool w4 = p.w4 != 0;
+  // bytes per k-atom landing on the leader's full barrier: both CTAs' activations and (W8) weights; W4 weights land on bar_bfull
+  const uint32_t atom_tx = w4 ? 2u * static_cast<uint32_t>(Cfg::A_BYTES) : 2u * static_cast<uint32_t>(Cfg::A_BYTES + bh * 128);
+  const uint32_t atom_tx_o = 2u * static_cast<uint32_t>(Cfg::A_BYTES + bh * 128);   // fp16 outlier k-blocks: never packed
   const uint32_t b_atom = static_cast<uint32_t>(bh) * 128u;                         // bytes between the k-atoms of a weight stage
   // TMEM plan (plan_tmem, mixq_gemm.cuh).  Passes are numbered globally (G = tile * P + c): pass G uses barrier pair /
   // buffer G % NB in phase (G / NB) & 1.
   const int my_tiles_geo = (pair < ntiles) ? (ntiles - 1 - pair) / npairs + 1 : 0;
-  const TmemPlan tp = plan_tmem(W, has_o, my_tiles_geo, (p.ablate & 16) != 0);   // (tuning knob 16: one big pass buffer)
+  // W4: the epilogue warps unpack during the mainloop, so tiles do not overlap: one accumulator slot
+  const TmemPlan tp = plan_tmem(W, has_o, w4 ? 1 : my_tiles_geo, (p.ablate & 16) != 0);   // (tuning knob 16: one big pass buffer)
   const int SLOTS = tp.slots, P = tp.passes, R = tp.pass_cols, NB = tp.buffers;
   const uint32_t outl_col0 = static_cast<uint32_t>(SLOTS * W);   // first TMEM column of the outlier buffers
 
   auto stage_a = [&](int s) { return smem + static_cast<size_t>(s) * stage_bytes; };
   auto stage_b = [&](int s) { return smem + static_cast<size_t>(s) * stage_bytes + static_cast<size_t>(KA) * Cfg::A_BYTES; };
+  auto stage_bp = [&](int s) { return stage_b(s) + static_cast<size_t>(bh) * 128; };   // W4: packed rows (64 B each), KA == 1
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tm_a);
@@ -93,6 +102,10 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
     for (int s = 0; s < MAXS; ++s) {
       mbar_init(&bar_full[s], 1);
       mbar_init(&bar_empty[s], 1);
+      if (w4) {
+        mbar_init(&bar_bfull[s], 1);
+        mbar_init(&bar_ready[s], 2 * Cfg::EPI_WARPS);   // one arrival per unpack warp of both CTAs
+      }
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bar_tfull[s], 1);
@@ -135,7 +148,14 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
         arm = false;
       }
       if (arm && leader) mbar_arrive_expect_tx(&bar_full[s], atom_tx * static_cast<uint32_t>(KA));
-      if (KA == 1) {
+      if (w4) {   // packed nibbles: 64 bytes of a weight row per k-atom, onto this CTA's own barrier
+        const int k0 = kb * 128;
+        if (do_wgt) {
+          if (arm) mbar_arrive_expect_tx(&bar_bfull[s], static_cast<uint32_t>(bh) * 64u);
+          tma_load_2d_2cta(tmb, smem_u32(&bar_bfull[s]), stage_bp(s), k0 >> 1, n0, kEvictFirst);
+        }
+        if (do_act) tma_load_2d_2cta(&p.tm_a, full_leader, stage_a(s), k0, m0, kEvictLast);
+      } else if (KA == 1) {
         const int k0 = kb * 128;
         if (do_wgt) tma_load_2d_2cta(tmb, full_leader, stage_b(s), k0, n0, kEvictFirst);
         if (do_act) tma_load_2d_2cta(&p.tm_a, full_leader, stage_a(s), k0, m0, kEvictLast);
@@ -144,7 +164,8 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
         if (do_act) tma_load_3d_2cta(&p.tm_a, full_leader, stage_a(s), 0, m0, kb * KA, kEvictLast);
       }
     } else {
-      if (arm && leader) mbar_arrive_expect_tx(&bar_full[s], atom_tx);
+      if (arm && leader) mbar_arrive_expect_tx(&bar_full[s], atom_tx_o);
+      if (w4 && do_wgt && arm) mbar_arrive(&bar_bfull[s]);   // nothing packed in an outlier block: the stage's W4 barriers just tick
       const int ko = (kb - nk) * 64;
       if (do_wgt) tma_load_2d_2cta(tmob, full_leader, stage_b(s), ko, n0, kEvictFirst);
       if (do_act) tma_load_2d_2cta(&p.tm_oa, full_leader, stage_a(s), ko, m0, kEvictLast);
@@ -236,6 +257,7 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
         const uint32_t d1 = tmem_base + static_cast<uint32_t>((SLOTS == 2 ? (i & 1) : 0) * W), d2 = d1 + static_cast<uint32_t>(n1);
         for (int kb = 0; kb < nk; ++kb) {
           mbar_wait(&bar_full[s], ph, 4, s);
+          if (w4) mbar_wait(&bar_ready[s], ph, 14, s);   // both CTAs' weight halves are unpacked
           tc_fence_after();
           const uint32_t lo_a = lo_a0 + static_cast<uint32_t>(s) * stage_step;
           const uint32_t lo_b = lo_b0 + static_cast<uint32_t>(s) * stage_step;
@@ -267,6 +289,7 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
             uint32_t pho = ph_o;
             if (so >= nstages) { so -= nstages; pho ^= 1; }
             mbar_wait(&bar_full[so], pho, 4, so);
+            if (w4) mbar_wait(&bar_ready[so], pho, 14, so);
           }
           tc_fence_after();
           for (int c = 0; c < P; ++c) {
@@ -309,27 +332,63 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
     const int half = (warp - 4) >> 2;       // which half of the tile's output columns
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t stage_sa = smem_u32(smem + Cfg::PIPE_BYTES + 256 + 512 + (warp - 4) * kEpiStageBytes);
-    const uint32_t gate_sa = smem_u32(smem + Cfg::PIPE_BYTES + 256 + 512 + q * kEpiStageBytes);   // staging tile of warp (q, half 0)
     __half* s_scale = reinterpret_cast<__half*>(smem + Cfg::PIPE_BYTES + 256 + 512 + Cfg::EPI_WARPS * kEpiStageBytes) + half * 256;
     const uint32_t scale_sa = smem_u32(s_scale);
+    const uint32_t scale_g_sa = scale_sa - static_cast<uint32_t>(half) * 512u, scale_u_sa = scale_g_sa + 512u;   // pair: gate | up scales
     const uint32_t tempty0 = mapa_u32(smem_u32(&bar_tempty[0]), 0), tempty1 = mapa_u32(smem_u32(&bar_tempty[1]), 0);
     const int h1 = n1 >> 1;                 // output columns of this half that live in MMA chunk 1
     const int mode = (p.outl != nullptr || p.bias != nullptr || p.act == 1) ? 2 : (p.residual != nullptr ? 1 : 0);
+    // W4: these eight warps are idle while a tile's int8 k-blocks stream (one accumulator slot, no epilogue to overlap), so they
+    // expand the packed nibbles: each stage's 64-byte weight rows (low nibble = even k, linear.py:14-18) become the
+    // SWIZZLE_128B int8 tile the UMMA descriptor expects (row r: 16-byte chunk c at c ^ (r & 7)).  256 threads walk the
+    // (row, 16-byte packed chunk) pairs of the stage; the leader's bar_ready collects both CTAs' warps.
+    int us = 0;
+    uint32_t uph = 0;
+    const uint32_t ready_leader = mapa_u32(smem_u32(&bar_ready[0]), 0);
     for (int i = 0; i < my_tiles; ++i) {
+      if (w4) {
+        const int ut = threadIdx.x - 128;          // 0 .. 255
+        for (int kb = 0; kb < nkt; ++kb) {          // (fp16 outlier k-blocks: nothing to unpack, the barriers just tick)
+          mbar_wait(&bar_bfull[us], uph, 15, us);
+          const uint8_t* src_base = stage_bp(us);
+          uint8_t* dst_base = stage_b(us);
+          for (int it = ut; it < (kb < nk ? bh * 4 : 0); it += 256) {
+            const int r = it >> 2, v = it & 3;
+            const uint4 pk = *reinterpret_cast<const uint4*>(src_base + r * 64 + v * 16);
+            const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+            uint32_t o[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t lo = nib_lo_s8x4(w[j]);
+              const uint32_t hi = nib_hi_s8x4(w[j]);
+              o[2 * j] = __byte_perm(lo, hi, 0x5140);
+              o[2 * j + 1] = __byte_perm(lo, hi, 0x7362);
+            }
+            uint8_t* drow = dst_base + r * 128;
+            *reinterpret_cast<uint4*>(drow + (((2 * v) ^ (r & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(drow + (((2 * v + 1) ^ (r & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+          fence_proxy_async_smem();                 // generic-proxy smem writes -> visible to the pair's tcgen05.mma (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_release(ready_leader + static_cast<uint32_t>(us) * 8u);
+          if (++us == nstages) { us = 0; uph ^= 1; }
+        }
+      }
       const int tile = pair + i * npairs;
       const int m0 = (tile % MP) * 256 + static_cast<int>(rank) * 128 + q * 32;   // first row of this warp
       const int n0 = pairm ? (tile / MP) * bh : (tile / MP) * W + half * bh;     // first output column of this warp
       const int row = m0 + lane;
       float xs = 0.f;
       if (p.epilogue == EPI_DEQUANT_F16 && row < p.M) xs = __half2float(p.x_scale[row]);
-      // scale_col of this half -> smem, once per tile, by the first of the four warps that share it
-      named_bar_sync(13 + half, 128);
+      // scale_col of this half -> smem, once per tile, by the first of the four warps that share it (SwiGLU pair: every warp
+      // reads both halves' scales, so all eight warps meet)
+      named_bar_sync(pairm ? 13 : 13 + half, pairm ? 256 : 128);
       if (q == 0 && p.epilogue == EPI_DEQUANT_F16)
         for (int j = lane * 8; j < bh; j += 256)
           *reinterpret_cast<uint4*>(s_scale + j) =
               (n0 + j < p.N) ? __ldg(reinterpret_cast<const uint4*>(((pairm && half == 1) ? p.scale_col2 : p.scale_col) + n0 + j))
                              : make_uint4(0, 0, 0, 0);
-      named_bar_sync(13 + half, 128);
+      named_bar_sync(pairm ? 13 : 13 + half, pairm ? 256 : 128);
 
       const uint32_t int_col0 = static_cast<uint32_t>((SLOTS == 2 ? (i & 1) : 0) * W);   // this tile's int32 accumulator slot
       for (int c = 0; c < P; ++c) {
@@ -361,13 +420,13 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
           const uint32_t t_o = t_outl + (a - x0);
           const uint32_t sc = scale_sa + a * 2;
           if (pairm) {
-            if (half == 0) {
-              if (has_o) epilogue_run_swiglu<true, 0>(p, stage_sa, gate_sa, 1 + q, t_int, t_o, m0, n0 + a, b - a, xs, sc, lane);
-              else epilogue_run_swiglu<false, 0>(p, stage_sa, gate_sa, 1 + q, t_int, 0u, m0, n0 + a, b - a, xs, sc, lane);
-            } else {
-              if (has_o) epilogue_run_swiglu<true, 1>(p, stage_sa, gate_sa, 1 + q, t_int, t_o, m0, n0 + a, b - a, xs, sc, lane);
-              else epilogue_run_swiglu<false, 1>(p, stage_sa, gate_sa, 1 + q, t_int, 0u, m0, n0 + a, b - a, xs, sc, lane);
-            }
+            // output columns [a, b) of the tile: gate accumulator | up accumulator (| their outlier accumulators of this pass)
+            const uint32_t t_g = lane_base + int_col0 + static_cast<uint32_t>(part == 0 ? a : n1 + (a - h1));
+            const uint32_t t_u = lane_base + int_col0 + static_cast<uint32_t>(part == 0 ? h1 + a : n1 + (n2 >> 1) + (a - h1));
+            const uint32_t t_og = lane_base + outl_col0 + static_cast<uint32_t>(buf * R + (a - x0));
+            const uint32_t t_ou = t_og + static_cast<uint32_t>(nc >> 1);
+            if (has_o) epilogue_run_swiglu<true>(p, stage_sa, t_g, t_u, t_og, t_ou, m0, n0 + a, b - a, xs, scale_g_sa + a * 2, scale_u_sa + a * 2, lane, half);
+            else epilogue_run_swiglu<false>(p, stage_sa, t_g, t_u, 0u, 0u, m0, n0 + a, b - a, xs, scale_g_sa + a * 2, scale_u_sa + a * 2, lane, half);
           } else if (p.epilogue == EPI_DEQUANT_F16) {
             if (has_o) {
               if (mode == 0) epilogue_run_coalesced<true, 0>(p, stage_sa, t_int, t_o, m0, n0 + a, b - a, xs, sc, lane);
@@ -390,9 +449,6 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
     }
     if (trace && warp == 4 && lane == 0) trace[5] = globaltimer_ns();
   }
-  // tensor-parallel push: this thread's stores into the peers' receive slots are performed system-wide before the CTA retires
-  if (p.peer_cols > 0) __threadfence_system();
-
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();      // nobody leaves while the peer may still read our smem / signal our barriers

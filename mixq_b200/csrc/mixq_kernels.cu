@@ -512,20 +512,26 @@ __global__ void __launch_bounds__(256) allreduce_multicast_kernel(McAllReduceArg
 }
 
 // ---------------------------------------------------------------- fused exchange, second half (see XchgFinishArgs)
-// Handshake counters: word `phase` of EVERY rank is incremented once per exchange by every rank (one multimem.red through the
-// switch, or one red.release.sys per peer); a rank proceeds when its own word reaches world * exchange count.
-__device__ __forceinline__ void xf_signal(const XchgFinishArgs& a, int phase) {
-  __threadfence_system();
+// Handshake counters: word `phase` of EVERY rank is incremented by every rank (one multimem.red through the switch, or one red
+// per peer); a rank proceeds when its own word reaches the expected count.  Measured on NVSwitch (tools/bench_exchange.py,
+// profiles/r02_exchange_anatomy_*): a flag takes 2.8 us one way, a system-scope fence 3 us on an idle SM and 6-9 us when stores
+// to peers are in flight — so the kernel issues as few of them in series as the protocol allows:
+//   phase 0: ONE fence + red by block 0 ("the pushes of my GEMM — the previous kernel of the stream — are performed");
+//   phase 1: every block releases its own slice stores with one red (count = world * blocks per exchange), no block waits
+//            for another block of its own grid; block 0 alone waits for the grand total and closes the exchange.
+__device__ __forceinline__ void xf_red(const XchgFinishArgs& a, int phase, bool release) {
   if (a.mc_flags != nullptr) {
-    asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(a.mc_flags + phase), "r"(1u) : "memory");
+    if (release) asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(a.mc_flags + phase), "r"(1u) : "memory");
+    else asm volatile("multimem.red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(a.mc_flags + phase), "r"(1u) : "memory");
   } else {
-    for (int p = 0; p < a.world; ++p)
-      asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(a.flags[p] + phase), "r"(1u) : "memory");
+    for (int p = 0; p < a.world; ++p) {
+      if (release && p == 0) asm volatile("fence.acq_rel.sys;" ::: "memory");
+      asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(a.flags[p] + phase), "r"(1u) : "memory");
+    }
   }
 }
-__device__ __forceinline__ void xf_wait(const XchgFinishArgs& a, int phase, uint32_t e) {
+__device__ __forceinline__ void xf_wait(const XchgFinishArgs& a, int phase, uint32_t target) {
   const uint32_t* w = a.flags[a.rank] + phase;
-  const uint32_t target = e * static_cast<uint32_t>(a.world);
   const uint64_t t0 = globaltimer_ns();
   uint32_t v, spins = 0;
   do {
@@ -534,22 +540,53 @@ __device__ __forceinline__ void xf_wait(const XchgFinishArgs& a, int phase, uint
   } while (static_cast<int32_t>(v - target) < 0);
 }
 
+__global__ void pingpong_kernel(uint32_t* mine, uint32_t* peer, uint32_t* mc, int iters, int rank, unsigned long long* out_ns) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const uint64_t t0 = globaltimer_ns();
+  for (int i = 1; i <= iters; ++i) {
+    if (rank == 0) {
+      if (mc) asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc), "r"(1u) : "memory");
+      else asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer), "r"(static_cast<uint32_t>(i)) : "memory");
+    }
+    uint32_t v;
+    const uint32_t target = mc ? static_cast<uint32_t>(2 * i - (rank == 0 ? 0 : 1)) : static_cast<uint32_t>(i);
+    uint32_t spins = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if (++spins > 400000000u) return;
+    } while (static_cast<int32_t>(v - target) < 0);
+    if (rank != 0) {
+      if (mc) asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc), "r"(1u) : "memory");
+      else asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer), "r"(static_cast<uint32_t>(i)) : "memory");
+    }
+  }
+  *out_ns = globaltimer_ns() - t0;
+}
+
 __global__ void __launch_bounds__(256) exchange_finish_kernel(XchgFinishArgs a) {
   pdl_launch_dependents();
   pdl_wait();                                   // my GEMM (previous kernel of the stream) has pushed all of its tiles
   __shared__ uint32_t s_epoch;
+  const bool tr = a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  if (tr) a.trace[0] = globaltimer_ns();
   if (threadIdx.x == 0) {
     const uint32_t e = *reinterpret_cast<volatile uint32_t*>(a.epoch) + 1;
     s_epoch = e;
-    if (blockIdx.x == 0) xf_signal(a, 0);       // "my pushes of exchange e are complete"
-    xf_wait(a, 0, e);                           // ... and so are everybody's into my slots
+    if (!(a.ablate & 2)) {
+      if (blockIdx.x == 0) xf_red(a, 0, true);  // "my pushes of exchange e are performed" (release: cumulative over pdl_wait)
+      if (tr) a.trace[1] = globaltimer_ns();
+      xf_wait(a, 0, e * static_cast<uint32_t>(a.world));   // ... and so are everybody's into my slots
+    }
   }
   __syncthreads();
-  const int Ns = a.N / a.world;
+  if (tr) a.trace[2] = globaltimer_ns();
+  const bool one_shot = a.one_shot != 0;        // every rank holds every rank's FULL partial: reduce everything locally, no broadcast
+  const int Ns = one_shot ? a.N : a.N / a.world;
   const int vpr = Ns >> 3;                      // 16-byte vectors per slot row
   const long long nv = static_cast<long long>(a.M) * vpr;
   const size_t slot = static_cast<size_t>(a.M) * Ns;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
+  const size_t col0 = one_shot ? 0 : static_cast<size_t>(a.rank) * Ns;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < ((a.ablate & 4) ? 0 : nv);
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int row = static_cast<int>(i / vpr), c8 = static_cast<int>(i - static_cast<long long>(row) * vpr);
     float acc[8];
@@ -565,7 +602,7 @@ __global__ void __launch_bounds__(256) exchange_finish_kernel(XchgFinishArgs a) 
         acc[2 * j + 1] += f.y;
       }
     }
-    const size_t off = static_cast<size_t>(row) * a.N + static_cast<size_t>(a.rank) * Ns + static_cast<size_t>(c8) * 8;
+    const size_t off = static_cast<size_t>(row) * a.N + col0 + static_cast<size_t>(c8) * 8;
     H8 r, o;
     if (a.residual != nullptr) r.u = *reinterpret_cast<const uint4*>(a.residual + off);
 #pragma unroll
@@ -577,7 +614,9 @@ __global__ void __launch_bounds__(256) exchange_finish_kernel(XchgFinishArgs a) 
       }
       o.h2[j] = y2;
     }
-    if (a.mc_result != nullptr) {
+    if (one_shot) {
+      *reinterpret_cast<uint4*>(a.result[a.rank] + off) = o.u;
+    } else if (a.mc_result != nullptr) {
       asm volatile("multimem.st.relaxed.sys.global.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(a.mc_result + off), "r"(o.u.x), "r"(o.u.y),
                    "r"(o.u.z), "r"(o.u.w)
                    : "memory");
@@ -585,15 +624,26 @@ __global__ void __launch_bounds__(256) exchange_finish_kernel(XchgFinishArgs a) 
       for (int p = 0; p < a.world; ++p) *reinterpret_cast<uint4*>(a.result[p] + off) = o.u;
     }
   }
-  __syncthreads();
+  __syncthreads();                              // every thread's slice stores happen-before thread 0's release below
+  if (tr) a.trace[3] = globaltimer_ns();
   if (threadIdx.x == 0) {
-    __threadfence_system();
-    if (atomicAdd(a.done, 1u) == gridDim.x - 1) {   // last block out: every block's slice stores have been issued and fenced
-      xf_signal(a, 1);                               // "my slice of exchange e is in every result buffer"
-      xf_wait(a, 1, s_epoch);                        // ... and everybody else's is in mine
-      *a.done = 0;
+    const uint32_t e = s_epoch;
+    if (one_shot || (a.ablate & 3)) {
+      // nothing was sent to anybody: the exchange closes when every block of THIS grid has read the epoch
       __threadfence();
-      *reinterpret_cast<volatile uint32_t*>(a.epoch) = s_epoch;
+      if (atomicAdd(a.done, 1u) == gridDim.x - 1) {
+        *a.done = 0;
+        __threadfence();
+        *reinterpret_cast<volatile uint32_t*>(a.epoch) = e;
+      }
+    } else {
+      xf_red(a, 1, true);                       // "this block's part of my slice is in every result buffer"
+      if (tr) a.trace[4] = globaltimer_ns();
+      if (blockIdx.x == 0) {                    // every block of every rank has released: all slices are in MY result buffer,
+        xf_wait(a, 1, e * static_cast<uint32_t>(a.world) * gridDim.x);   // and every block of this grid is past its epoch read
+        if (tr) a.trace[7] = globaltimer_ns();
+        *reinterpret_cast<volatile uint32_t*>(a.epoch) = e;
+      }
     }
   }
 }

@@ -70,8 +70,13 @@ struct XchgFinishArgs {
   uint32_t* done;              // local: blocks finished in the current launch
   const __half* residual;      // local [M, N] or nullptr
   int M, N, world, rank;
+  int one_shot;                // 1: recv holds every rank's FULL partial [world][M, N] (broadcast push): reduce all of it, no second phase
   unsigned long long timeout_ns;
+  int ablate;                  // tuning aid (MIXQ_DEBUG_XF; results are garbage): 1 = no second handshake, 2 = no handshakes, 4 = no data
+  unsigned long long* trace;   // tuning aid: 8 globaltimer stamps of block 0 (mixq_set_trace_buffer) or nullptr
 };
 __global__ void exchange_finish_kernel(XchgFinishArgs a);
+// tuning aid: `iters` flag round trips between two ranks inside one launch; *out_ns = elapsed nanoseconds (rank 0)
+__global__ void pingpong_kernel(uint32_t* mine, uint32_t* peer, uint32_t* mc, int iters, int rank, unsigned long long* out_ns);
 
 }  // namespace mixq

@@ -256,6 +256,18 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- packed-nibble sign extension
+// Four two's-complement nibbles (the low / high nibbles of the four bytes of w) -> four int8 lanes: n | (n & 8 ? 0xF0 : 0).
+// ((w >> 3) & 0x01010101) * 0xF0 puts 0xF0 in the lanes whose nibble has its sign bit set (one bit per lane: no carries), so
+// each half costs two logic ops and one IMAD — the SIMD-in-a-word video instructions (__vsub4) are emulated on this
+// architecture and made the unpack the pace-setter of the W4 mainloop.
+__device__ __forceinline__ uint32_t nib_lo_s8x4(uint32_t w) {
+  return ((w >> 3) & 0x01010101u) * 0xF0u + (w & 0x0F0F0F0Fu);
+}
+__device__ __forceinline__ uint32_t nib_hi_s8x4(uint32_t w) {
+  return ((w >> 7) & 0x01010101u) * 0xF0u + ((w >> 4) & 0x0F0F0F0Fu);
+}
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
   uint32_t v;
@@ -310,6 +322,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) 
 // cluster-scope release would also wait for the warp's outstanding global stores of y (measured: ~1 us per arrive).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cta.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Cluster-scope release: everything this thread wrote (to ITS OWN shared memory, read next by the pair's tensor cores) is
+// ordered before the arrival.  Used by the nibble-unpack warps, which have no global stores in flight.
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),

@@ -294,9 +294,9 @@ class MixLinear_GEMM(nn.Module):
         a.y = _ptr(y)
         # tensor-parallel push: column slice j of y goes straight into rank j's receive slot (tp.PushExchange.push_targets())
         if push is None:
-            a.peer_cols = 0
+            a.peer_cols = a.peer_bcast = 0
         else:
-            ptrs, a.peer_cols = push
+            ptrs, a.peer_cols, a.peer_bcast = push
             for j, pj in enumerate(ptrs):
                 a.y_peer[j] = pj
         a.act = act

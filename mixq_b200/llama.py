@@ -144,8 +144,8 @@ class LlamaDecoder:
         self.norm_f = torch.ones(H, dtype=f16, device=device)
         self.lm_head = rand_w(cfg.vocab, H)   # fp16, never quantised (base.py:285-288 only walks decoder layers)
         self.discovered = False
-        # one launch for up_proj + gate_proj + SiLU + gate*up (needs the 2-CTA kernel: M > 128, bit 8)
-        self.fuse_swiglu = (bit == 8 and batch > 128)
+        # one launch for up_proj + gate_proj + SiLU + gate*up (needs the 2-CTA kernel: M > 128)
+        self.fuse_swiglu = batch > 128
         # attention + o_proj's activation prologue in one launch (MIXQ_FUSE_ATTN_QUANT=0: separate launches)
         self.fuse_attn_quant = os.environ.get("MIXQ_FUSE_ATTN_QUANT", "1") != "0"
         self.graph = None
@@ -192,6 +192,28 @@ class LlamaDecoder:
                                                        self._stream()), "rope_attention_decode")
         return out
 
+    def _attention_sdpa(self, qkv, past_len, layer_idx):
+        """Attention over a real KV cache through the LIBRARY path, as the reference does (flash-attn at fused/attn.py:256-258;
+        torch SDPA here): RoPE at position past_len (HF rotate_half), cache append, single-query attention over past_len + 1
+        keys.  Used for the KV-cache variant of the metric; attention math is outside the quantised hot path."""
+        cfg = self.cfg
+        M, H, Hkv, D = qkv.shape[0], self.h_loc, self.kv_loc, cfg.head_dim
+        kc, vc = self.kv[layer_idx]
+        x = qkv.view(M, H + 2 * Hkv, D)
+        q, k, v = x[:, :H], x[:, H:H + Hkv], x[:, H + Hkv:]
+        if past_len > 0:
+            inv = 1.0 / (cfg.rope_theta ** (torch.arange(0, D, 2, device=qkv.device, dtype=torch.float32) / D))
+            ang = past_len * inv
+            cos, sin = torch.cat((ang, ang)).cos(), torch.cat((ang, ang)).sin()
+            rot = lambda t: torch.cat((-t[..., D // 2:], t[..., :D // 2]), -1)
+            q = (q.float() * cos + rot(q.float()) * sin).half()
+            k = (k.float() * cos + rot(k.float()) * sin).half()
+        kc[:, :, past_len] = k
+        vc[:, :, past_len] = v
+        out = torch.nn.functional.scaled_dot_product_attention(q.unsqueeze(2), kc[:, :, :past_len + 1], vc[:, :, :past_len + 1],
+                                                               enable_gqa=(H != Hkv))
+        return out.reshape(M, H * D)
+
     def _attention_quant(self, qkv, lin, past_len=0, layer_idx=0):
         """Attention + the activation prologue of `lin` (o_proj) in ONE launch: the kernel owns whole token rows, so it
         gathers lin's outlier columns, takes the row abs-max and quantises its own output (linear.py:187-193 on the
@@ -234,7 +256,19 @@ class LlamaDecoder:
                 qkv = L["W_pack"].forward_norm_fused(h, L["ln1"], cfg.eps)
             else:
                 qkv = self._norm_then_linear(h, L["ln1"], L["W_pack"])
-            if steady and self.fuse_attn_quant:
+            if self.kv is not None and getattr(self, "kv_library_attention", False):
+                attn = self._attention_sdpa(qkv, past_len, li)
+                if tp and self.xchg is not None:
+                    if getattr(self.xchg, "fused", False):
+                        L["o_proj"](attn, None, True, push=self.xchg.push_targets())
+                    else:
+                        L["o_proj"](attn, None, True, out=self.xchg.next_partial())
+                    h = self.xchg.reduce(h)
+                elif tp:
+                    h = h + self._allreduce(L["o_proj"](attn, None, True))
+                else:
+                    h = L["o_proj"](attn, None, True, residual=h)
+            elif steady and self.fuse_attn_quant:
                 # attention quantises its own output rows for o_proj: o_proj has no activation prologue left
                 self._attention_quant(qkv, L["o_proj"], past_len, li)
                 M = qkv.shape[0]
@@ -311,7 +345,7 @@ class LlamaDecoder:
             torch.cuda.synchronize()
             torch.distributed.barrier(group=self.group)
 
-    def capture(self, tokens: torch.Tensor):
+    def capture(self, tokens: torch.Tensor, past_len: int = 0):
         """Capture the steady-state step into a CUDA graph (tokens are copied into a static buffer per replay)."""
         assert self.discovered, "run discover() first"
         self._rank_barrier()
@@ -320,13 +354,13 @@ class LlamaDecoder:
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(2):
-                self.step(self._static_tokens)
+                self.step(self._static_tokens, past_len)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self._rank_barrier()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self._static_logits = self.step(self._static_tokens)
+            self._static_logits = self.step(self._static_tokens, past_len)
         self._rank_barrier()
         return self.graph
 
@@ -411,7 +445,7 @@ class LlamaDecoder:
         self.norm_f = rest["model.norm.weight"].to(device)
         self.lm_head = rest["lm_head.weight"].to(device)
         self.discovered = False
-        self.fuse_swiglu = (self.bit == 8 and batch > 128)
+        self.fuse_swiglu = batch > 128
         self.fuse_attn_quant = os.environ.get("MIXQ_FUSE_ATTN_QUANT", "1") != "0"
         self.graph = self._static_tokens = self._static_logits = self.kv = None
         self.lib = _lib.load()

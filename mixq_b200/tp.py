@@ -283,49 +283,64 @@ class PushExchange:
     fused = True
     two_shot = True
 
-    def __init__(self, rows: int, cols: int, rank: int, world: int, group=None, device="cuda", multicast: bool = True):
+    def __init__(self, rows: int, cols: int, rank: int, world: int, group=None, device="cuda", multicast: bool = True,
+                 one_shot=None):
         from . import _lib
+        import os
         import torch.distributed as dist
         if not (2 <= world <= 8):
             raise ValueError("PushExchange needs 2..8 ranks on one node")
         if cols % world or (cols // world) % 128:
             raise ValueError("hidden size / world must be a multiple of 128 (a GEMM tile may not straddle two ranks' slices)")
+        if one_shot is None:
+            # one-shot: every rank pushes its WHOLE partial to every rank ((world-1) n fp16 over NVLink, hidden under the GEMM)
+            # and one handshake remains; two-phase: reduce-scatter push + broadcast, 2 (world-1)/world n and two handshakes.
+            # A flag takes 2.8 us one way over NVSwitch (tools/bench_exchange.py): one-shot wins while the extra bytes stay
+            # hidden, i.e. for two ranks.
+            env = os.environ.get("MIXQ_TP_ONE_SHOT")
+            one_shot = (world == 2) if env is None else env == "1"
+        self.one_shot = bool(one_shot)
+        self.two_shot = not self.one_shot
         self.lib, self._check = _lib.load(), _lib.check
         self.rows, self.cols, self.rank, self.world, self.device = rows, cols, rank, world, device
         self.ns = cols // world
         nb = rows * cols * 2
-        self._nb = nb
-        local, ptrs, mc, self._keep, self._close = _symmetric_alloc(4 * nb + 256, rank, world, group, device)
+        rb = nb * (world if self.one_shot else 1)          # receive area per exchange buffer
+        local, ptrs, mc, self._keep, self._close = _symmetric_alloc(2 * rb + 2 * nb + 256, rank, world, group, device)
         if not multicast:
             mc = 0
-        self.multicast = mc != 0
+        self.multicast = mc != 0 and not self.one_shot
         self._local, self._ptrs, self._mc = local, ptrs, mc
         self._state = torch.zeros(2, dtype=torch.int32, device=device)      # epoch, done
-        self._fin = []
-        self._targets = []
-        slot = rows * self.ns * 2
+        self._fin, self._targets = [], []
+        res0, fl = 2 * rb, 2 * rb + 2 * nb
+        slot = nb if self.one_shot else rows * self.ns * 2
         for b in range(2):
             a = _lib.ExchangeFinishArgs()
-            a.recv = local + b * nb
+            a.recv = local + b * rb
             for r in range(world):
-                a.result[r] = ptrs[r] + 2 * nb + b * nb
-                a.flags[r] = ptrs[r] + 4 * nb
-            a.mc_result = (mc + 2 * nb + b * nb) if mc else 0
-            a.mc_flags = (mc + 4 * nb) if mc else 0
+                a.result[r] = ptrs[r] + res0 + b * nb
+                a.flags[r] = ptrs[r] + fl
+            a.mc_result = (mc + res0 + b * nb) if self.multicast else 0
+            a.mc_flags = (mc + fl) if mc else 0
             a.epoch = self._state.data_ptr()
             a.done = self._state.data_ptr() + 4
             a.M, a.N, a.world, a.rank = rows, cols, world, rank
+            a.one_shot = 1 if self.one_shot else 0
             self._fin.append(a)
-            self._targets.append([ptrs[j] + b * nb + rank * slot for j in range(world)])
-        self._views = [_DeviceBuffer(local + 2 * nb + b * nb, (rows, cols), "<f2") for b in range(2)]
+            self._targets.append([ptrs[j] + b * rb + rank * slot for j in range(world)])
+        self._views = [_DeviceBuffer(local + res0 + b * nb, (rows, cols), "<f2") for b in range(2)]
         self.results = [torch.as_tensor(v, device=device) for v in self._views]
         self.buf = 0
         torch.cuda.synchronize()
         dist.barrier(group=group)       # nobody pushes or signals before everybody has mapped everything
 
     def push_targets(self):
-        """(slot pointers, slice width) for MixLinear_GEMM.forward(..., push=) of THIS exchange."""
-        return self._targets[self.buf], self.ns
+        """(slot pointers, slice width, broadcast count) for MixLinear_GEMM.forward(..., push=) of THIS exchange: two-phase —
+        column slice j of the partial goes to pointer j; one-shot — the whole partial goes to every pointer."""
+        if self.one_shot:
+            return self._targets[self.buf], 0, self.world
+        return self._targets[self.buf], self.ns, 0
 
     def reduce(self, residual, out: torch.Tensor = None) -> torch.Tensor:
         a = self._fin[self.buf]

@@ -190,8 +190,11 @@ def test_int8_fused_dequantize(lib, tile, act, with_outl):
 
 
 @pytest.mark.parametrize("tile", [128, 256])
-def test_int4_fused_dequantize_and_unpack(lib, tile):
-    M, N, K = 70, 264, 1056
+@pytest.mark.parametrize("M", [70, 300])
+def test_int4_fused_dequantize_and_unpack(lib, tile, M):
+    """M = 70: the 1-CTA kernel's unpack warps; M = 300: the 2-CTA kernel (epilogue warps unpack during the mainloop); ragged
+    N and a K that ends inside a 128-byte k-atom."""
+    N, K = 264, 1056
     rng = np.random.default_rng(tile)
     q4 = rng.integers(-8, 8, (N, K), dtype=np.int8)
     qwp = O.pack_to_i4(q4)
@@ -495,8 +498,16 @@ def test_launch_modes_bit_identical(lib, monkeypatch):
             else:
                 monkeypatch.setenv("MIXQ_DEBUG_KATOMS", katoms)
             ys.append(host(run_fused(lib, x, qw, ws, cols, wc, 8, residual=res)["y"]))
+        # how the grid barrier's co-residency is guaranteed: PDL (default), cooperative launch, or no barrier at all (split)
+        monkeypatch.delenv("MIXQ_DEBUG_KATOMS", raising=False)
+        for mode in (1, 2):
+            check(lib.mixq_set_grid_barrier_mode(mode))
+            t = run_fused(lib, x, qw, ws, cols, wc, 8, residual=res)
+            ys.append(host(t["y"]))
+            bits_equal(host(t["q_x"]), host(run_fused(lib, x, qw, ws, cols, wc, 8, residual=res)["q_x"]), "q_x")
     finally:
         check(lib.mixq_set_pdl(1))
+        check(lib.mixq_set_grid_barrier_mode(0))
     for y in ys[1:]:
         bits_equal(y, ys[0], "y across launch modes")
 
@@ -616,3 +627,27 @@ def test_baseline_swiglu_pair_shapes_vs_oracle(lib, M, N, K, n):
     upv = O.dequantize(O.gemm_i8(q_x, qu), xs, ws_u, outl=ou, act=0)
     y_ref = (gate.astype(np.float32) * upv.astype(np.float32)).astype(np.float16)
     rel_close(host(t["y"]), y_ref, "silu(gate) * up")
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 11008, 4096), (300, 528, 1024)], ids=["C3-swiglu-pair-w4", "ragged"])
+def test_linear_fused_swiglu_pair_w4(lib, M, N, K):
+    """W4A4O16 gate/up pair in ONE launch on the 2-CTA kernel (packed-nibble TMA loads, in-smem unpack by the epilogue warps,
+    128 static fp16 outlier columns) against the oracle's three reference steps (fused/mlp.py:61-64 with bit-4 MixLinears)."""
+    rng = np.random.default_rng(N + K)
+    n = 128
+    x, cols = make_x(rng, M, K, 41)
+    rest = np.setdiff1d(np.arange(K, dtype=np.int32), cols)
+    ind = np.concatenate([rest[-(n - len(cols)):], cols]).astype(np.int32)
+    ws_g = (rng.random((1, N)) * 1e-2 + 1e-3).astype(np.float16)
+    ws_u = (rng.random((1, N)) * 1e-2 + 1e-3).astype(np.float16)
+    qg = rng.integers(0, 256, (N, K // 2), dtype=np.uint8)
+    qu = rng.integers(0, 256, (N, K // 2), dtype=np.uint8)
+    wc_g = (rng.standard_normal((N, n)) * 0.02).astype(np.float16)
+    wc_u = (rng.standard_normal((N, n)) * 0.02).astype(np.float16)
+    t = run_fused(lib, x, qg, ws_g, ind, wc_g, 4, up=(qu, ws_u, wc_u))
+    g = oracle_fused(x, qg, ws_g, ind, wc_g, 4, act=1)
+    u = oracle_fused(x, qu, ws_u, ind, wc_u, 4)
+    bits_equal(host(t["q_x"]), g["q_x"], "q_x (int4 range)")
+    bits_equal(host(t["xs"]), g["xs"].reshape(-1), "x_scale")
+    y_ref = (g["y"].astype(np.float32) * u["y"].astype(np.float32)).astype(np.float16)
+    rel_close(host(t["y"]), y_ref, "silu(gate) * up (W4)")

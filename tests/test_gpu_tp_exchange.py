@@ -17,7 +17,8 @@ def test_peer_exchange_two_ranks():
                         "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "check_peer_exchange.py")],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    assert "push exchange ok" in r.stdout and "push decoder ok" in r.stdout
-    assert "push-nomc exchange ok" in r.stdout
+    for kind in ("push-oneshot", "push-twophase", "push-nomc-oneshot", "push-nomc-twophase"):
+        assert f"{kind} exchange ok" in r.stdout, kind
+    assert "push decoder ok" in r.stdout
     assert "peer exchange ok" in r.stdout
     assert "multicast exchange ok" in r.stdout or "multicast exchange unavailable" in r.stdout

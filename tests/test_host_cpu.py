@@ -126,9 +126,10 @@ def test_linear_args_struct_layout_matches_header():
 #include <stddef.h>
 #include "mixq.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(mixq_linear_args), offsetof(mixq_linear_args, q_weight),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(mixq_linear_args), offsetof(mixq_linear_args, q_weight),
          offsetof(mixq_linear_args, ind), offsetof(mixq_linear_args, q_x), offsetof(mixq_linear_args, residual),
-         offsetof(mixq_linear_args, y), offsetof(mixq_linear_args, tile_n));
+         offsetof(mixq_linear_args, y), offsetof(mixq_linear_args, tile_n), offsetof(mixq_linear_args, y_peer),
+         offsetof(mixq_linear_args, peer_cols));
   return 0;
 }'''
     import tempfile
@@ -139,7 +140,8 @@ int main(void) {
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
         got = [int(v) for v in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
     A = _lib.LinearArgs
-    want = [ctypes.sizeof(A), A.q_weight.offset, A.ind.offset, A.q_x.offset, A.residual.offset, A.y.offset, A.tile_n.offset]
+    want = [ctypes.sizeof(A), A.q_weight.offset, A.ind.offset, A.q_x.offset, A.residual.offset, A.y.offset, A.tile_n.offset,
+            A.y_peer.offset, A.peer_cols.offset]
     assert got == want
 
 
@@ -174,6 +176,41 @@ int main(void) {
     assert b"all-reduce" in lib.mixq_last_error()
     a.world, a.n = 2, 12                        # n % 8 != 0
     assert lib.mixq_allreduce_residual(ctypes.byref(a), None) != 0
+
+
+def test_exchange_args_struct_layouts_and_validation():
+    """mixq_exchange_finish_args / mixq_mc_allreduce_args (the fused and the NVLS exchanges) vs their ctypes mirrors."""
+    src = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "mixq.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(mixq_exchange_finish_args), offsetof(mixq_exchange_finish_args, result),
+         offsetof(mixq_exchange_finish_args, mc_result), offsetof(mixq_exchange_finish_args, flags),
+         offsetof(mixq_exchange_finish_args, epoch), offsetof(mixq_exchange_finish_args, residual), offsetof(mixq_exchange_finish_args, rank));
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(mixq_mc_allreduce_args), offsetof(mixq_mc_allreduce_args, partial_off),
+         offsetof(mixq_mc_allreduce_args, flags_off), offsetof(mixq_mc_allreduce_args, epoch), offsetof(mixq_mc_allreduce_args, n),
+         offsetof(mixq_mc_allreduce_args, buf));
+  return 0;
+}'''
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "t.c")
+        open(c, "w").write(src)
+        exe = os.path.join(td, "t")
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        got = [int(v) for v in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    A, B = _lib.ExchangeFinishArgs, _lib.McAllReduceArgs
+    want = [ctypes.sizeof(A), A.result.offset, A.mc_result.offset, A.flags.offset, A.epoch.offset, A.residual.offset, A.rank.offset,
+            ctypes.sizeof(B), B.partial_off.offset, B.flags_off.offset, B.epoch.offset, B.n.offset, B.buf.offset]
+    assert got == want
+    lib = _lib.load()
+    a = A()
+    a.world, a.N, a.M = 3, 4096, 8            # N % (8 * world) != 0
+    assert lib.mixq_exchange_finish(ctypes.byref(a), None) != 0 and b"exchange_finish" in lib.mixq_last_error()
+    b = B()
+    b.world = 1
+    assert lib.mixq_allreduce_multicast(ctypes.byref(b), None) != 0
 
 
 def _plan(M, N, K, bit=8, n=0, pair=0, tile=0, sms=148):

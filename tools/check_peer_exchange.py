@@ -146,17 +146,17 @@ def check_decoder(kind, rank, world):
     return rel, rel1
 
 
-def check_push(rank, world, multicast):
+def check_push(rank, world, multicast, one_shot=None):
     """The fused exchange: a real row-parallel MixLinear pushes its partial from the GEMM epilogue (both GEMM kernels: M = 512
     and M = 128), the finish kernel reduces + broadcasts; reference = the same Linear's partials (all-gathered over NCCL) summed
     in fp32 in rank order, rounded to fp16, + residual — bit-exact, identical on all ranks, eager and graph-replayed."""
     from mixq_b200.cache import MixLibCache
     from mixq_b200.linear import MixLinear_GEMM
-    kind = "push" if multicast else "push-nomc"
+    kind = ("push" if multicast else "push-nomc") + ("" if one_shot is None else ("-oneshot" if one_shot else "-twophase"))
     for M, N, Ktot in ((512, 4096, 4096), (128, 2048, 1024)):
         Kr = Ktot // world
         g = torch.Generator(device="cuda").manual_seed(77 + rank)
-        ex = PushExchange(M, N, rank, world, multicast=multicast)
+        ex = PushExchange(M, N, rank, world, multicast=multicast, one_shot=one_shot)
         cache = MixLibCache(inputdim=M, sigma=6, bit=8)
 
         class W:
@@ -245,7 +245,8 @@ def main():
     kinds = [os.environ["CHECK_KIND"]] if os.environ.get("CHECK_KIND") else ["push", "push-nomc", "peer", "multicast"]
     for kind in kinds:
         if kind.startswith("push"):
-            check_push(rank, world, multicast=(kind == "push"))
+            for one_shot in (True, False):
+                check_push(rank, world, multicast=(kind == "push"), one_shot=one_shot)
             check_decoder(kind, rank, world)
         else:
             check_kind(kind, rank, world)
