@@ -183,7 +183,10 @@ def load() -> C.CDLL:
             "or `make -C mixq_b200/csrc` — there is no CPU or PyTorch fallback for the MixLinear path"
         )
     lib = C.CDLL(str(path))
+    lenient = os.environ.get("MIXQ_LIB_LENIENT") == "1"     # A/B-testing an older build of the library (tools only)
     for name, argtypes in SIGNATURES.items():
+        if lenient and not hasattr(lib, name):
+            continue
         fn = getattr(lib, name)  # AttributeError here == header/library drift
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)

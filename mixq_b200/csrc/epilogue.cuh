@@ -26,14 +26,27 @@ __device__ __forceinline__ __half* y_base(const LinearParams& p, int n, int& ld)
   return p.y;
 }
 
-// f(base, ld) for every destination of the tile that holds output column n.
+// Destinations of the tile that holds output column n: ONE (y, or the owning rank's slot) unless the broadcast push is on.
+// A rolled loop around a single call site: the epilogue is instruction-fetch sensitive, its body must not be duplicated.
+#ifdef MIXQ_AB_NO_BCAST
+__device__ __forceinline__ int y_ndest(const LinearParams& p) { return 1; }
+#else
+__device__ __forceinline__ int y_ndest(const LinearParams& p) { return p.peer_bcast > 0 ? p.peer_bcast : 1; }
+#endif
+__device__ __forceinline__ __half* y_dest(const LinearParams& p, int n, int d, int& ld) {
+  if (p.peer_bcast > 0) {
+    ld = p.N;
+    return p.y_peer[d];
+  }
+  return y_base(p, n, ld);
+}
 template <class F>
 __device__ __forceinline__ void for_each_ydest(const LinearParams& p, int n, F f) {
-  if (p.peer_bcast > 0) {
-    for (int d = 0; d < p.peer_bcast; ++d) f(p.y_peer[d], p.N);
-  } else {
+  const int nd = y_ndest(p);
+#pragma unroll 1
+  for (int d = 0; d < nd; ++d) {
     int ld;
-    __half* b = y_base(p, n, ld);
+    __half* b = y_dest(p, n, d, ld);
     f(b, ld);
   }
 }
@@ -359,14 +372,6 @@ __device__ __forceinline__ void epilogue_run_coalesced(const LinearParams& p, ui
       tmem_ld_wait();
       epilogue_group16<false, MODE, 0, 32>(p, acc, acc, xs, scale_sa + g * 32, row_sa, sw, (g & 3) * 2, row, row_ok, n0 + g * 16);
       epilogue_group16<false, MODE, 16, 32>(p, acc, acc, xs, scale_sa + (g + 1) * 32, row_sa, sw, ((g + 1) & 3) * 2, row, row_ok, n0 + (g + 1) * 16);
-    } else if (HAS_O && two && !(p.ablate & 8)) {
-      // with outliers too: both accumulators 32 columns per tcgen05.ld / wait (half the exposed TMEM round trips of a pass)
-      uint32_t acc[32], oacc[32];
-      tmem_ld_32x32(t_int + g * 16, acc);
-      tmem_ld_32x32(t_outl + g * 16, oacc);
-      tmem_ld_wait();
-      epilogue_group16<true, MODE, 0, 32>(p, acc, oacc, xs, scale_sa + g * 32, row_sa, sw, (g & 3) * 2, row, row_ok, n0 + g * 16);
-      epilogue_group16<true, MODE, 16, 32>(p, acc, oacc, xs, scale_sa + (g + 1) * 32, row_sa, sw, ((g + 1) & 3) * 2, row, row_ok, n0 + (g + 1) * 16);
     } else {
 #pragma unroll 1
       for (int h = 0; h < (two ? 2 : 1); ++h) {

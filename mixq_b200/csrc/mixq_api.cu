@@ -199,14 +199,15 @@ int launch_linear(const LinearParams& p, int grid, bool cooperative, cudaStream_
   return 0;
 }
 
-int launch_linear2(const LinearParams& p, int grid, bool cooperative, cudaStream_t st) {
+template <bool W4>
+int launch_linear2_t(const LinearParams& p, int grid, bool cooperative, cudaStream_t st) {
   using Cfg = Gemm2Cfg;
   static thread_local int last_dev = -1;
   static thread_local int max_clusters = 0;
   int dev = 0;
   MIXQ_CUDA(cudaGetDevice(&dev));
   if (dev != last_dev) {
-    MIXQ_CUDA(cudaFuncSetAttribute(mixq_linear2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    MIXQ_CUDA(cudaFuncSetAttribute(mixq_linear2_kernel<W4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     // the grid barrier needs every CTA pair resident at once: ask the driver how many clusters of this kernel fit the device
     cudaLaunchConfig_t q{};
     q.gridDim = dim3(2);
@@ -218,7 +219,7 @@ int launch_linear2(const LinearParams& p, int grid, bool cooperative, cudaStream
     qa[0].val.clusterDim.y = qa[0].val.clusterDim.z = 1;
     q.attrs = qa;
     q.numAttrs = 1;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, mixq_linear2_kernel, &q) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, mixq_linear2_kernel<W4>, &q) != cudaSuccess) {
       (void)cudaGetLastError();
       max_clusters = 0;   // unknown: do not block the launch on a failed query
     }
@@ -236,9 +237,13 @@ int launch_linear2(const LinearParams& p, int grid, bool cooperative, cudaStream
   LaunchAttrs la(cooperative, pdl_on());
   cfg.attrs = la.a;
   cfg.numAttrs = la.n;
-  MIXQ_CUDA(cudaLaunchKernelEx(&cfg, mixq_linear2_kernel, p));
+  MIXQ_CUDA(cudaLaunchKernelEx(&cfg, mixq_linear2_kernel<W4>, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
+}
+
+int launch_linear2(const LinearParams& p, int grid, bool cooperative, cudaStream_t st) {
+  return p.w4 ? launch_linear2_t<true>(p, grid, cooperative, st) : launch_linear2_t<false>(p, grid, cooperative, st);
 }
 
 // Tile width of the 2-CTA kernel.  The widest strip that still gives every pair one tile: the `npairs / MP` pairs that

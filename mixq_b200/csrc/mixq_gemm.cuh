@@ -78,6 +78,7 @@ struct Gemm2Cfg {
   static constexpr int SMEM_BYTES = PIPE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 512 /*RowQuantSmem*/ +
                                     EPI_WARPS * 32 * 128 /*epilogue staging*/ + 1024 /*scale_col of the tile*/;
 };
+template <bool W4>
 __global__ void mixq_linear2_kernel(const __grid_constant__ LinearParams p);
 
 // TMEM plan of the 2-CTA kernel (512 columns), ONE definition for the kernel and for the host-side planner

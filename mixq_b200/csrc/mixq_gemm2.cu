@@ -29,6 +29,10 @@
 
 namespace mixq {
 
+// W4 (packed-nibble weights, unpacked in shared memory by the epilogue warps) is a TEMPLATE parameter: as a run-time flag its
+// mere presence cost the W8 instantiation ~1 us per launch (A/B builds, profiles/r02_ab_*: register allocation and scheduling
+// of the MMA / producer loops).
+template <bool W4>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg::NUM_THREADS, 1)
 mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
   using Cfg = Gemm2Cfg;
@@ -72,7 +76,7 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
   const int NT = (p.N + wout - 1) / wout;
   const int ntiles = MP * NT;
   const bool has_o = nko > 0;
-  const bool w4 = p.w4 != 0;
+  constexpr bool w4 = W4;
   // bytes per k-atom landing on the leader's full barrier: both CTAs' activations and (W8) weights; W4 weights land on bar_bfull
   const uint32_t atom_tx = w4 ? 2u * static_cast<uint32_t>(Cfg::A_BYTES) : 2u * static_cast<uint32_t>(Cfg::A_BYTES + bh * 128);
   const uint32_t atom_tx_o = 2u * static_cast<uint32_t>(Cfg::A_BYTES + bh * 128);   // fp16 outlier k-blocks: never packed
@@ -187,6 +191,8 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
       const int tile = pair + (it / nkt) * npairs;
       produce(tile, it % nkt, it, /*act*/ false, /*wgt*/ true, /*arm*/ true);
     }
+    // (Tried and dropped: cp.async.bulk.prefetch.tensor of the next ring's worth of weight boxes here, to cover the ~1.3 us MMA
+    // stall at the first wrap of the ring — HBM latency exceeds the 4 stages' cover — made every launch ~2 us SLOWER.)
   }
   __syncwarp();
   pdl_wait();              // everything below reads or writes tensors that earlier kernels touch
@@ -457,5 +463,8 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
     tmem_dealloc_2cta(tmem_base, 512);
   }
 }
+
+template __global__ void mixq_linear2_kernel<false>(const __grid_constant__ LinearParams);
+template __global__ void mixq_linear2_kernel<true>(const __grid_constant__ LinearParams);
 
 }  // namespace mixq
