@@ -204,14 +204,6 @@ namespace mixq {
 
 constexpr int kEpiStageBytes = 32 * 128;
 
-__device__ __forceinline__ uint4 lds128(uint32_t sa) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sa) : "memory");
-  return v;
-}
-__device__ __forceinline__ void sts128(uint32_t sa, const uint4& v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
 // stage[r][c] (r < 32 rows, c < 8 chunks of 16 bytes) lives at stage_sa + r * 128 + ((c ^ (r & 7)) << 4)
 __device__ __forceinline__ uint32_t epi_slot_sa(uint32_t stage_sa, int row, int chunk) {
   return stage_sa + row * 128 + ((chunk ^ (row & 7)) << 4);

@@ -301,6 +301,7 @@ int pick_row_groups(RowQuantArgs* a, int grid, int warps_per_cta, long long smem
 // arithmetic (exported as mixq_plan_linear so that the heuristics are testable without a GPU).
 struct GemmPlan {
   int two_cta, tile_w, k_atoms, stage_bytes, nstages, tiles, tiles_per_unit, units;
+  int npacked = 0;   // W4 on the 2-CTA kernel: slots of the packed-row ring behind the main stages
   TmemPlan tmem;
 };
 int plan_gemm(int M, int N, int K, int bit, int n_out, bool pair, int tile_req, int sms, GemmPlan* g) {
@@ -318,11 +319,13 @@ int plan_gemm(int M, int N, int K, int bit, int n_out, bool pair, int tile_req, 
   if (const char* e = getenv("MIXQ_DEBUG_KATOMS")) { const int v = atoi(e); if (v == 1) k_atoms = 1; }
   int stage2 = 0, nstages2 = 0;
   for (;;) {
-    stage2 = k_atoms * (Gemm2Cfg::A_BYTES + (bn / 2) * 128) + (w4 ? (bn / 2) * 64 : 0);   // W4: + the packed landing rows
+    stage2 = k_atoms * (Gemm2Cfg::A_BYTES + (bn / 2) * 128);
     stage2 = (stage2 + 1023) / 1024 * 1024;
     if (const char* e = getenv("MIXQ_DEBUG_STAGE_BYTES")) { const int v = atoi(e); if (v >= stage2 && v % 1024 == 0) stage2 = v; }
     nstages2 = Gemm2Cfg::PIPE_BYTES / stage2;
     if (nstages2 > Gemm2Cfg::MAX_STAGES) nstages2 = Gemm2Cfg::MAX_STAGES;
+    if (w4 && two_cta && nstages2 > 3) nstages2 = 3;   // W4: three main stages cover the unpack -> MMA -> commit chain; the rest of
+                                                      // the pipeline memory is the packed-row ring that covers HBM latency
     if (const char* e = getenv("MIXQ_DEBUG_STAGES")) { const int v = atoi(e); if (v >= 2 && v < nstages2) nstages2 = v; }
     // the outlier k-blocks of a tile stay resident in the ring during the epilogue passes: with the big stages they may not fit
     if (k_atoms == 2 && (nstages2 < 3 || (n_out + 63) / 64 > nstages2 - 1)) { k_atoms = 1; continue; }
@@ -335,6 +338,14 @@ int plan_gemm(int M, int N, int K, int bit, int n_out, bool pair, int tile_req, 
     bn = pick_tile_n(tile_req, M, N, sms, n_out > 0);
   }
   g->two_cta = two_cta ? 1 : 0;
+  g->npacked = 0;
+  if (two_cta && w4) {
+    const int pitch = ((bn / 2) * 64 + 127) / 128 * 128;
+    int np = (Gemm2Cfg::PIPE_BYTES - nstages2 * stage2) / pitch;
+    if (np > Gemm2Cfg::MAX_STAGES) np = Gemm2Cfg::MAX_STAGES;
+    if (np < 2) return fail(MIXQ_EINVAL, "W4: no room for the packed-row ring at this tile width");
+    g->npacked = np;
+  }
   g->tile_w = bn;
   g->k_atoms = two_cta ? k_atoms : 1;
   if (two_cta) {
@@ -528,6 +539,7 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
   p.stage_bytes = stage2;
   p.k_atoms = ka2 ? 2 : 1;
   p.w4 = (w4 && two_cta) ? 1 : 0;
+  p.npacked = gp.npacked;
   if (const char* e = getenv("MIXQ_DEBUG_ABLATE")) p.ablate = atoi(e);
   p.q_w = static_cast<const uint8_t*>(c.q_w);
   p.q_w_pitch = w4 ? c.K / 2 : c.K;

@@ -45,7 +45,8 @@ struct LinearParams {
   int ablate;          // tuning aid (MIXQ_DEBUG_ABLATE; results are garbage): 1 = no MMAs, 2 = no activation loads, 4 = no weight loads, 8 = 16-column epilogue reads, 16 = single outlier pass buffer (8 and 16 keep results exact)
   int k_atoms;         // 2-CTA kernel: 128-byte k-atoms per pipeline stage and TMA op (1, or 2 with 3-D tm_a / tm_b / tm_b2)
   int w4;              // 2-CTA kernel: weights are packed nibbles (tm_b / tm_b2: uint8 [N, K/2], box 64 B x W/2 rows, no swizzle);
-                       // the epilogue warps unpack each stage's 64-byte rows into the SWIZZLE_128B int8 tile during the mainloop
+                       // the epilogue warps unpack each 64-byte row into the SWIZZLE_128B int8 tile during the mainloop
+  int npacked;         // W4: slots of the packed-row ring that follows the nstages main stages in shared memory
   const uint8_t* q_w;  // raw weight pointer + row pitch in bytes (L2 prefetch of the weight stream)
   long long q_w_pitch;
   unsigned long long* trace;  // optional [gridDim.x * 8] globaltimer stamps (mixq_set_trace_buffer), debug/tuning only

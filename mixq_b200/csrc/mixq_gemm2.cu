@@ -45,10 +45,13 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
   uint64_t* bar_tfull = bar_empty + MAXS;                                      // [0]: one phase per epilogue pass; per CTA
   uint64_t* bar_tempty = bar_tfull + 2;                                        // [0]: pass consumed by both CTAs' epilogues; leader
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
-  // W4 only (they live in the slack of the RowQuantSmem block): the packed weight rows of a stage land on the CTA's OWN
-  // bar_bfull; bar_ready (leader) counts the unpack warps of both CTAs that have expanded the stage to int8
+  // W4 only.  The packed weight rows travel through their OWN ring of p.npacked slots behind the main stages (deep enough to
+  // cover HBM latency; the 3 main stages only have to cover the unpack -> MMA -> commit chain): bar_bfull / bar_bempty are this
+  // CTA's (slot landed / slot consumed by its 8 unpack warps; they live in the slack of the RowQuantSmem block); bar_ready
+  // (leader) counts the unpack warps of both CTAs that have expanded a main stage's weight half to int8.
   uint64_t* bar_bfull = reinterpret_cast<uint64_t*>(smem + Cfg::PIPE_BYTES + 256 + 384);
-  uint64_t* bar_ready = bar_bfull + MAXS;
+  uint64_t* bar_bempty = bar_bfull + MAXS;
+  uint64_t* bar_ready = reinterpret_cast<uint64_t*>(smem + Cfg::PIPE_BYTES + 168);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -91,7 +94,9 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
 
   auto stage_a = [&](int s) { return smem + static_cast<size_t>(s) * stage_bytes; };
   auto stage_b = [&](int s) { return smem + static_cast<size_t>(s) * stage_bytes + static_cast<size_t>(KA) * Cfg::A_BYTES; };
-  auto stage_bp = [&](int s) { return stage_b(s) + static_cast<size_t>(bh) * 128; };   // W4: packed rows (64 B each), KA == 1
+  const int NP = p.npacked;                                   // W4: packed-row ring
+  const uint32_t pk_pitch = (static_cast<uint32_t>(bh) * 64u + 127u) & ~127u;
+  auto packed_slot = [&](int ps) { return smem + static_cast<size_t>(nstages) * stage_bytes + static_cast<size_t>(ps) * pk_pitch; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tm_a);
@@ -108,7 +113,8 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
       mbar_init(&bar_empty[s], 1);
       if (w4) {
         mbar_init(&bar_bfull[s], 1);
-        mbar_init(&bar_ready[s], 2 * Cfg::EPI_WARPS);   // one arrival per unpack warp of both CTAs
+        mbar_init(&bar_bempty[s], Cfg::EPI_WARPS);      // this CTA's unpack warps (both groups)
+        mbar_init(&bar_ready[s], 2 * Cfg::EPI_WARPS);   // ... of both CTAs
       }
     }
     for (int s = 0; s < 2; ++s) {
@@ -152,13 +158,8 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
         arm = false;
       }
       if (arm && leader) mbar_arrive_expect_tx(&bar_full[s], atom_tx * static_cast<uint32_t>(KA));
-      if (w4) {   // packed nibbles: 64 bytes of a weight row per k-atom, onto this CTA's own barrier
-        const int k0 = kb * 128;
-        if (do_wgt) {
-          if (arm) mbar_arrive_expect_tx(&bar_bfull[s], static_cast<uint32_t>(bh) * 64u);
-          tma_load_2d_2cta(tmb, smem_u32(&bar_bfull[s]), stage_bp(s), k0 >> 1, n0, kEvictFirst);
-        }
-        if (do_act) tma_load_2d_2cta(&p.tm_a, full_leader, stage_a(s), k0, m0, kEvictLast);
+      if (w4) {   // activations only: the packed weights go through produce_packed / the unpack warps
+        if (do_act) tma_load_2d_2cta(&p.tm_a, full_leader, stage_a(s), kb * 128, m0, kEvictLast);
       } else if (KA == 1) {
         const int k0 = kb * 128;
         if (do_wgt) tma_load_2d_2cta(tmb, full_leader, stage_b(s), k0, n0, kEvictFirst);
@@ -169,11 +170,18 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
       }
     } else {
       if (arm && leader) mbar_arrive_expect_tx(&bar_full[s], atom_tx_o);
-      if (w4 && do_wgt && arm) mbar_arrive(&bar_bfull[s]);   // nothing packed in an outlier block: the stage's W4 barriers just tick
       const int ko = (kb - nk) * 64;
       if (do_wgt) tma_load_2d_2cta(tmob, full_leader, stage_b(s), ko, n0, kEvictFirst);
       if (do_act) tma_load_2d_2cta(&p.tm_oa, full_leader, stage_a(s), ko, m0, kEvictLast);
     }
+  };
+
+  // W4: packed weight rows of int8 k-block kb of `tile` -> packed slot ps (64 bytes of every weight row, no swizzle)
+  auto produce_packed = [&](int tile, int kb, int ps) {
+    const int n0 = pairm ? (tile / MP) * bh : (tile / MP) * W + static_cast<int>(rank) * bh;
+    const CUtensorMap* tmb = (pairm && rank == 1) ? &p.tm_b2 : &p.tm_b;
+    mbar_arrive_expect_tx(&bar_bfull[ps], static_cast<uint32_t>(bh) * 64u);
+    tma_load_2d_2cta(tmb, smem_u32(&bar_bfull[ps]), packed_slot(ps), (kb * 128) >> 1, n0, kEvictFirst);
   };
 
   const int my_tiles = (pair < ntiles) ? (ntiles - 1 - pair) / npairs + 1 : 0;
@@ -182,7 +190,11 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
                              ? static_cast<int>((static_cast<size_t>(p.rq.ngroups) * p.rq.K * 2 + stage_bytes - 1) / stage_bytes)
                              : 0;
   const int free_stages = nstages - row_stages;
-  const int n_pre = my_items < free_stages ? my_items : free_stages;
+  // W4: nothing is prefetched into the main stages (their weight halves are written by the unpack warps); the whole packed
+  // ring is filled instead
+  const int n_pre = w4 ? 0 : (my_items < free_stages ? my_items : free_stages);
+  const int my_packed = my_tiles * nk;
+  const int n_pre_p = my_packed < NP ? my_packed : NP;
 
   // The quantised weights are constants: fill every free pipeline stage with them BEFORE waiting for the kernels ahead
   // of us in the stream (programmatic dependent launch) — and, with the fused prologue, before phase A.
@@ -191,6 +203,8 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
       const int tile = pair + (it / nkt) * npairs;
       produce(tile, it % nkt, it, /*act*/ false, /*wgt*/ true, /*arm*/ true);
     }
+    if (w4)
+      for (int pi = 0; pi < n_pre_p; ++pi) produce_packed(pair + (pi / nk) * npairs, pi % nk, pi);
     // (Tried and dropped: cp.async.bulk.prefetch.tensor of the next ring's worth of weight boxes here, to cover the ~1.3 us MMA
     // stall at the first wrap of the ring — HBM latency exceeds the 4 stages' cover — made every launch ~2 us SLOWER.)
   }
@@ -213,7 +227,44 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
   // 71 with two).  Warp 3 streams the weights (and arms the stage barrier), warp 0 the activations.
   // (Tried and dropped: pulling the weight boxes into L2 ahead of the loads — cp.async.bulk.prefetch.tensor costs a TMA
   // issue slot per box and made the loop 15 % slower; a spare warp issuing prefetch.global.L2 changed nothing.)
-  if (warp == 0 || warp == 3) {
+  if (w4 && (warp == 0 || warp == 3)) {
+    // W4 producers.  Warp 3: ONLY the packed weight rows, into the packed ring — gated by bar_bempty alone, so it runs up to NP
+    // k-blocks ahead of the MMAs (it must not touch the main stages: a producer that skips uses of a stage cannot wait on that
+    // stage's parity barrier).  Warp 0: everything that lands in a main stage — the activations of every item and both operands
+    // of the fp16 outlier blocks — and the arming of the leader's full barrier.
+    const bool wgt = warp == 3;
+    fence_proxy_async_all();
+    int it = 0, s = 0, pi = 0, ps = 0;
+    uint32_t ph = 0, pph = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int tile = pair + i * npairs;
+      for (int kb = 0; kb < nkt; ++kb, ++it) {
+        if (wgt) {
+          if (kb < nk) {
+            if (pi >= NP) {
+              mbar_wait(&bar_bempty[ps], pph ^ 1, 16, ps);
+              if (elect_one()) produce_packed(tile, kb, ps);
+              __syncwarp();
+            }
+            ++pi;
+            if (++ps == NP) { ps = 0; pph ^= 1; }
+          }
+        } else {
+          if (it >= nstages) mbar_wait(&bar_empty[s], ph ^ 1, 1, s);
+          if (elect_one()) {
+            if (kb < nk) {
+              if (leader) mbar_arrive_expect_tx(&bar_full[s], atom_tx);
+              produce(tile, kb, s, true, false, false);
+            } else {
+              produce(tile, kb, s, true, true, true);
+            }
+          }
+          __syncwarp();
+          if (++s == nstages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 0 || warp == 3) {
     const bool wgt = warp == 3;
     fence_proxy_async_all();
     int it = 0, s = 0;
@@ -348,35 +399,60 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
     // expand the packed nibbles: each stage's 64-byte weight rows (low nibble = even k, linear.py:14-18) become the
     // SWIZZLE_128B int8 tile the UMMA descriptor expects (row r: 16-byte chunk c at c ^ (r & 7)).  256 threads walk the
     // (row, 16-byte packed chunk) pairs of the stage; the leader's bar_ready collects both CTAs' warps.
-    int us = 0;
-    uint32_t uph = 0;
+    int us = 0, ups = 0, uit = 0;
+    uint32_t uph = 0, upph = 0;
     const uint32_t ready_leader = mapa_u32(smem_u32(&bar_ready[0]), 0);
     for (int i = 0; i < my_tiles; ++i) {
       if (w4) {
-        const int ut = threadIdx.x - 128;          // 0 .. 255
-        for (int kb = 0; kb < nkt; ++kb) {          // (fp16 outlier k-blocks: nothing to unpack, the barriers just tick)
-          mbar_wait(&bar_bfull[us], uph, 15, us);
-          const uint8_t* src_base = stage_bp(us);
-          uint8_t* dst_base = stage_b(us);
-          for (int it = ut; it < (kb < nk ? bh * 4 : 0); it += 256) {
-            const int r = it >> 2, v = it & 3;
-            const uint4 pk = *reinterpret_cast<const uint4*>(src_base + r * 64 + v * 16);
-            const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
-            uint32_t o[8];
+        // Two groups of four warps take alternate items, so that one item's unpack (~0.5 us: generic-proxy shared-memory
+        // traffic competes with the tensor core's operand reads) overlaps the next one's.  Every group still WAITS on every
+        // item's barriers in order (a parity wait may not skip a phase); it unpacks and arrives only for its own items.
+        const int ugrp = (warp - 4) >> 2;          // 0: warps 4-7, 1: warps 8-11
+        const int ut = threadIdx.x - 128 - ugrp * 128;   // 0 .. 127 within the group
+        for (int kb = 0; kb < nkt; ++kb, ++uit) {
+          const bool mine = (uit & 1) == ugrp;
+          const bool utr = p.trace != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0 && uit < 40;
+          if (utr) p.trace[1200 + 4 * uit] = globaltimer_ns();
+          // the main stage is free again (its previous MMAs have retired) — also orders this item's bar_ready tick after the
+          // MMA warp has consumed the stage's previous one
+          if (uit >= nstages) mbar_wait_lane0(&bar_empty[us], uph ^ 1, 17, us);
+          if (utr) p.trace[1200 + 4 * uit + 1] = globaltimer_ns();
+          if (kb < nk) {
+            mbar_wait_lane0(&bar_bfull[ups], upph, 15, ups);
+            if (utr) p.trace[1200 + 4 * uit + 2] = globaltimer_ns();
+            if (mine) {
+              // 32-bit shared-window addresses + ld/st.shared (generic 64-bit pointers compile to LD.E / ST.E: slower path)
+              const uint32_t src_sa = smem_u32(packed_slot(ups)), dst_sa = smem_u32(stage_b(us));
+#pragma unroll 2
+              for (int it = ut; it < bh * 4; it += 128) {
+                const uint32_t r = static_cast<uint32_t>(it) >> 2, v = static_cast<uint32_t>(it) & 3u;
+                const uint4 pk = lds128(src_sa + r * 64u + v * 16u);
+                const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+                uint32_t o[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t lo = nib_lo_s8x4(w[j]);
-              const uint32_t hi = nib_hi_s8x4(w[j]);
-              o[2 * j] = __byte_perm(lo, hi, 0x5140);
-              o[2 * j + 1] = __byte_perm(lo, hi, 0x7362);
+                for (int j = 0; j < 4; ++j) {
+                  const uint32_t lo = nib_lo_s8x4(w[j]);
+                  const uint32_t hi = nib_hi_s8x4(w[j]);
+                  o[2 * j] = __byte_perm(lo, hi, 0x5140);
+                  o[2 * j + 1] = __byte_perm(lo, hi, 0x7362);
+                }
+                const uint32_t drow = dst_sa + r * 128u;
+                sts128(drow + (((2u * v) ^ (r & 7u)) << 4), make_uint4(o[0], o[1], o[2], o[3]));
+                sts128(drow + (((2u * v + 1u) ^ (r & 7u)) << 4), make_uint4(o[4], o[5], o[6], o[7]));
+              }
+              fence_proxy_async_smem();             // generic-proxy smem writes -> visible to the pair's tcgen05.mma (async proxy)
+              __syncwarp();
             }
-            uint8_t* drow = dst_base + r * 128;
-            *reinterpret_cast<uint4*>(drow + (((2 * v) ^ (r & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<uint4*>(drow + (((2 * v + 1) ^ (r & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+            if (lane == 0) mbar_arrive(&bar_bempty[ups]);     // the packed slot may be refilled once BOTH groups are past it
+            if (++ups == NP) { ups = 0; upph ^= 1; }
+            if (utr) p.trace[1200 + 4 * uit + 3] = globaltimer_ns();
           }
-          fence_proxy_async_smem();                 // generic-proxy smem writes -> visible to the pair's tcgen05.mma (async proxy)
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster_release(ready_leader + static_cast<uint32_t>(us) * 8u);
+          // CTA-scope release, like the TMEM hand-back arrive of the epilogue: the unpacked tile sits in THIS CTA's shared memory
+          // (fence.proxy.async above made it visible to the async proxy); a cluster-scope release costs ~0.8 us per arrive
+          // (in-kernel trace, profiles/r02_trace_w4*) and paced the whole W4 mainloop at 1.5 us per k-block
+          // (both groups arrive — the other one right after its waits — so that no barrier of the item can advance two phases
+          // before a group has looked at it)
+          if (lane == 0) mbar_arrive_cluster(ready_leader + static_cast<uint32_t>(us) * 8u);
           if (++us == nstages) { us = 0; uph ^= 1; }
         }
       }

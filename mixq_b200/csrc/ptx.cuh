@@ -111,6 +111,12 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, i
   __syncwarp();
 }
 
+// Short waits by whole warps inside a pipeline: lane 0 polls without back-off.
+__device__ __forceinline__ void mbar_wait_lane0(uint64_t* bar, uint32_t parity, int what = 0, int tag = 0) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity, what, tag);
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------- proxies
 // generic-proxy writes (st.global / st.shared) that a later async-proxy op (TMA, tcgen05.mma)
 // must observe, and the reverse.
@@ -267,6 +273,24 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
   return (1u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
 }
+
+// ---------------------------------------------------------------- shared memory through 32-bit shared-window addresses
+// (a pointer derived from the aligned dynamic-smem base has lost its address space: the compiler emits generic LD.E / ST.E,
+// a slower path than LDS / STS)
+__device__ __forceinline__ uint4 lds128(uint32_t sa) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sa) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t sa, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint16_t lds16(uint32_t sa) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(sa) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts16(uint32_t sa, uint16_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(sa), "h"(v) : "memory"); }
 
 // ---------------------------------------------------------------- packed-nibble sign extension
 // Four two's-complement nibbles (the low / high nibbles of the four bytes of w) -> four int8 lanes: n | (n & 8 ? 0xF0 : 0).

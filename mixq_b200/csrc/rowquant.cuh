@@ -175,7 +175,7 @@ __device__ __forceinline__ void process_row(const RowQuantArgs& a, int m, int gr
   const int bar_id = 1 + group;
   float* s_sum = sm->slots[iter & 1][0];
   float* s_max = sm->slots[iter & 1][1];
-  uint4* row4 = reinterpret_cast<uint4*>(row_s);
+  const uint32_t row_sa = smem_u32(row_s);          // the row in shared memory, addressed through ld/st.shared
   __half* xrow = a.x + static_cast<size_t>(m) * K;
   const bool norm = a.norm_w != nullptr;
 
@@ -184,7 +184,7 @@ __device__ __forceinline__ void process_row(const RowQuantArgs& a, int m, int gr
   if (norm) {
     float ss = 0.f;
 #pragma unroll 2
-    for (int i = gl; i < nvec; i += gsize) ss = sumsq8(row4[i], ss);
+    for (int i = gl; i < nvec; i += gsize) ss = sumsq8(lds128(row_sa + i * 16), ss);
     ss = group_reduce<false>(ss, G, warp0, warp, lane, s_sum, bar_id);
     rstd = __fdiv_rn(1.0f, __fsqrt_rn(__fdiv_rn(ss, static_cast<float>(K)) + a.eps));
   }
@@ -192,7 +192,7 @@ __device__ __forceinline__ void process_row(const RowQuantArgs& a, int m, int gr
     const uint4* w4 = reinterpret_cast<const uint4*>(a.norm_w);
     uint4* o4 = reinterpret_cast<uint4*>(a.norm_out + static_cast<size_t>(m) * K);
 #pragma unroll 2
-    for (int i = gl; i < nvec; i += gsize) o4[i] = norm8(row4[i], __ldg(w4 + i), rstd);
+    for (int i = gl; i < nvec; i += gsize) o4[i] = norm8(lds128(row_sa + i * 16), __ldg(w4 + i), rstd);
     return;
   }
 
@@ -201,11 +201,11 @@ __device__ __forceinline__ void process_row(const RowQuantArgs& a, int m, int gr
   if (a.n_ind > 0) {
     for (int j = gl; j < a.n_ind; j += gsize) {
       const int c = a.ind[j];
-      __half val = row_s[c];
+      __half val = __ushort_as_half(lds16(row_sa + c * 2));
       if (norm) val = __float2half_rn(__fmul_rn(__fmul_rn(__half2float(val), rstd), __half2float(a.norm_w[c])));
       else if (a.x != nullptr) xrow[c] = __float2half_rn(0.f);   // (a producer-fused caller may keep no fp16 copy at all)
       a.act_out[static_cast<size_t>(m) * a.ld_ao + j] = val;
-      row_s[c] = __float2half_rn(0.f);
+      sts16(row_sa + c * 2, 0);
     }
     if (G == 1) __syncwarp();
     else named_bar_sync(bar_id, gsize);
@@ -218,14 +218,14 @@ __device__ __forceinline__ void process_row(const RowQuantArgs& a, int m, int gr
     uint4* o4 = a.norm_out ? reinterpret_cast<uint4*>(a.norm_out + static_cast<size_t>(m) * K) : nullptr;
 #pragma unroll 2
     for (int i = gl; i < nvec; i += gsize) {
-      const uint4 u = norm8(row4[i], __ldg(w4 + i), rstd);
-      row4[i] = u;   // each thread re-reads only its own vectors below
+      const uint4 u = norm8(lds128(row_sa + i * 16), __ldg(w4 + i), rstd);
+      sts128(row_sa + i * 16, u);   // each thread re-reads only its own vectors below
       if (o4) o4[i] = u;
       am2 = absmax8(u, am2);
     }
   } else {
 #pragma unroll 4
-    for (int i = gl; i < nvec; i += gsize) am2 = absmax8(row4[i], am2);
+    for (int i = gl; i < nvec; i += gsize) am2 = absmax8(lds128(row_sa + i * 16), am2);
   }
   float amax = fmaxf(__low2float(am2), __high2float(am2));
   amax = group_reduce<true>(amax, G, warp0, warp, lane, s_max, bar_id);
@@ -245,7 +245,7 @@ __device__ __forceinline__ void process_row(const RowQuantArgs& a, int m, int gr
   uint2* dst = reinterpret_cast<uint2*>(a.q_x + static_cast<size_t>(m) * K);
 #pragma unroll 2
   for (int i = gl; i < nvec; i += gsize) {
-    const uint4 u = row4[i];
+    const uint4 u = lds128(row_sa + i * 16);
     dst[i] = quant8(u, r, qmax);
     if (scan) scan8(u, sigma, a.col_over + i * 8);
   }

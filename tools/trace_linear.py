@@ -11,6 +11,7 @@ trace = torch.zeros(16384, dtype=torch.int64, device=dev)
 NOUT = int(os.environ.get('NOUT', '41'))
 PAIR = os.environ.get('PAIR') == '1'   # SwiGLU pair launch (gate + up)
 NORM = os.environ.get('NORM') == '1'
+BIT = int(os.environ.get('BIT', '8'))
 TILE = int(os.environ.get('TILE', '0'))
 MODES = os.environ.get('MODES', 'plain,skip').split(',')
 SHAPES = [tuple(int(v) for v in t.split('x')) for t in os.environ.get('SHAPES', '12288x4096,4096x4096,4096x11008').split(',')]
@@ -18,7 +19,8 @@ for (N, K) in SHAPES:
     n, cap = NOUT, max(64, (NOUT + 63) // 64 * 64)
     cols = torch.randperm(K, generator=g, device=dev)[:max(n, 1)].sort().values.int()
     x0 = torch.randn(M, K, generator=g, device=dev); x0[:, cols.long()] *= 20; x0 = x0.half()
-    ws_l = [(torch.randint(-127, 128, (N, K), generator=g, device=dev, dtype=torch.int8),
+    ws_l = [((torch.randint(-127, 128, (N, K), generator=g, device=dev, dtype=torch.int8) if BIT == 8 else
+              torch.randint(0, 256, (N, K // 2), generator=g, device=dev, dtype=torch.uint8)),
              (torch.rand(N, generator=g, device=dev) * 1e-3 + 1e-4).half(),
              (torch.randn(N, cap, generator=g, device=dev) * 0.02).half()) for _ in range(4)]
     q_x = torch.zeros(M, K, dtype=torch.int8, device=dev); xs = torch.zeros(M, dtype=torch.float16, device=dev)
@@ -28,7 +30,7 @@ for (N, K) in SHAPES:
         for it, (qw, ws, wc) in enumerate(ws_l):
             a = _lib.LinearArgs()
             a.x = x.data_ptr(); a.M, a.N, a.K = M, N, K
-            a.q_weight = qw.data_ptr(); a.scale_col = ws.data_ptr(); a.bit = 8
+            a.q_weight = qw.data_ptr(); a.scale_col = ws.data_ptr(); a.bit = BIT
             a.ind = cols.data_ptr(); a.n_ind = n; a.weight_cache = wc.data_ptr(); a.ld_wc = cap
             a.q_x = q_x.data_ptr(); a.x_scale = xs.data_ptr(); a.act_outliers = ao.data_ptr(); a.ld_ao = cap
             if PAIR:
@@ -67,6 +69,10 @@ for (N, K) in SHAPES:
                   f"stage-out {ep[ok, 2].mean():8.0f} | calls {ep[ok, 3].mean():.1f}")
         if os.environ.get("CADENCE"):
             base = t[0, 0]
+            up = full[1200:1200 + 160].view(40, 4)
+            if up[:, 0].sum() > 0:
+                print("    unpack warp 4 (enter, stage free, packed landed, done) us: " + " | ".join(
+                    " ".join(f"{(v - base) / 1e3:.2f}" if v > 0 else "-" for v in row) for row in up.tolist() if row[0] > 0))
             for name, off, cnt in (("mma", 2048, 96), ("wgt-tma", 2048 + 256, 48), ("act-tma", 2048 + 512, 48)):
                 v = full[off:off + cnt]
                 v = v[v > 0]
