@@ -281,40 +281,56 @@ def tp_parity_check(args, cfg, model, tok0, rank, world):
 
 
 def time_exchanges(model, n):
-    """Per-exchange device time of the exchange kernel alone: one CUDA graph of n exchanges on the real buffers (every rank
-    replays it at the same time).  For the fused exchange this is the finish kernel — the exposed half; the reduce-scatter
-    half rides inside the row-parallel GEMM's epilogue."""
+    """Per-exchange device time the exchange ADDS to the step: one CUDA graph of n exchanges on the real buffers (every rank
+    replays it at the same time).  For the fused exchange the reduce-scatter half rides inside the row-parallel GEMM's
+    epilogue, so the graph holds layer 0's o_proj pushing its tiles + the finish kernel, and the same o_proj alone is timed
+    and subtracted."""
     import torch
     h = torch.zeros((model.batch, model.cfg.hidden), dtype=torch.float16, device="cuda")
-    if not hasattr(model.xchg, "next_partial"):
-        model.xchg.next_partial = lambda: None
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    model._rank_barrier()
-    with torch.cuda.stream(side):
-        for _ in range(2):
+    fused = getattr(model.xchg, "fused", False)
+    if fused:
+        lin = model.layers[0]["o_proj"]
+        x = torch.randn((model.batch, lin.in_features), device="cuda").half()
+
+        def one(push=True):
+            lin(x, None, True, push=model.xchg.push_targets() if push else None)
+            if push:
+                model.xchg.reduce(h)
+    else:
+        def one(push=True):
             model.xchg.next_partial()
             model.xchg.reduce(h)
-    torch.cuda.current_stream().wait_stream(side)
-    model._rank_barrier()
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        for _ in range(n):
-            model.xchg.next_partial()
-            model.xchg.reduce(h)
-    model._rank_barrier()
-    g.replay()
-    model._rank_barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 3
-    e0.record()
-    for _ in range(reps):
+
+    def timed(push):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        model._rank_barrier()
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                one(push)
+        torch.cuda.current_stream().wait_stream(side)
+        model._rank_barrier()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(n):
+                one(push)
+        model._rank_barrier()
         g.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) * 1e3 / (reps * n)
-    del g
-    model._rank_barrier()
+        model._rank_barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / (reps * n)
+        del g
+        model._rank_barrier()
+        return us
+    us = timed(True)
+    if fused:
+        us -= timed(False)
     return us
 
 

@@ -317,6 +317,25 @@ typedef struct mixq_exchange_finish_args {
 } mixq_exchange_finish_args;
 int mixq_exchange_finish(const mixq_exchange_finish_args* a, void* stream);
 
+/* The same second half with NO flags and NO fences — the data is its own signal (measured on NVSwitch: a flag takes 2.8 us one
+ * way and a system-scope release after stores to peers 6-9 us; the flag protocol above pays two of each per exchange).  Receive
+ * slots and result buffers hold the sentinel fp16 0xFFFF (a NaN payload no arithmetic produces) until a peer's store lands:
+ * a reader spins on the 16-byte vector it needs until none of its halves is the sentinel, and whoever consumes a vector puts
+ * the sentinel back.  The caller fills recv / result buffers with 0xFFFF once, alternates two buffer sets, and passes as
+ * `reset` the local result buffer of the PREVIOUS exchange (dead after this launch has read it as the residual).
+ * Ordering needs no handshake: a peer pushes into this rank's slots of exchange e only after finishing exchange e - 1, which
+ * needed this rank's slice of e - 1, produced after exchange e - 2 released those slots (stream order). */
+typedef struct mixq_exchange_poll_args {
+  void* recv;              /* local fp16 [world][M, N/world] (one_shot: [world][M, N]) receive slots of this exchange */
+  void* result[8];         /* rank r's result buffer of this exchange as mapped here (one_shot: only [rank] is used) */
+  void* mc_result;         /* multicast address of the result buffer or NULL */
+  void* reset;             /* local: the other result buffer, re-armed (sentinel-filled) by this launch; or NULL */
+  const void* residual;    /* local fp16 [M, N] or NULL (may be the `reset` buffer) */
+  int M, N, world, rank;
+  int one_shot;
+} mixq_exchange_poll_args;
+int mixq_exchange_finish_poll(const mixq_exchange_poll_args* a, void* stream);
+
 /* How long (milliseconds, default 120 000; environment MIXQ_PEER_TIMEOUT_MS) an exchange waits for a silent peer before the
  * kernel reports the stall (device printf + trap => a sticky CUDA error on the host).  Ranks drift apart by seconds around
  * host-synchronising phases (outlier discovery, graph capture, rank-0-only work): callers should still put a process-group

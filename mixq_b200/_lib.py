@@ -118,6 +118,23 @@ class ExchangeFinishArgs(C.Structure):
     ]
 
 
+class ExchangePollArgs(C.Structure):
+    """Mirror of `mixq_exchange_poll_args` (include/mixq.h)."""
+
+    _fields_ = [
+        ("recv", C.c_void_p),
+        ("result", C.c_void_p * 8),
+        ("mc_result", C.c_void_p),
+        ("reset", C.c_void_p),
+        ("residual", C.c_void_p),
+        ("M", C.c_int),
+        ("N", C.c_int),
+        ("world", C.c_int),
+        ("rank", C.c_int),
+        ("one_shot", C.c_int),
+    ]
+
+
 class LinearPlan(C.Structure):
     """Mirror of `mixq_linear_plan` (include/mixq.h)."""
 
@@ -156,6 +173,7 @@ SIGNATURES = {
     "mixq_allreduce_residual": [C.POINTER(AllReduceArgs), _vp],
     "mixq_allreduce_multicast": [C.POINTER(McAllReduceArgs), _vp],
     "mixq_exchange_finish": [C.POINTER(ExchangeFinishArgs), _vp],
+    "mixq_exchange_finish_poll": [C.POINTER(ExchangePollArgs), _vp],
     "mixq_set_peer_timeout_ms": [_ll],
     "mixq_set_tile_n": [_i],
     "mixq_set_pdl": [_i],

@@ -1076,6 +1076,35 @@ int mixq_quik_addend(const void* meta, const void* reduced_w, const void* fp_res
   return 0;
 }
 
+int mixq_exchange_finish_poll(const mixq_exchange_poll_args* a, void* stream) {
+  if (!a || a->world < 2 || a->world > kMaxPeers || a->rank < 0 || a->rank >= a->world || !a->recv || a->M < 1 || a->N < 8 ||
+      a->N % (8 * a->world) != 0)
+    return fail(MIXQ_EINVAL, "bad exchange_finish_poll arguments (2 <= world <= 8, N % (8 * world) == 0)");
+  XchgPollArgs k{};
+  k.recv = static_cast<__half*>(a->recv);
+  for (int p = 0; p < a->world; ++p) {
+    if (!a->mc_result && !a->result[p] && !(a->one_shot && p != a->rank)) return fail(MIXQ_EINVAL, "missing peer pointer");
+    k.result[p] = static_cast<__half*>(a->result[p]);
+  }
+  if (!a->result[a->rank]) return fail(MIXQ_EINVAL, "missing local result buffer");
+  k.mc_result = static_cast<__half*>(a->mc_result);
+  k.reset = static_cast<__half*>(a->reset);
+  k.residual = static_cast<const __half*>(a->residual);
+  k.M = a->M;
+  k.N = a->N;
+  k.world = a->world;
+  k.rank = a->rank;
+  k.one_shot = a->one_shot ? 1 : 0;
+  k.timeout_ns = g_peer_timeout_ms.load(std::memory_order_relaxed) * 1000000ull;
+  k.trace = g_trace.load(std::memory_order_relaxed);
+  DeviceInfo di;
+  if (int r = device_info(&di)) return r;
+  const int grid = grid_for(static_cast<long long>(a->M) * (a->N / (a->one_shot ? 1 : a->world) / 8), 256, di.sms, 2);
+  MIXQ_CUDA(launch_small(exchange_finish_poll_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), k));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
 int mixq_debug_pingpong(void* mine, void* peer, void* mc, int iters, int rank, void* out_ns, void* stream) {
   pingpong_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<uint32_t*>(mine), static_cast<uint32_t*>(peer),
                                                                     static_cast<uint32_t*>(mc), iters, rank,

@@ -540,6 +540,107 @@ __device__ __forceinline__ void xf_wait(const XchgFinishArgs& a, int phase, uint
   } while (static_cast<int32_t>(v - target) < 0);
 }
 
+// ---------------------------------------------------------------- fused exchange, second half, sentinel-polling form
+// No handshake at all (see XchgPollArgs): measured on NVSwitch a flag costs 2.8 us one way and a system-scope release after
+// stores to peers 6-9 us (profiles/r02_exchange_anatomy_*), and the flag protocol needs two of each per exchange.  Here every
+// wait is a spin on local memory for data that is already on its way:
+//   own slice: for each 16-byte vector, wait until every rank's partial has landed in its slot (GEMM-epilogue pushes), add them
+//   in fp32 in rank order, round, + residual (separate fp16 rounding), store the vector into EVERY rank's result buffer, put
+//   the sentinel back into the slots;
+//   other slices: wait until their owners' stores have landed in the local result buffer.
+// Why nothing can be overwritten too early: a peer pushes into my slots of exchange e only after it has finished exchange e-1,
+// which needed my slice of e-1, which I produced after my exchange e-2 had released these very slots (same stream); the same
+// chain protects the result buffers.  The other result buffer (read last by this launch, as the residual) is re-armed here.
+constexpr uint32_t kSentinel2 = 0xFFFFFFFFu;     // two fp16 sentinels
+__device__ __forceinline__ bool has_sentinel(const uint4& v) {
+  auto w = [](uint32_t x) { return (x & 0xFFFFu) == 0xFFFFu || (x >> 16) == 0xFFFFu; };
+  return w(v.x) || w(v.y) || w(v.z) || w(v.w);
+}
+__device__ __forceinline__ uint4 poll_vec(const uint4* p, unsigned long long timeout_ns, int what) {
+  uint4 v = __ldcv(p);
+  if (!has_sentinel(v)) return v;
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  do {
+    v = __ldcv(p);
+    if ((++spins & 0xff) == 0 && globaltimer_ns() - t0 > timeout_ns) spin_timeout_trap(what, static_cast<int>(blockIdx.x), static_cast<int>(threadIdx.x));
+  } while (has_sentinel(v));
+  return v;
+}
+
+__global__ void __launch_bounds__(256) exchange_finish_poll_kernel(XchgPollArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();                                   // my GEMM (previous kernel of the stream) has pushed all of its tiles
+  const bool tr = a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  if (tr) a.trace[0] = globaltimer_ns();
+  const bool one_shot = a.one_shot != 0;
+  const int Ns = one_shot ? a.N : a.N / a.world;
+  const int vpr = Ns >> 3;                      // 16-byte vectors per slot row
+  const long long nv = static_cast<long long>(a.M) * vpr;
+  const size_t slot = static_cast<size_t>(a.M) * Ns;
+  const size_t col0 = one_shot ? 0 : static_cast<size_t>(a.rank) * Ns;
+  const uint4 sent = make_uint4(kSentinel2, kSentinel2, kSentinel2, kSentinel2);
+  const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long nthr = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = tid; i < nv; i += nthr) {
+    const int row = static_cast<int>(i / vpr), c8 = static_cast<int>(i - static_cast<long long>(row) * vpr);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int s = 0; s < a.world; ++s) {
+      uint4* sp = reinterpret_cast<uint4*>(a.recv + s * slot + static_cast<size_t>(row) * Ns) + c8;
+      H8 v;
+      v.u = poll_vec(sp, a.timeout_ns, 41);
+      *sp = sent;                                // consumed: re-arm the slot for the exchange after the next one
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(v.h2[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+    const size_t off = static_cast<size_t>(row) * a.N + col0 + static_cast<size_t>(c8) * 8;
+    H8 r, o;
+    if (a.residual != nullptr) r.u = *reinterpret_cast<const uint4*>(a.residual + off);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __half2 y2 = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+      if (a.residual != nullptr) {
+        const float2 yf = __half22float2(y2), rf = __half22float2(r.h2[j]);
+        y2 = __floats2half2_rn(__fadd_rn(yf.x, rf.x), __fadd_rn(yf.y, rf.y));
+      }
+      o.h2[j] = y2;
+    }
+    if (a.reset != nullptr) *reinterpret_cast<uint4*>(a.reset + off) = sent;   // (after the residual read of the same vector)
+    if (one_shot) {
+      *reinterpret_cast<uint4*>(a.result[a.rank] + off) = o.u;
+    } else if (a.mc_result != nullptr) {
+      asm volatile("multimem.st.relaxed.sys.global.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(a.mc_result + off), "r"(o.u.x), "r"(o.u.y),
+                   "r"(o.u.z), "r"(o.u.w)
+                   : "memory");
+    } else {
+      for (int p = 0; p < a.world; ++p) *reinterpret_cast<uint4*>(a.result[p] + off) = o.u;
+    }
+  }
+  if (tr) a.trace[3] = globaltimer_ns();
+  if (!one_shot) {
+    // the other ranks' slices: re-arm the dead buffer, then wait for the owners' stores to land here
+    const int vprN = a.N >> 3;
+    const long long nvN = static_cast<long long>(a.M) * vprN;
+    const int lo = static_cast<int>(col0 >> 3), hi = lo + vpr;
+    for (long long i = tid; i < nvN; i += nthr) {
+      const int c = static_cast<int>(i % vprN);
+      if (c >= lo && c < hi) {                  // my own slice: re-armed above; a multicast store comes back through the switch
+        if (a.mc_result != nullptr) (void)poll_vec(reinterpret_cast<const uint4*>(a.result[a.rank]) + i, a.timeout_ns, 43);
+        continue;
+      }
+      if (a.reset != nullptr) *(reinterpret_cast<uint4*>(a.reset) + i) = sent;
+      (void)poll_vec(reinterpret_cast<const uint4*>(a.result[a.rank]) + i, a.timeout_ns, 42);
+    }
+  }
+  if (tr) a.trace[7] = globaltimer_ns();
+}
+
 __global__ void pingpong_kernel(uint32_t* mine, uint32_t* peer, uint32_t* mc, int iters, int rank, unsigned long long* out_ns) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const uint64_t t0 = globaltimer_ns();

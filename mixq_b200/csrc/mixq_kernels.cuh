@@ -76,6 +76,21 @@ struct XchgFinishArgs {
   unsigned long long* trace;   // tuning aid: 8 globaltimer stamps of block 0 (mixq_set_trace_buffer) or nullptr
 };
 __global__ void exchange_finish_kernel(XchgFinishArgs a);
+// The same second half WITHOUT flags or fences: the data is its own signal.  Receive slots and result buffers hold a sentinel
+// (fp16 0xFFFF: a NaN payload no arithmetic produces — hardware NaNs are 0x7FFF) until a peer's store lands; a reader spins on
+// the vector it needs until no half of it is the sentinel, and whoever consumes a vector puts the sentinel back.
+struct XchgPollArgs {
+  __half* recv;                // local: [world][M, Ns] receive slots of this exchange (one_shot: [world][M, N])
+  __half* result[kMaxPeers];   // every rank's result buffer [M, N] of this exchange as mapped here (own rank: local)
+  __half* mc_result;           // multicast address of the result buffer, or nullptr
+  __half* reset;               // local: the OTHER result buffer (last read, as the residual, by this launch): sentinel-filled here
+  const __half* residual;      // local [M, N] or nullptr
+  int M, N, world, rank;
+  int one_shot;
+  unsigned long long timeout_ns;
+  unsigned long long* trace;
+};
+__global__ void exchange_finish_poll_kernel(XchgPollArgs a);
 // tuning aid: `iters` flag round trips between two ranks inside one launch; *out_ns = elapsed nanoseconds (rank 0)
 __global__ void pingpong_kernel(uint32_t* mine, uint32_t* peer, uint32_t* mc, int iters, int rank, unsigned long long* out_ns);
 

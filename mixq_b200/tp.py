@@ -278,16 +278,22 @@ class PushExchange:
     transfer rides under the GEMM's own tail.  All-gather half: `reduce(residual)` launches the small finish kernel — handshake,
     local fp32 reduction of this rank's slice in rank order (+ residual, a separate fp16 rounding), broadcast of the slice into
     every rank's result buffer (multimem.st through the NVSwitch when a multicast mapping exists), handshake.
-    Bit-identical on all ranks and equal to oracle.mixq_oracle.tp_exchange (rank-order fp32 sum)."""
+    Bit-identical on all ranks and equal to oracle.mixq_oracle.tp_exchange (rank-order fp32 sum).
+    The returned result buffer is valid until the NEXT reduce() has run (which re-arms it in the polling form)."""
 
     fused = True
     two_shot = True
 
     def __init__(self, rows: int, cols: int, rank: int, world: int, group=None, device="cuda", multicast: bool = True,
-                 one_shot=None):
+                 one_shot=None, sync=None):
         from . import _lib
         import os
         import torch.distributed as dist
+        # sync: "poll" — no flags, the data is its own signal (mixq_exchange_finish_poll; buffers are armed with the fp16
+        # sentinel 0xFFFF and re-armed by their consumer); "flags" — the release/acquire handshake (mixq_exchange_finish).
+        self.sync = sync or os.environ.get("MIXQ_TP_SYNC", "poll")
+        if self.sync not in ("poll", "flags"):
+            raise ValueError("sync must be 'poll' or 'flags'")
         if not (2 <= world <= 8):
             raise ValueError("PushExchange needs 2..8 ranks on one node")
         if cols % world or (cols // world) % 128:
@@ -307,7 +313,7 @@ class PushExchange:
         nb = rows * cols * 2
         rb = nb * (world if self.one_shot else 1)          # receive area per exchange buffer
         local, ptrs, mc, self._keep, self._close = _symmetric_alloc(2 * rb + 2 * nb + 256, rank, world, group, device)
-        if not multicast:
+        if not multicast or os.environ.get("MIXQ_TP_BCAST", "mc") == "peer":
             mc = 0
         self.multicast = mc != 0 and not self.one_shot
         self._local, self._ptrs, self._mc = local, ptrs, mc
@@ -316,21 +322,30 @@ class PushExchange:
         res0, fl = 2 * rb, 2 * rb + 2 * nb
         slot = nb if self.one_shot else rows * self.ns * 2
         for b in range(2):
-            a = _lib.ExchangeFinishArgs()
+            if self.sync == "poll":
+                a = _lib.ExchangePollArgs()
+                a.reset = local + res0 + (b ^ 1) * nb
+            else:
+                a = _lib.ExchangeFinishArgs()
+                for r in range(world):
+                    a.flags[r] = ptrs[r] + fl
+                a.mc_flags = (mc + fl) if mc else 0
+                a.epoch = self._state.data_ptr()
+                a.done = self._state.data_ptr() + 4
             a.recv = local + b * rb
             for r in range(world):
                 a.result[r] = ptrs[r] + res0 + b * nb
-                a.flags[r] = ptrs[r] + fl
             a.mc_result = (mc + res0 + b * nb) if self.multicast else 0
-            a.mc_flags = (mc + fl) if mc else 0
-            a.epoch = self._state.data_ptr()
-            a.done = self._state.data_ptr() + 4
             a.M, a.N, a.world, a.rank = rows, cols, world, rank
             a.one_shot = 1 if self.one_shot else 0
             self._fin.append(a)
             self._targets.append([ptrs[j] + b * rb + rank * slot for j in range(world)])
         self._views = [_DeviceBuffer(local + res0 + b * nb, (rows, cols), "<f2") for b in range(2)]
         self.results = [torch.as_tensor(v, device=device) for v in self._views]
+        if self.sync == "poll":
+            # arm the receive slots and both result buffers with the sentinel
+            self._arm = _DeviceBuffer(local, ((2 * rb + 2 * nb) // 2,), "<i2")
+            torch.as_tensor(self._arm, device=device).fill_(-1)
         self.buf = 0
         torch.cuda.synchronize()
         dist.barrier(group=group)       # nobody pushes or signals before everybody has mapped everything
@@ -345,15 +360,15 @@ class PushExchange:
     def reduce(self, residual, out: torch.Tensor = None) -> torch.Tensor:
         a = self._fin[self.buf]
         a.residual = 0 if residual is None else residual.data_ptr()
-        self._check(self.lib.mixq_exchange_finish(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
-                    "exchange_finish")
+        fn = self.lib.mixq_exchange_finish_poll if self.sync == "poll" else self.lib.mixq_exchange_finish
+        self._check(fn(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "exchange_finish")
         out = self.results[self.buf]
         self.buf ^= 1
         return out
 
     def close(self):
         torch.cuda.synchronize()
-        self.results, self._views = [], []
+        self.results, self._views, self._arm = [], [], None
         self._close()
         self._close = lambda: None
         self._keep = None

@@ -234,8 +234,8 @@ def test_launch_plan_headline_shapes():
     assert (p.passes, p.pass_cols, p.pass_buffers) == (4, 96, 2)
     rc, p = _plan(32, 4096, 4096, n=41)                         # C1: M <= 128 runs the 1-CTA kernel
     assert rc == 0 and p.two_cta == 0 and p.tile_w in (128, 256) and p.units == 148
-    rc, p = _plan(512, 12288, 4096, bit=4, n=128)               # W4 runs the 1-CTA kernel as well
-    assert rc == 0 and p.two_cta == 0
+    rc, p = _plan(512, 12288, 4096, bit=4, n=128)               # W4: the same 2-CTA kernel, 3 main stages + the packed-row ring
+    assert rc == 0 and p.two_cta == 1 and p.nstages == 3 and p.acc_slots == 1
     rc, _ = _plan(64, 11008, 4096, pair=1)                      # the pair launch needs the 2-CTA kernel
     assert rc != 0 and b"pair" in _lib.load().mixq_last_error()
 

@@ -84,9 +84,9 @@ def main():
     kinds = [("peer one-shot", lambda: PeerExchange(M, H, rank, world, two_shot=False)),
              ("peer two-shot", lambda: PeerExchange(M, H, rank, world, two_shot=True)),
              ("multicast all-reduce", lambda: MulticastExchange(M, H, rank, world)),
-             ("push finish (multicast)", lambda: PushExchange(M, H, rank, world, multicast=True, one_shot=False)),
-             ("push finish (peer stores)", lambda: PushExchange(M, H, rank, world, multicast=False, one_shot=False)),
-             ("push finish (one-shot)", lambda: PushExchange(M, H, rank, world, one_shot=True))]
+             ("push finish (multicast)", lambda: PushExchange(M, H, rank, world, multicast=True, one_shot=False, sync="flags")),
+             ("push finish (peer stores)", lambda: PushExchange(M, H, rank, world, multicast=False, one_shot=False, sync="flags")),
+             ("push finish (one-shot)", lambda: PushExchange(M, H, rank, world, one_shot=True, sync="flags"))]
     for name, mk in kinds:
         try:
             ex = mk()
@@ -107,6 +107,43 @@ def main():
             lib.mixq_set_trace_buffer(None)
             med = [sorted(s[i] for s in stamps)[len(stamps) // 2] for i in range(8)]
             out["push finish phases us (entry, sig0 sent, wait0 done, data done, fence done, last block, sig1 sent, wait1 done)"] = [round(v, 2) for v in med]
+        del g
+        ex.close()
+        dist.barrier()
+    # the whole fused exchange as the decoder runs it: row-parallel o_proj (K = 4096 / world) pushing from its epilogue + the
+    # finish kernel, against the same Linear alone -> what one exchange adds to the step
+    from mixq_b200.cache import MixLibCache
+    from mixq_b200.linear import MixLinear_GEMM
+    Kr = 4096 // world
+    gg = torch.Generator(device="cuda").manual_seed(3 + rank)
+
+    class W:
+        weight = (torch.randn(H, Kr, generator=gg, device="cuda") * 0.02).half()
+        bias = None
+        out_features, in_features = H, Kr
+    cache = MixLibCache(inputdim=M, sigma=6, bit=8)
+    lin = MixLinear_GEMM.from_linear(W, 8, cache=cache)
+    x = torch.randn(M, Kr, generator=gg, device="cuda")
+    x[:, 3::97] *= 20
+    x = x.half()
+    for _ in range(2):
+        lin(x.clone(), None, True)
+    us_lin, g = time_graph(lambda: lin(x, None, True))
+    out["row-parallel o_proj alone us"] = round(us_lin, 2)
+    del g
+    for name, kw in (("poll two-phase multicast", dict(sync="poll", one_shot=False)),
+                     ("poll two-phase peer stores", dict(sync="poll", one_shot=False, multicast=False)),
+                     ("poll one-shot", dict(sync="poll", one_shot=True)),
+                     ("flags two-phase multicast", dict(sync="flags", one_shot=False)),
+                     ("flags one-shot", dict(sync="flags", one_shot=True))):
+        ex = PushExchange(M, H, rank, world, **kw)
+
+        def both():
+            lin(x, None, True, push=ex.push_targets())
+            ex.reduce(h)
+        us, g = time_graph(both)
+        out[f"o_proj + fused exchange ({name}) us"] = round(us, 2)
+        out[f"fused exchange ({name}) adds us"] = round(us - us_lin, 2)
         del g
         ex.close()
         dist.barrier()

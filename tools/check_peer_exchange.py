@@ -146,17 +146,17 @@ def check_decoder(kind, rank, world):
     return rel, rel1
 
 
-def check_push(rank, world, multicast, one_shot=None):
+def check_push(rank, world, multicast, one_shot=None, sync="poll"):
     """The fused exchange: a real row-parallel MixLinear pushes its partial from the GEMM epilogue (both GEMM kernels: M = 512
     and M = 128), the finish kernel reduces + broadcasts; reference = the same Linear's partials (all-gathered over NCCL) summed
     in fp32 in rank order, rounded to fp16, + residual — bit-exact, identical on all ranks, eager and graph-replayed."""
     from mixq_b200.cache import MixLibCache
     from mixq_b200.linear import MixLinear_GEMM
-    kind = ("push" if multicast else "push-nomc") + ("" if one_shot is None else ("-oneshot" if one_shot else "-twophase"))
+    kind = ("push" if multicast else "push-nomc") + ("" if one_shot is None else ("-oneshot" if one_shot else "-twophase")) + "-" + sync
     for M, N, Ktot in ((512, 4096, 4096), (128, 2048, 1024)):
         Kr = Ktot // world
         g = torch.Generator(device="cuda").manual_seed(77 + rank)
-        ex = PushExchange(M, N, rank, world, multicast=multicast, one_shot=one_shot)
+        ex = PushExchange(M, N, rank, world, multicast=multicast, one_shot=one_shot, sync=sync)
         cache = MixLibCache(inputdim=M, sigma=6, bit=8)
 
         class W:
@@ -230,6 +230,15 @@ def check_push(rank, world, multicast, one_shot=None):
             torch.cuda.synchronize()
             for j in range(2):
                 assert torch.equal(outs[j], refs[j]), f"rank {rank} {kind} M={M} graph replay {rep} exchange {j}"
+        # ranks free-running: 50 replays back to back with no host synchronisation, rank r delayed by r * 200 us at the start
+        torch.cuda._sleep(int(rank * 200e-6 * 1.9e9))
+        for rep in range(50):
+            for j in range(2):
+                xw[j].copy_(xs[j])
+            gph.replay()
+        torch.cuda.synchronize()
+        for j in range(2):
+            assert torch.equal(outs[j], refs[j]), f"rank {rank} {kind} M={M} free-running replays exchange {j}"
         del gph
         ex.close()
         dist.barrier()
@@ -245,8 +254,9 @@ def main():
     kinds = [os.environ["CHECK_KIND"]] if os.environ.get("CHECK_KIND") else ["push", "push-nomc", "peer", "multicast"]
     for kind in kinds:
         if kind.startswith("push"):
-            for one_shot in (True, False):
-                check_push(rank, world, multicast=(kind == "push"), one_shot=one_shot)
+            for sync in ("poll", "flags"):
+                for one_shot in (True, False):
+                    check_push(rank, world, multicast=(kind == "push"), one_shot=one_shot, sync=sync)
             check_decoder(kind, rank, world)
         else:
             check_kind(kind, rank, world)

@@ -20,9 +20,11 @@ run tp$N $N
 run c4_tp$N $N --model llama-3-8b
 if [ "$N" = "8" ]; then run c5_tp8 8 --model llama-2-70b --batch 128; fi
 if [ "$N" = "4" ]; then MIXQ_TP_ONE_SHOT=1 run tp4_oneshot 4; fi
+if [ -n "$BCAST_PEER_TOO" ]; then MIXQ_TP_BCAST=peer run tp${N}_peerbcast $N; fi
+if [ -n "$FLAGS_TOO" ]; then MIXQ_TP_SYNC=flags run tp${N}_flags $N; fi
 python - <<'PY'
 import json, glob
-for f in sorted(glob.glob("gpurun_out/r02_bench_tp[48]*.json") + glob.glob("gpurun_out/r02_bench_c[45]_*.json")):
+for f in sorted(glob.glob("gpurun_out/r02_bench_tp[248]*.json") + glob.glob("gpurun_out/r02_bench_c[45]_*.json")):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
         tp = d.get("tp_parity") or {}
