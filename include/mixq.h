@@ -234,6 +234,8 @@ int mixq_quik_addend(const void* meta, const void* reduced_w, const void* fp_res
 /* Tuning aid: `iters` flag round trips between two ranks inside ONE launch (rank 0 writes rank 1's word, rank 1 answers);
  * *out_ns (device uint64) = elapsed nanoseconds.  mine / peer: this rank's word and the other rank's word as mapped here;
  * mc: multicast address of the word (then both sides use multimem.red) or NULL. */
+/* Re-read the MIXQ_DEBUG_* tuning variables (they are otherwise read once, when the library loads — never per launch). */
+void mixq_reload_debug_env(void);
 int mixq_debug_pingpong(void* mine, void* peer, void* mc, int iters, int rank, void* out_ns, void* stream);
 
 /* elementwise gate *= up (mlp.py:64) kept for the decode harness */

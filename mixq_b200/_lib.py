@@ -163,6 +163,7 @@ SIGNATURES = {
     "mixq_rope_attention_decode_quant": [_vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _f, _vp, _i, _vp, _i, _vp, _vp, _i, _vp],
     "mixq_quik_quantize": [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
     "mixq_quik_addend": [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp],
+    "mixq_reload_debug_env": [],
     "mixq_debug_pingpong": [_vp, _vp, _vp, _i, _i, _vp, _vp],
     "mixq_mul_inplace": [_vp, _vp, _ll, _vp],
     "mixq_peer_alloc": [C.c_ulonglong, C.POINTER(C.c_void_p)],
@@ -184,7 +185,7 @@ SIGNATURES = {
     "mixq_launch_count": [],
     "mixq_last_error": [],
 }
-_RESTYPES = {"mixq_launch_count": C.c_ulonglong, "mixq_last_error": C.c_char_p}
+_RESTYPES = {"mixq_launch_count": C.c_ulonglong, "mixq_last_error": C.c_char_p, "mixq_reload_debug_env": None}
 
 _lib = None
 

@@ -193,6 +193,9 @@ class AutoForCausalLM:
         config = json.load(open(os.path.join(quant_path, "config.json")))
         config["max_new_tokens"] = 2048 if max_new_tokens is None else max_new_tokens     # base.py:253-260
         qc = ck.load_quant_config(quant_path)
+        if int(qc.get("w_bit", 0)) not in (4, 8):
+            raise ValueError(f"{quant_path}: no quant_config.json with w_bit 4 or 8 — not a quantised checkpoint (the reference "
+                             "quantises online in that case, base.py:252-258: use from_pretrained(...).quantize(...))")
         if qc.get("version") == "QUIK":
             raise NotImplementedError("QUIK checkpoints: build MixedQLinear modules with mixq_b200.qlinear (fuse_layers is False there: base.py:186-188)")
         if cache is None:

@@ -199,28 +199,34 @@ def load_state_dict(save_dir: str, safetensors: bool = False) -> Dict[str, torch
     return sd
 
 
-def load_quant_config(save_dir: str) -> dict:
-    """base.py:232-262: defaults when quant_config.json is missing."""
+def load_quant_config(save_dir: str, version: str = "Mix") -> dict:
+    """base.py:249-258: quant_config.json, or {"w_bit": 0, "version": version} when the file is missing — the reference's
+    marker for "not a quantised checkpoint, quantise online"."""
     path = os.path.join(save_dir, QUANT_CONFIG_NAME)
     if os.path.exists(path):
-        return json.load(open(path))
-    return {"w_bit": 8, "version": "MIX", "q_group_size": 128}
+        with open(path) as f:
+            return json.load(f)
+    return {"w_bit": 0, "version": version}
 
 
 def load_quantized(save_dir: str, cache=None, dev="cuda", safetensors: bool = False, fuse_layers: bool = False,
-                   eight_bit_names: Iterable[str] = ("o_proj", "down_proj")
+                   eight_bit_names: Iterable[str] = ("down_proj", "o_proj", "fc_out")
                    ) -> Tuple[Dict[str, MixLinear_GEMM], Dict[str, torch.Tensor], dict]:
     """from_quantized (base.py:162-229) for the quantised Linears: returns ({prefix: MixLinear}, remaining tensors, quant_config).
-    `eight_bit_names`: modules that stay 8-bit in a 4-bit model (utils/module.py:2, base.py:308-312).  With `fuse_layers`
+    `eight_bit_names`: modules that stay 8-bit in a 4-bit model — matched as SUBSTRINGS of the module name, as the reference
+    does (utils/module.py:2 `eightbit_only_name`, base.py:308-312).  With `fuse_layers`
     every `<p>.q_proj / k_proj / v_proj` triple is replaced by `<p>.W_pack` (llama.py:98-166)."""
     qc = load_quant_config(save_dir)
+    if int(qc.get("w_bit", 0)) not in (4, 8):
+        raise ValueError(f"{save_dir}: no {QUANT_CONFIG_NAME} with w_bit 4 or 8 (w_bit 0 = not a quantised checkpoint; quantise it "
+                         "with AutoForCausalLM.from_pretrained(...).quantize(...) first)")
     sd = load_state_dict(save_dir, safetensors)
     prefixes = sorted({k[: -len(".q_weight")] for k in sd if k.endswith(".q_weight")})
     mods: Dict[str, MixLinear_GEMM] = {}
     used = set()
     for p in prefixes:
         bit = qc["w_bit"]
-        if bit == 4 and p.rsplit(".", 1)[-1] in set(eight_bit_names):
+        if bit == 4 and any(key in p for key in eight_bit_names):
             bit = 8
         mods[p] = linear_from_state(sd, p, bit, cache=cache, dev=dev)
         used.update(k for k in sd if k.startswith(p + "."))

@@ -48,6 +48,21 @@ std::atomic<int> g_barrier_mode{[] {
 }()};
 int barrier_mode() { return g_barrier_mode.load(std::memory_order_relaxed); }
 
+// MIXQ_DEBUG_* tuning knobs: read once when the library loads (and again by mixq_reload_debug_env, for tests that change them),
+// never on the launch path.
+struct DebugEnv {
+  std::atomic<int> katoms{0}, stage_bytes{0}, stages{0}, ablate{0};
+  void load() {
+    auto rd = [](const char* n) { const char* e = getenv(n); return e ? atoi(e) : 0; };
+    katoms.store(rd("MIXQ_DEBUG_KATOMS"));
+    stage_bytes.store(rd("MIXQ_DEBUG_STAGE_BYTES"));
+    stages.store(rd("MIXQ_DEBUG_STAGES"));
+    ablate.store(rd("MIXQ_DEBUG_ABLATE"));
+  }
+  DebugEnv() { load(); }
+};
+DebugEnv g_dbg;
+
 // Launch attributes shared by every kernel of the library.  A kernel with a grid barrier needs all of its CTAs
 // co-resident: a cooperative launch guarantees it; under PDL the grid is exactly one CTA per SM and the CTAs of the
 // previous kernel leave without waiting for anybody, so ours all become resident as those exit.
@@ -133,6 +148,36 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// Encoded tensor maps are pure functions of (base address, geometry): a module calling with the same buffers gets its maps from
+// this cache instead of 4-7 cuTensorMapEncodeTiled calls per launch (the eager call pattern of benchbitsand.py; under a CUDA
+// graph the launch path does not run at all).
+struct MapKey {
+  uint64_t v[8];
+  bool operator==(const MapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    for (uint64_t x : k.v) h = (h ^ x) * 0xFF51AFD7ED558CCDull + (h >> 29);
+    return static_cast<size_t>(h);
+  }
+};
+std::mutex g_map_mu;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+constexpr size_t kMapCacheCap = 8192;      // ~1 MB; cleared when full (a 70B model has 80 x 4 modules x <= 7 maps)
+bool map_cache_get(const MapKey& k, CUtensorMap* m) {
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  auto it = g_maps.find(k);
+  if (it == g_maps.end()) return false;
+  *m = it->second;
+  return true;
+}
+void map_cache_put(const MapKey& k, const CUtensorMap& m) {
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  if (g_maps.size() >= kMapCacheCap) g_maps.clear();
+  g_maps.emplace(k, m);
+}
+
 // 2-D row-major tensor [rows, cols] of `elt` bytes, row pitch `pitch_bytes`; box = box_cols x box_rows.
 int make_map(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int elt, long long cols, long long rows,
              long long pitch_bytes, int box_cols, int box_rows, CUtensorMapSwizzle sw) {
@@ -140,6 +185,10 @@ int make_map(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int elt, l
   if (fn == nullptr) return fail(MIXQ_EDRIVER, "cuTensorMapEncodeTiled not available from the driver");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(MIXQ_EINVAL, "TMA operand not 16-byte aligned");
   if (pitch_bytes % 16 != 0) return fail(MIXQ_EINVAL, "TMA operand row pitch not a multiple of 16 bytes");
+  const MapKey key{{reinterpret_cast<uintptr_t>(ptr), static_cast<uint64_t>(dt) | (static_cast<uint64_t>(sw) << 32), static_cast<uint64_t>(cols),
+                    static_cast<uint64_t>(rows), static_cast<uint64_t>(pitch_bytes), static_cast<uint64_t>(box_cols),
+                    static_cast<uint64_t>(box_rows), 2}};
+  if (map_cache_get(key, m)) return 0;
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstr[1] = {static_cast<cuuint64_t>(pitch_bytes)};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
@@ -148,6 +197,7 @@ int make_map(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int elt, l
   CUresult r = fn(m, dt, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(MIXQ_EDRIVER, "cuTensorMapEncodeTiled failed (CUresult " + std::to_string(r) + ")");
+  map_cache_put(key, *m);
   return 0;
 }
 
@@ -157,6 +207,9 @@ int make_map_katoms(CUtensorMap* m, const void* ptr, long long K, long long rows
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return fail(MIXQ_EDRIVER, "cuTensorMapEncodeTiled not available from the driver");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(MIXQ_EINVAL, "TMA operand not 16-byte aligned");
+  const MapKey key{{reinterpret_cast<uintptr_t>(ptr), static_cast<uint64_t>(K), static_cast<uint64_t>(rows), static_cast<uint64_t>(box_rows),
+                    static_cast<uint64_t>(atoms), 0, 0, 3}};
+  if (map_cache_get(key, m)) return 0;
   cuuint64_t gdim[3] = {128, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(K / 128)};
   cuuint64_t gstr[2] = {static_cast<cuuint64_t>(K), 128};
   cuuint32_t box[3] = {128, static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(atoms)};
@@ -164,6 +217,7 @@ int make_map_katoms(CUtensorMap* m, const void* ptr, long long K, long long rows
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(MIXQ_EDRIVER, "cuTensorMapEncodeTiled (3-D) failed (CUresult " + std::to_string(r) + ")");
+  map_cache_put(key, *m);
   return 0;
 }
 
@@ -316,17 +370,17 @@ int plan_gemm(int M, int N, int K, int bit, int n_out, bool pair, int tile_req, 
   // narrow tiles are paced by the TMA op count (one op ~340 clocks of the SM's TMA unit whatever its size): two k-atoms
   // (256 bytes of K) per op and pipeline stage whenever at least three such stages fit
   int k_atoms = (two_cta && !w4 && K % 128 == 0 && K >= 256 && bn <= 256) ? 2 : 1;
-  if (const char* e = getenv("MIXQ_DEBUG_KATOMS")) { const int v = atoi(e); if (v == 1) k_atoms = 1; }
+  if (g_dbg.katoms.load(std::memory_order_relaxed) == 1) k_atoms = 1;
   int stage2 = 0, nstages2 = 0;
   for (;;) {
     stage2 = k_atoms * (Gemm2Cfg::A_BYTES + (bn / 2) * 128);
     stage2 = (stage2 + 1023) / 1024 * 1024;
-    if (const char* e = getenv("MIXQ_DEBUG_STAGE_BYTES")) { const int v = atoi(e); if (v >= stage2 && v % 1024 == 0) stage2 = v; }
+    if (const int v = g_dbg.stage_bytes.load(std::memory_order_relaxed); v >= stage2 && v % 1024 == 0) stage2 = v;
     nstages2 = Gemm2Cfg::PIPE_BYTES / stage2;
     if (nstages2 > Gemm2Cfg::MAX_STAGES) nstages2 = Gemm2Cfg::MAX_STAGES;
     if (w4 && two_cta && nstages2 > 3) nstages2 = 3;   // W4: three main stages cover the unpack -> MMA -> commit chain; the rest of
                                                       // the pipeline memory is the packed-row ring that covers HBM latency
-    if (const char* e = getenv("MIXQ_DEBUG_STAGES")) { const int v = atoi(e); if (v >= 2 && v < nstages2) nstages2 = v; }
+    if (const int v = g_dbg.stages.load(std::memory_order_relaxed); v >= 2 && v < nstages2) nstages2 = v;
     // the outlier k-blocks of a tile stay resident in the ring during the epilogue passes: with the big stages they may not fit
     if (k_atoms == 2 && (nstages2 < 3 || (n_out + 63) / 64 > nstages2 - 1)) { k_atoms = 1; continue; }
     break;
@@ -355,8 +409,7 @@ int plan_gemm(int M, int N, int K, int bit, int n_out, bool pair, int tile_req, 
     g->tiles = ((M + 255) / 256) * ((N + wout - 1) / wout);
     g->units = npairs;
     g->tiles_per_unit = (g->tiles + npairs - 1) / npairs;
-    bool single = false;
-    if (const char* e = getenv("MIXQ_DEBUG_ABLATE")) single = (atoi(e) & 16) != 0;
+    const bool single = (g_dbg.ablate.load(std::memory_order_relaxed) & 16) != 0;
     g->tmem = plan_tmem(bn, n_out > 0, w4 ? 1 : g->tiles_per_unit, single);
   } else {
     g->stage_bytes = w4 ? (bn == 256 ? GemmCfg<256, true>::STAGE_BYTES : GemmCfg<128, true>::STAGE_BYTES)
@@ -540,7 +593,7 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
   p.k_atoms = ka2 ? 2 : 1;
   p.w4 = (w4 && two_cta) ? 1 : 0;
   p.npacked = gp.npacked;
-  if (const char* e = getenv("MIXQ_DEBUG_ABLATE")) p.ablate = atoi(e);
+  p.ablate = g_dbg.ablate.load(std::memory_order_relaxed);
   p.q_w = static_cast<const uint8_t*>(c.q_w);
   p.q_w_pitch = w4 ? c.K / 2 : c.K;
   if (two_cta) {
@@ -1104,6 +1157,8 @@ int mixq_exchange_finish_poll(const mixq_exchange_poll_args* a, void* stream) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
+
+void mixq_reload_debug_env(void) { g_dbg.load(); }
 
 int mixq_debug_pingpong(void* mine, void* peer, void* mc, int iters, int rank, void* out_ns, void* stream) {
   pingpong_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<uint32_t*>(mine), static_cast<uint32_t*>(peer),

@@ -426,6 +426,8 @@ class LlamaDecoder:
         models/llama.py:98-166, o_proj / down_proj kept 8-bit in 4-bit models) instead of random-initialising."""
         from . import checkpoint as ck
         qc = ck.load_quant_config(save_dir)
+        if int(qc.get("w_bit", 0)) not in (4, 8):
+            raise ValueError(f"{save_dir}: not a quantised checkpoint (no quant_config.json with w_bit 4 or 8)")
         self = cls.__new__(cls)
         self.cfg, self.batch, self.bit, self.device = cfg, batch, int(qc["w_bit"]), device
         self.rank, self.world, self.group = 0, 1, None

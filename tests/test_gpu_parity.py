@@ -497,9 +497,11 @@ def test_launch_modes_bit_identical(lib, monkeypatch):
                 monkeypatch.delenv("MIXQ_DEBUG_KATOMS", raising=False)
             else:
                 monkeypatch.setenv("MIXQ_DEBUG_KATOMS", katoms)
+            lib.mixq_reload_debug_env()
             ys.append(host(run_fused(lib, x, qw, ws, cols, wc, 8, residual=res)["y"]))
         # how the grid barrier's co-residency is guaranteed: PDL (default), cooperative launch, or no barrier at all (split)
         monkeypatch.delenv("MIXQ_DEBUG_KATOMS", raising=False)
+        lib.mixq_reload_debug_env()
         for mode in (1, 2):
             check(lib.mixq_set_grid_barrier_mode(mode))
             t = run_fused(lib, x, qw, ws, cols, wc, 8, residual=res)

@@ -104,6 +104,15 @@ def main():
                 run_all()
                 torch.cuda.synchronize()
                 continue
+            # host cost of one eager C-ABI call (argument checks + launch plan + tensor maps + cudaLaunchKernelEx), launch queue
+            # not full: wall clock over the enqueue loop only
+            import time
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(8):
+                run_all()
+            host_us = (time.perf_counter() - t0) * 1e6 / (8 * len(arglist))
+            torch.cuda.synchronize()
             gr = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gr):
                 run_all()
@@ -120,7 +129,7 @@ def main():
             fl = 2.0 * M * N * K * nl
             by = nl * (N * K * args.bit / 8 + 2 * N + 2 * n * N) + 2 * M * K + 2 * M * N
             print(json.dumps({"M": M, "N": N, "K": K, "bit": args.bit, "mode": mode, "n_out": n, "tile": args.tile,
-                              "us": round(us, 2), "tflops": round(fl / us / 1e6, 1), "gbs": round(by / us / 1e3, 1)}), flush=True)
+                              "us": round(us, 2), "host_us_per_eager_call": round(host_us, 2), "tflops": round(fl / us / 1e6, 1), "gbs": round(by / us / 1e3, 1)}), flush=True)
             del gr
         del copies
 
