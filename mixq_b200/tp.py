@@ -299,12 +299,13 @@ class PushExchange:
         if cols % world or (cols // world) % 128:
             raise ValueError("hidden size / world must be a multiple of 128 (a GEMM tile may not straddle two ranks' slices)")
         if one_shot is None:
-            # one-shot: every rank pushes its WHOLE partial to every rank ((world-1) n fp16 over NVLink, hidden under the GEMM)
-            # and one handshake remains; two-phase: reduce-scatter push + broadcast, 2 (world-1)/world n and two handshakes.
-            # A flag takes 2.8 us one way over NVSwitch (tools/bench_exchange.py): one-shot wins while the extra bytes stay
-            # hidden, i.e. for two ranks.
+            # one-shot: every rank pushes its WHOLE partial to every rank ((world-1) n fp16 over NVLink) and reduces all of it;
+            # two-phase: reduce-scatter push + broadcast of the reduced slice, 2 (world-1)/world n.  Measured with the polling
+            # form (profiles/r02_exchange_anatomy_tp*_poll.json, what one exchange adds to the row-parallel o_proj): 2 ranks
+            # 8.4 us two-phase vs 11.4 one-shot; 8 ranks 18.9 vs 65.9 -> two-phase everywhere.  (With the flag protocol one-shot
+            # won at 2 ranks: it saves a handshake.)
             env = os.environ.get("MIXQ_TP_ONE_SHOT")
-            one_shot = (world == 2) if env is None else env == "1"
+            one_shot = (world == 2 and self.sync == "flags") if env is None else env == "1"
         self.one_shot = bool(one_shot)
         self.two_shot = not self.one_shot
         self.lib, self._check = _lib.load(), _lib.check
@@ -313,7 +314,11 @@ class PushExchange:
         nb = rows * cols * 2
         rb = nb * (world if self.one_shot else 1)          # receive area per exchange buffer
         local, ptrs, mc, self._keep, self._close = _symmetric_alloc(2 * rb + 2 * nb + 256, rank, world, group, device)
-        if not multicast or os.environ.get("MIXQ_TP_BCAST", "mc") == "peer":
+        # broadcast of the reduced slice: multimem.st through the switch (one store, (w-1)/w of the egress saved) or plain
+        # stores to every peer.  Measured: peer stores win at 2 ranks (8.4 vs 11.2 us: the own copy stays local), multicast
+        # at 8 (18.9 vs 19.5).  MIXQ_TP_BCAST=mc|peer overrides.
+        bcast = os.environ.get("MIXQ_TP_BCAST", "peer" if world == 2 else "mc")
+        if not multicast or bcast == "peer":
             mc = 0
         self.multicast = mc != 0 and not self.one_shot
         self._local, self._ptrs, self._mc = local, ptrs, mc
