@@ -436,7 +436,13 @@ def run_mixq(args):
                 return m.forward_swiglu_fused(ups[i], h, model.layers[0]["ln2"], cfg.eps)
             if kind == "gate_proj":
                 return m.forward_without_preconditionFusedSilu(h, model.cache)
+            if kind == "o_proj" and o_quantized:
+                # as the step runs it: the attention kernel has quantised o_proj's input rows, no activation prologue left
+                return m.forward_quantized(B, residual=h) if world == 1 else m.forward_quantized(B)
             return m(xw, None, True, residual=h) if world == 1 else m(xw, None, True)
+        o_quantized = kind == "o_proj" and getattr(model, "fuse_attn_quant", False)
+        if o_quantized:           # every layer's o_proj shares the module cache: one ordinary call leaves q_x / x_scale / outliers there
+            mods[0](xw, None, True)
         if kind == "gate_proj":   # needs up_proj's q_x in the cache
             model.layers[0]["up_proj"].forward_norm_fused(h, model.layers[0]["ln2"], cfg.eps)
         # one CUDA graph holding this Linear of every layer (distinct weights: L2-cold, as in the step), so that the

@@ -338,6 +338,15 @@ typedef struct mixq_exchange_poll_args {
 } mixq_exchange_poll_args;
 int mixq_exchange_finish_poll(const mixq_exchange_poll_args* a, void* stream);
 
+/* The same exchange + the activation prologue of the MixLinear that consumes its result (fused/norm.py:24-33 in front of W_pack /
+ * up_proj+gate_proj): after the exchange every rank holds whole rows of the residual stream, and every rank would run the same
+ * RMSNorm -> ExtractOutliers -> FindRowScale -> quantise over them at the head of its next launch.  One CTA owns one token row
+ * here, so the row is normalised and quantised as soon as its last slice has landed: writes q_x int8 [M, N], x_scale fp16 [M],
+ * act_outliers fp16 [M, ld_ao] (normed values of columns ind[0..n_ind)) besides the result buffer.  The consumer runs
+ * mixq_linear_fused(skip_prologue = 1) — the reference's "fused" call mode.  Bit-identical to finish + separate prologue. */
+int mixq_exchange_finish_poll_quant(const mixq_exchange_poll_args* a, const void* norm_weight, float eps, const int32_t* ind,
+                                    int n_ind, void* act_outliers, int ld_ao, void* q_x, void* x_scale, int bit, void* stream);
+
 /* How long (milliseconds, default 120 000; environment MIXQ_PEER_TIMEOUT_MS) an exchange waits for a silent peer before the
  * kernel reports the stall (device printf + trap => a sticky CUDA error on the host).  Ranks drift apart by seconds around
  * host-synchronising phases (outlier discovery, graph capture, rank-0-only work): callers should still put a process-group

@@ -175,6 +175,7 @@ SIGNATURES = {
     "mixq_allreduce_multicast": [C.POINTER(McAllReduceArgs), _vp],
     "mixq_exchange_finish": [C.POINTER(ExchangeFinishArgs), _vp],
     "mixq_exchange_finish_poll": [C.POINTER(ExchangePollArgs), _vp],
+    "mixq_exchange_finish_poll_quant": [C.POINTER(ExchangePollArgs), _vp, _f, _vp, _i, _vp, _i, _vp, _vp, _i, _vp],
     "mixq_set_peer_timeout_ms": [_ll],
     "mixq_set_tile_n": [_i],
     "mixq_set_pdl": [_i],

@@ -200,6 +200,23 @@ __device__ __forceinline__ void epilogue_span(const LinearParams& p, uint32_t t_
 // of it; two epilogue warps per scheduler at ~260 SASS instructions per 16 columns): the variants below are templated on
 // what the call actually needs, address shared memory through 32-bit shared-window addresses (ld/st.shared, no generic
 // 64-bit pointer arithmetic), and bring residual / addend tiles in through the same coalesced staging path.
+// -DMIXQ_EPI_TRACE (tuning builds only): clock64 stamps of CTA 0 / warp 4 inside the outlier-pass epilogue, 8 per call,
+// at p.trace[1800 + 8 * call]
+#ifdef MIXQ_EPI_TRACE
+#define MIXQ_EPI_STAMP(j)                                                                                          \
+  do {                                                                                                             \
+    if (p.trace != nullptr && blockIdx.x == 0 && (threadIdx.x >> 5) == 4 && lane == 0 && p.trace[1799] < 24)       \
+      p.trace[1800 + 8 * p.trace[1799] + (j)] = static_cast<unsigned long long>(clock64());                                                  \
+  } while (0)
+#define MIXQ_EPI_NEXT()                                                                                            \
+  do {                                                                                                             \
+    if (p.trace != nullptr && blockIdx.x == 0 && (threadIdx.x >> 5) == 4 && lane == 0) p.trace[1799] += 1;         \
+  } while (0)
+#else
+#define MIXQ_EPI_STAMP(j) ((void)0)
+#define MIXQ_EPI_NEXT() ((void)0)
+#endif
+
 namespace mixq {
 
 constexpr int kEpiStageBytes = 32 * 128;
@@ -369,21 +386,27 @@ __device__ __forceinline__ void epilogue_run_coalesced(const LinearParams& p, ui
       for (int h = 0; h < (two ? 2 : 1); ++h) {
         uint32_t acc[16];
         uint32_t oacc[16];
+        MIXQ_EPI_STAMP(0 + 3 * h);
         tmem_ld_32x16(t_int + (g + h) * 16, acc);
         if (HAS_O) tmem_ld_32x16(t_outl + (g + h) * 16, oacc);
         tmem_ld_wait();
+        MIXQ_EPI_STAMP(1 + 3 * h);
         epilogue_group16<HAS_O, MODE, 0, 16>(p, acc, oacc, xs, scale_sa + (g + h) * 32, row_sa, sw, ((g + h) & 3) * 2, row, row_ok, n0 + (g + h) * 16);
+        MIXQ_EPI_STAMP(2 + 3 * h);
       }
     }
     const int last = two ? g + 1 : g;
     if ((last & 3) == 3 || last == ngroups - 1) {   // block complete (or run finished): 64 columns out, coalesced
       __syncwarp();
+      MIXQ_EPI_STAMP(6);
       for_each_ydest(p, n0, [&](__half* yb, int ldy) {
         epi_stage_out(stage_sa, yb, ldy, m_base, n0 + (g & ~3) * 16, ((last & 3) + 1) * 2, p.M, p.N, lane);
       });
       __syncwarp();
+      MIXQ_EPI_STAMP(7);
     }
   }
+  MIXQ_EPI_NEXT();
 }
 
 }  // namespace mixq

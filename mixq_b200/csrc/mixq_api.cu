@@ -1129,11 +1129,13 @@ int mixq_quik_addend(const void* meta, const void* reduced_w, const void* fp_res
   return 0;
 }
 
-int mixq_exchange_finish_poll(const mixq_exchange_poll_args* a, void* stream) {
+}  // extern "C"
+namespace {
+int fill_xchg_poll(XchgPollArgs* kp, const mixq_exchange_poll_args* a) {
+  XchgPollArgs& k = *kp;
   if (!a || a->world < 2 || a->world > kMaxPeers || a->rank < 0 || a->rank >= a->world || !a->recv || a->M < 1 || a->N < 8 ||
       a->N % (8 * a->world) != 0)
     return fail(MIXQ_EINVAL, "bad exchange_finish_poll arguments (2 <= world <= 8, N % (8 * world) == 0)");
-  XchgPollArgs k{};
   k.recv = static_cast<__half*>(a->recv);
   for (int p = 0; p < a->world; ++p) {
     if (!a->mc_result && !a->result[p] && !(a->one_shot && p != a->rank)) return fail(MIXQ_EINVAL, "missing peer pointer");
@@ -1150,10 +1152,35 @@ int mixq_exchange_finish_poll(const mixq_exchange_poll_args* a, void* stream) {
   k.one_shot = a->one_shot ? 1 : 0;
   k.timeout_ns = g_peer_timeout_ms.load(std::memory_order_relaxed) * 1000000ull;
   k.trace = g_trace.load(std::memory_order_relaxed);
+  return 0;
+}
+}  // namespace
+extern "C" {
+
+int mixq_exchange_finish_poll(const mixq_exchange_poll_args* a, void* stream) {
+  XchgPollArgs k{};
+  if (int r = fill_xchg_poll(&k, a)) return r;
   DeviceInfo di;
   if (int r = device_info(&di)) return r;
   const int grid = grid_for(static_cast<long long>(a->M) * (a->N / (a->one_shot ? 1 : a->world) / 8), 256, di.sms, 2);
   MIXQ_CUDA(launch_small(exchange_finish_poll_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), k));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int mixq_exchange_finish_poll_quant(const mixq_exchange_poll_args* a, const void* norm_weight, float eps, const int32_t* ind,
+                                    int n_ind, void* act_outliers, int ld_ao, void* q_x, void* x_scale, int bit, void* stream) {
+  XchgPollArgs k{};
+  if (int r = fill_xchg_poll(&k, a)) return r;
+  if (!norm_weight || !q_x || !x_scale) return fail(MIXQ_EINVAL, "exchange_finish_poll_quant needs norm_weight, q_x and x_scale");
+  if (static_cast<long long>(a->N) * 2 > 48 * 1024) return fail(MIXQ_EINVAL, "row does not fit the shared-memory row buffer");
+  RowQuantArgs rq{};
+  if (int r = fill_rowquant(&rq, nullptr, norm_weight, nullptr, eps, ind, n_ind, act_outliers, ld_ao, q_x, x_scale, a->M, a->N, bit,
+                            0.f, nullptr, nullptr))
+    return r;
+  rq.group_warps = 4;   // the whole CTA (kXchgQuantThreads) owns the row
+  rq.ngroups = 1;
+  MIXQ_CUDA(launch_exchange_finish_rowquant(k, rq, a->M, pdl_on(), static_cast<cudaStream_t>(stream)));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }

@@ -485,8 +485,14 @@ mixq_linear2_kernel(const __grid_constant__ LinearParams p) {
           __syncwarp();
           pre_staged = true;
         }
+#ifdef MIXQ_EPI_TRACE
+        if (trace && blockIdx.x == 0 && warp == 4 && lane == 0 && i == 0 && c < 16) p.trace[2000 + 2 * c] = static_cast<unsigned long long>(clock64());
+#endif
         mbar_wait_warp(&bar_tfull[buf], (G / NB) & 1, 5, c);
         tc_fence_after();
+#ifdef MIXQ_EPI_TRACE
+        if (trace && blockIdx.x == 0 && warp == 4 && lane == 0 && i == 0 && c < 16) p.trace[2000 + 2 * c + 1] = static_cast<unsigned long long>(clock64());
+#endif
         if (trace && !p.fused_prologue && warp == 4 && lane == 0 && i == 0 && c == 0) trace[7] = globaltimer_ns();
         if (trace && blockIdx.x == 0 && warp == 4 && lane == 0 && i == 0 && c < 16) p.trace[1536 + 2 * c] = globaltimer_ns();
         const int x0 = c * (R >> 1);                                   // this pass: output columns [x0, x1) of the half

@@ -641,6 +641,99 @@ __global__ void __launch_bounds__(256) exchange_finish_poll_kernel(XchgPollArgs 
   if (tr) a.trace[7] = globaltimer_ns();
 }
 
+// ---------------------------------------------------------------- the same, + the NEXT MixLinear's activation prologue
+// After an exchange every rank holds whole rows of the residual stream h, and the Linear that follows (W_pack / the SwiGLU pair)
+// starts with RMSNorm -> outlier gather -> row abs-max -> quantise over exactly those rows (norm.py:24-33) — on EVERY rank, the
+// same work, 3.5 us of prologue + a 1.8 us grid barrier per launch.  Here one CTA owns one token row: it reduces the row's own
+// slice, broadcasts it, collects the other slices as they land (all through the row buffer in shared memory) and runs
+// process_row (rowquant.cuh, the very code of the Linear's phase A) on it.  The Linear then runs with skip_prologue, the
+// reference's "fused" call mode with this kernel as the producer.
+constexpr int kXchgQuantThreads = 128;
+__global__ void __launch_bounds__(kXchgQuantThreads, 4) exchange_finish_rowquant_kernel(XchgPollArgs a, const RowQuantArgs rq) {
+  extern __shared__ __align__(128) uint8_t xq_smem[];
+  __shared__ RowQuantSmem sm;
+  __half* row_s = reinterpret_cast<__half*>(xq_smem);
+  const uint32_t row_sa = smem_u32(row_s);
+  pdl_launch_dependents();
+  pdl_wait();
+  const bool one_shot = a.one_shot != 0;
+  const int Ns = one_shot ? a.N : a.N / a.world;
+  const int vpr = Ns >> 3, vprN = a.N >> 3;
+  const size_t slot = static_cast<size_t>(a.M) * Ns;
+  const int lo = one_shot ? 0 : (a.rank * Ns) >> 3;       // first 16-byte vector of the own slice within a row
+  const uint4 sent = make_uint4(kSentinel2, kSentinel2, kSentinel2, kSentinel2);
+  for (int m = blockIdx.x, iter = 0; m < a.M; m += gridDim.x, ++iter) {
+    const size_t rowoff = static_cast<size_t>(m) * a.N;
+    for (int c8 = threadIdx.x; c8 < vpr; c8 += kXchgQuantThreads) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int s = 0; s < a.world; ++s) {
+        uint4* sp = reinterpret_cast<uint4*>(a.recv + s * slot + static_cast<size_t>(m) * Ns) + c8;
+        H8 v;
+        v.u = poll_vec(sp, a.timeout_ns, 44);
+        *sp = sent;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(v.h2[j]);
+          acc[2 * j] += f.x;
+          acc[2 * j + 1] += f.y;
+        }
+      }
+      const size_t off = rowoff + static_cast<size_t>(lo + c8) * 8;
+      H8 r, o;
+      if (a.residual != nullptr) r.u = *reinterpret_cast<const uint4*>(a.residual + off);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __half2 y2 = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+        if (a.residual != nullptr) {
+          const float2 yf = __half22float2(y2), rf = __half22float2(r.h2[j]);
+          y2 = __floats2half2_rn(__fadd_rn(yf.x, rf.x), __fadd_rn(yf.y, rf.y));
+        }
+        o.h2[j] = y2;
+      }
+      if (a.reset != nullptr) *reinterpret_cast<uint4*>(a.reset + off) = sent;
+      if (one_shot) {
+        *reinterpret_cast<uint4*>(a.result[a.rank] + off) = o.u;
+      } else if (a.mc_result != nullptr) {
+        asm volatile("multimem.st.relaxed.sys.global.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(a.mc_result + off), "r"(o.u.x), "r"(o.u.y),
+                     "r"(o.u.z), "r"(o.u.w)
+                     : "memory");
+      } else {
+        for (int p = 0; p < a.world; ++p) *reinterpret_cast<uint4*>(a.result[p] + off) = o.u;
+      }
+      sts128(row_sa + (lo + c8) * 16, o.u);
+    }
+    if (!one_shot) {
+      for (int c = threadIdx.x; c < vprN; c += kXchgQuantThreads) {
+        const bool own = c >= lo && c < lo + vpr;
+        if (own && a.mc_result == nullptr) continue;
+        const size_t i = static_cast<size_t>(m) * vprN + c;
+        if (!own && a.reset != nullptr) *(reinterpret_cast<uint4*>(a.reset) + i) = sent;
+        const uint4 v = poll_vec(reinterpret_cast<const uint4*>(a.result[a.rank]) + i, a.timeout_ns, 45);
+        if (!own) sts128(row_sa + c * 16, v);
+      }
+    }
+    __syncthreads();
+    process_row(rq, m, 0, threadIdx.x, iter, &sm, row_s);
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_exchange_finish_rowquant(const XchgPollArgs& a, const RowQuantArgs& rq, int grid, bool pdl, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kXchgQuantThreads);
+  cfg.dynamicSmemBytes = static_cast<size_t>(a.N) * 2;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, exchange_finish_rowquant_kernel, a, rq);
+}
+
 __global__ void pingpong_kernel(uint32_t* mine, uint32_t* peer, uint32_t* mc, int iters, int rank, unsigned long long* out_ns) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const uint64_t t0 = globaltimer_ns();

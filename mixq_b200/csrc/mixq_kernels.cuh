@@ -91,6 +91,8 @@ struct XchgPollArgs {
   unsigned long long* trace;
 };
 __global__ void exchange_finish_poll_kernel(XchgPollArgs a);
+// + RMSNorm / outlier gather / quantisation of every row for the Linear that follows (one CTA per token row)
+cudaError_t launch_exchange_finish_rowquant(const XchgPollArgs& a, const RowQuantArgs& rq, int grid, bool pdl, cudaStream_t st);
 // tuning aid: `iters` flag round trips between two ranks inside one launch; *out_ns = elapsed nanoseconds (rank 0)
 __global__ void pingpong_kernel(uint32_t* mine, uint32_t* peer, uint32_t* mc, int iters, int rank, unsigned long long* out_ns);
 

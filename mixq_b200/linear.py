@@ -489,5 +489,26 @@ class MixLinear_GEMM(nn.Module):
         cache.activation_outliers = cache.ao_buffer(self._n_ind)[:M, : self._n_ind]
         return y.reshape(cache.shape)
 
+    def forward_swiglu_quantized(self, up, M, cache=None):
+        """forward_swiglu_fused when a producer kernel (the tensor-parallel exchange, mixq_exchange_finish_poll_quant) has
+        already normalised and quantised the rows: consumes cache.q_xcache / x_scale / activation_outliers like
+        forward_quantized, both GEMMs + SiLU + gate * up in one launch.  Steady state only."""
+        if cache is None:
+            cache = self.cache
+        if self.add_outliers and up.add_outliers:
+            raise _lib.MixqError("forward_swiglu_quantized is a steady-state path: run the discovery calls first")
+        if self._n_ind != up._n_ind or self.in_features != up.in_features or self.out_features != up.out_features:
+            raise _lib.MixqError("gate_proj and up_proj must share shape and outlier set")
+        if self._wc_buf.shape[1] != up._wc_buf.shape[1]:
+            n = max(self._wc_buf.shape[1], up._wc_buf.shape[1])
+            self._reserve_wc(n)
+            up._reserve_wc(n)
+        self._require_cuda(cache.q_xcache, self.q_weight)
+        y = torch.empty((M, self.out_features), dtype=torch.float16, device=self.q_weight.device)
+        cache.shape = (M, self.out_features)
+        ao, ld = self._cached_act_outliers(cache, M)
+        self._launch(cache, M, y, skip_prologue=True, q_x=cache.q_xcache, act_outliers=ao, ld_ao=ld, up=up)
+        return y
+
     def extra_repr(self):
         return f"in={self.in_features}, out={self.out_features}, bit={self.bit}, outliers={self._n_ind}"

@@ -148,6 +148,7 @@ class LlamaDecoder:
         self.fuse_swiglu = batch > 128
         # attention + o_proj's activation prologue in one launch (MIXQ_FUSE_ATTN_QUANT=0: separate launches)
         self.fuse_attn_quant = os.environ.get("MIXQ_FUSE_ATTN_QUANT", "1") != "0"
+        self.fuse_xchg_quant = os.environ.get("MIXQ_TP_FUSE_QUANT", "1") != "0"
         self.graph = None
         self._static_tokens = None
         self._static_logits = None
@@ -251,68 +252,61 @@ class LlamaDecoder:
         h = torch.nn.functional.embedding(tokens.reshape(-1), self.embed)   # [B, H] fp16
         steady = self.discovered
         tp = self.world > 1
+        M = h.shape[0]
+        fused_x = tp and self.xchg is not None and getattr(self.xchg, "fused", False)
+        # the exchange's finish kernel can run the next Linear's activation prologue on the rows it has just assembled
+        xq = steady and fused_x and self.fuse_xchg_quant and getattr(self.xchg, "can_quantize", False)
+        prequant = False          # q_x / x_scale / outliers of the coming norm-fused Linear are already in the cache
+
+        def row_parallel(lin, x=None, quant=None):
+            """o_proj / down_proj + the exchange (+ residual): x = fp16 activations, or None when a producer kernel has
+            already quantised them into the cache."""
+            nonlocal h
+            if tp and self.xchg is not None:
+                kw = {"push": self.xchg.push_targets()} if fused_x else {"out": self.xchg.next_partial()}
+                if x is None:
+                    lin.forward_quantized(M, **kw)
+                else:
+                    lin(x, None, True, **kw)
+                h = self.xchg.reduce(h, quant=quant) if quant is not None else self.xchg.reduce(h)
+            elif tp:
+                h = h + self._allreduce(lin.forward_quantized(M) if x is None else lin(x, None, True))
+            else:
+                h = lin.forward_quantized(M, residual=h) if x is None else lin(x, None, True, residual=h)
+
         for li, L in enumerate(self.layers):
-            if steady:
+            if prequant:
+                qkv = L["W_pack"].forward_quantized(M)
+            elif steady:
                 qkv = L["W_pack"].forward_norm_fused(h, L["ln1"], cfg.eps)
             else:
                 qkv = self._norm_then_linear(h, L["ln1"], L["W_pack"])
+            mlp_in = L["gate_proj"] if (steady and self.fuse_swiglu) else L["up_proj"]
+            q_mlp = (L["ln2"], cfg.eps, mlp_in, self.cache) if xq else None
             if self.kv is not None and getattr(self, "kv_library_attention", False):
-                attn = self._attention_sdpa(qkv, past_len, li)
-                if tp and self.xchg is not None:
-                    if getattr(self.xchg, "fused", False):
-                        L["o_proj"](attn, None, True, push=self.xchg.push_targets())
-                    else:
-                        L["o_proj"](attn, None, True, out=self.xchg.next_partial())
-                    h = self.xchg.reduce(h)
-                elif tp:
-                    h = h + self._allreduce(L["o_proj"](attn, None, True))
-                else:
-                    h = L["o_proj"](attn, None, True, residual=h)
+                row_parallel(L["o_proj"], self._attention_sdpa(qkv, past_len, li), q_mlp)
             elif steady and self.fuse_attn_quant:
                 # attention quantises its own output rows for o_proj: o_proj has no activation prologue left
                 self._attention_quant(qkv, L["o_proj"], past_len, li)
-                M = qkv.shape[0]
-                if tp and self.xchg is not None:
-                    if getattr(self.xchg, "fused", False):
-                        L["o_proj"].forward_quantized(M, push=self.xchg.push_targets())
-                    else:
-                        L["o_proj"].forward_quantized(M, out=self.xchg.next_partial())
-                    h = self.xchg.reduce(h)
-                elif tp:
-                    h = h + self._allreduce(L["o_proj"].forward_quantized(M))
-                else:
-                    h = L["o_proj"].forward_quantized(M, residual=h)
+                row_parallel(L["o_proj"], None, q_mlp)
             else:
-                attn = self._attention(qkv, past_len, li)
-                if tp and self.xchg is not None:
-                    if getattr(self.xchg, "fused", False):
-                        L["o_proj"](attn, None, True, push=self.xchg.push_targets())
-                    else:
-                        L["o_proj"](attn, None, True, out=self.xchg.next_partial())
-                    h = self.xchg.reduce(h)
-                elif tp:
-                    h = h + self._allreduce(L["o_proj"](attn, None, True))
-                else:
-                    h = L["o_proj"](attn, None, True, residual=h)
-            if steady and self.fuse_swiglu:
+                row_parallel(L["o_proj"], self._attention(qkv, past_len, li), q_mlp)
+            if xq and self.fuse_swiglu:
+                gate = L["gate_proj"].forward_swiglu_quantized(L["up_proj"], M)
+            elif steady and self.fuse_swiglu:
                 gate = L["gate_proj"].forward_swiglu_fused(L["up_proj"], h, L["ln2"], cfg.eps)
             else:
-                if steady:
+                if xq:
+                    up = L["up_proj"].forward_quantized(M)
+                elif steady:
                     up = L["up_proj"].forward_norm_fused(h, L["ln2"], cfg.eps)
                 else:
                     up = self._norm_then_linear(h, L["ln2"], L["up_proj"])
                 gate = L["gate_proj"].forward_without_preconditionFusedSilu(h, self.cache)
                 _lib.check(self.lib.mixq_mul_inplace(gate.data_ptr(), up.data_ptr(), gate.numel(), self._stream()), "mul")
-            if tp and self.xchg is not None:
-                if getattr(self.xchg, "fused", False):
-                    L["down_proj"](gate, None, True, push=self.xchg.push_targets())
-                else:
-                    L["down_proj"](gate, None, True, out=self.xchg.next_partial())
-                h = self.xchg.reduce(h)
-            elif tp:
-                h = h + self._allreduce(L["down_proj"](gate, None, True))
-            else:
-                h = L["down_proj"](gate, None, True, residual=h)
+            nxt = self.layers[li + 1] if li + 1 < len(self.layers) else None
+            prequant = xq and nxt is not None
+            row_parallel(L["down_proj"], gate, (nxt["ln1"], cfg.eps, nxt["W_pack"], self.cache) if prequant else None)
             if li == 0 and getattr(self, "probe_layer0", False):
                 self.hidden_after_layer0 = h.clone()     # parity probe (bench.py tp_parity): the residual stream after layer 0
         hn = torch.empty_like(h)
@@ -449,6 +443,7 @@ class LlamaDecoder:
         self.discovered = False
         self.fuse_swiglu = batch > 128
         self.fuse_attn_quant = os.environ.get("MIXQ_FUSE_ATTN_QUANT", "1") != "0"
+        self.fuse_xchg_quant = os.environ.get("MIXQ_TP_FUSE_QUANT", "1") != "0"
         self.graph = self._static_tokens = self._static_logits = self.kv = None
         self.lib = _lib.load()
         self.xchg = None

@@ -315,9 +315,9 @@ class PushExchange:
         rb = nb * (world if self.one_shot else 1)          # receive area per exchange buffer
         local, ptrs, mc, self._keep, self._close = _symmetric_alloc(2 * rb + 2 * nb + 256, rank, world, group, device)
         # broadcast of the reduced slice: multimem.st through the switch (one store, (w-1)/w of the egress saved) or plain
-        # stores to every peer.  Measured: peer stores win at 2 ranks (8.4 vs 11.2 us: the own copy stays local), multicast
-        # at 8 (18.9 vs 19.5).  MIXQ_TP_BCAST=mc|peer overrides.
-        bcast = os.environ.get("MIXQ_TP_BCAST", "peer" if world == 2 else "mc")
+        # stores to every peer.  Measured (us added per exchange, peer stores vs multicast): 2 ranks 8.4 vs 11.2 (the own copy
+        # stays local), 4 ranks 13.5 vs 14.7, 8 ranks 19.5 vs 18.9.  MIXQ_TP_BCAST=mc|peer overrides.
+        bcast = os.environ.get("MIXQ_TP_BCAST", "peer" if world <= 4 else "mc")
         if not multicast or bcast == "peer":
             mc = 0
         self.multicast = mc != 0 and not self.one_shot
@@ -362,11 +362,29 @@ class PushExchange:
             return self._targets[self.buf], 0, self.world
         return self._targets[self.buf], self.ns, 0
 
-    def reduce(self, residual, out: torch.Tensor = None) -> torch.Tensor:
+    can_quantize = property(lambda self: self.sync == "poll")
+
+    def reduce(self, residual, out: torch.Tensor = None, quant=None) -> torch.Tensor:
+        """quant = (norm_weight, eps, lin, cache): also run lin's activation prologue (RMSNorm -> outlier gather -> row scale ->
+        quantise, fused/norm.py:24-33) on the exchanged rows inside the finish kernel and leave q_xcache / x_scale /
+        activation_outliers in `cache`: lin (W_pack, or gate_proj of the SwiGLU pair) then runs forward_quantized / in its
+        fused call mode without an activation prologue.  Polling form only."""
         a = self._fin[self.buf]
         a.residual = 0 if residual is None else residual.data_ptr()
-        fn = self.lib.mixq_exchange_finish_poll if self.sync == "poll" else self.lib.mixq_exchange_finish
-        self._check(fn(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "exchange_finish")
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if quant is not None:
+            if self.sync != "poll":
+                raise ValueError("the quantising finish needs sync='poll'")
+            norm_w, eps, lin, cache = quant
+            n = lin._n_ind
+            ao, q_x = cache.ao_buffer(n), cache.q_x_buffer(self.rows, self.cols)
+            self._check(self.lib.mixq_exchange_finish_poll_quant(C.byref(a), norm_w.data_ptr(), float(eps), lin._ind_buf.data_ptr(), n,
+                                                                 ao.data_ptr(), ao.shape[1], q_x.data_ptr(), cache.x_scale.data_ptr(),
+                                                                 lin.bit, st), "exchange_finish_poll_quant")
+            cache.q_xcache, cache.activation_outliers, cache.ind = q_x, ao[:self.rows, :n], lin.ind
+        else:
+            fn = self.lib.mixq_exchange_finish_poll if self.sync == "poll" else self.lib.mixq_exchange_finish
+            self._check(fn(C.byref(a), st), "exchange_finish")
         out = self.results[self.buf]
         self.buf ^= 1
         return out

@@ -18,7 +18,8 @@ def test_peer_exchange_two_ranks():
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     for kind in ("push-oneshot", "push-twophase", "push-nomc-oneshot", "push-nomc-twophase"):
-        assert f"{kind} exchange ok" in r.stdout, kind
+        for sync in ("poll", "flags"):      # data-is-the-signal form (default) and the flag handshake
+            assert f"{kind}-{sync} exchange ok" in r.stdout, (kind, sync)
     assert "push decoder ok" in r.stdout
     assert "peer exchange ok" in r.stdout
     assert "multicast exchange ok" in r.stdout or "multicast exchange unavailable" in r.stdout

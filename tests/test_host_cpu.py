@@ -191,6 +191,9 @@ int main(void) {
   printf("%zu %zu %zu %zu %zu %zu\n", sizeof(mixq_mc_allreduce_args), offsetof(mixq_mc_allreduce_args, partial_off),
          offsetof(mixq_mc_allreduce_args, flags_off), offsetof(mixq_mc_allreduce_args, epoch), offsetof(mixq_mc_allreduce_args, n),
          offsetof(mixq_mc_allreduce_args, buf));
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(mixq_exchange_poll_args), offsetof(mixq_exchange_poll_args, result),
+         offsetof(mixq_exchange_poll_args, mc_result), offsetof(mixq_exchange_poll_args, reset),
+         offsetof(mixq_exchange_poll_args, residual), offsetof(mixq_exchange_poll_args, M), offsetof(mixq_exchange_poll_args, one_shot));
   return 0;
 }'''
     import tempfile
@@ -203,8 +206,14 @@ int main(void) {
     A, B = _lib.ExchangeFinishArgs, _lib.McAllReduceArgs
     want = [ctypes.sizeof(A), A.result.offset, A.mc_result.offset, A.flags.offset, A.epoch.offset, A.residual.offset, A.rank.offset,
             ctypes.sizeof(B), B.partial_off.offset, B.flags_off.offset, B.epoch.offset, B.n.offset, B.buf.offset]
+    P = _lib.ExchangePollArgs
+    want += [ctypes.sizeof(P), P.result.offset, P.mc_result.offset, P.reset.offset, P.residual.offset, P.M.offset, P.one_shot.offset]
     assert got == want
     lib = _lib.load()
+    pa = P()
+    pa.world, pa.N, pa.M = 3, 4096, 8
+    assert lib.mixq_exchange_finish_poll(ctypes.byref(pa), None) != 0 and b"exchange_finish_poll" in lib.mixq_last_error()
+    assert lib.mixq_exchange_finish_poll_quant(ctypes.byref(pa), None, 0.0, None, 0, None, 0, None, None, 8, None) != 0
     a = A()
     a.world, a.N, a.M = 3, 4096, 8            # N % (8 * world) != 0
     assert lib.mixq_exchange_finish(ctypes.byref(a), None) != 0 and b"exchange_finish" in lib.mixq_last_error()

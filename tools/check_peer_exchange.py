@@ -133,6 +133,14 @@ def check_decoder(kind, rank, world):
     # steady-state graph replay == eager step
     m = models[kind]
     eager = m.step(tok).clone()
+    if getattr(m.xchg, "can_quantize", False) and m.fuse_xchg_quant:
+        # the finish kernel running the next Linear's activation prologue == the Linear running it itself, bit for bit
+        m.fuse_xchg_quant = False
+        m._rank_barrier()
+        plain = m.step(tok).clone()
+        m.fuse_xchg_quant = True
+        m._rank_barrier()
+        assert torch.equal(plain, eager), f"rank {rank}: quantising finish kernel changes the logits (max diff {float((plain.float() - eager.float()).abs().max()):.3e})"
     m.capture(tok)
     rep = m.replay(tok).clone()
     torch.cuda.synchronize()

@@ -7,6 +7,7 @@ TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 CHECK_KIND=push timeout 600 $TR --nproc-per-node ${NGPU:-8} --master-port 29561 tools/check_peer_exchange.py > gpurun_out/r02_check_exchange_${NGPU:-8}.log 2>&1
 echo "check rc=$?"; grep -E " ok on |Error|error" gpurun_out/r02_check_exchange_${NGPU:-8}.log | tail -8
 for n in ${ANATOMY:-8}; do
+  [ "$n" = none ] && continue
   timeout 400 $TR --nproc-per-node $n --master-port 2957$n tools/bench_exchange.py > gpurun_out/r02_bench_exchange_$n.json 2> gpurun_out/r02_bench_exchange_$n.err
   echo "anatomy $n rc=$?"; grep "^{" gpurun_out/r02_bench_exchange_$n.json
 done

@@ -62,11 +62,15 @@ for (N, K) in SHAPES:
         if gb[:, 0].sum() > 0:
             f = lambda i: f"{(gb[:, i].min() - t0) / 1e3:.2f}..{(gb[:, i].max() - t0) / 1e3:.2f}"
             print(f"    grid barrier (all CTAs, us): enter {f(0)} | fence done {f(1)} | atomic done {f(2)} | flip seen {f(3)}")
-        ep = full[2048:2048 + 148 * 8 * 4].view(148 * 8, 4)
-        if ep[:, 3].sum() > 0:   # built with EXTRA=-DMIXQ_EPI_PROFILE: clock64 sums per epilogue warp
-            ok = ep[:, 3] > 0
-            print(f"    epilogue clocks per warp (mean over {int(ok.sum())} warps): tmem ld+wait {ep[ok, 0].mean():8.0f} | math+smem {ep[ok, 1].mean():8.0f} | "
-                  f"stage-out {ep[ok, 2].mean():8.0f} | calls {ep[ok, 3].mean():.1f}")
+        ncall = int(full[1799])
+        if 0 < ncall <= 24:      # built with EXTRA=-DMIXQ_EPI_TRACE: stamps inside the epilogue runs of CTA 0 / warp 4
+            et = full[1800:1800 + 8 * ncall].view(ncall, 8)
+            pw = full[2000:2032].view(16, 2)
+            c0 = pw[0, 0] if pw[0, 0] > 0 else et[et > 0].min()
+            print("    epilogue runs of CTA 0 warp 4, SM clocks since the first pass wait (ld0 start, ld0 done, math0 done, ld1 start, ld1 done, math1 done, out start, out done):")
+            for row in et.tolist():
+                print("      " + " ".join(f"{int(v - c0):6d}" if v > 0 else "     -" for v in row))
+            print("    pass waits (before, after): " + " | ".join(f"{int(a - c0)} {int(b - c0)}" for a, b in pw.tolist() if a > 0))
         if os.environ.get("CADENCE"):
             base = t[0, 0]
             up = full[1200:1200 + 160].view(40, 4)
