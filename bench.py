@@ -443,6 +443,8 @@ def run_mixq(args):
         o_quantized = kind == "o_proj" and getattr(model, "fuse_attn_quant", False)
         if o_quantized:           # every layer's o_proj shares the module cache: one ordinary call leaves q_x / x_scale / outliers there
             mods[0](xw, None, True)
+            n_max = max(m._n_ind for m in mods)          # (timing only: every layer reads the same gathered-outlier buffer)
+            model.cache.activation_outliers = model.cache.ao_buffer(n_max)[:B, :n_max] if n_max else None
         if kind == "gate_proj":   # needs up_proj's q_x in the cache
             model.layers[0]["up_proj"].forward_norm_fused(h, model.layers[0]["ln2"], cfg.eps)
         # one CUDA graph holding this Linear of every layer (distinct weights: L2-cold, as in the step), so that the
