@@ -197,6 +197,13 @@ typedef struct mixq_linear_args {
    * each of y_peer[0 .. peer_bcast) (fp16 [M,N] receive slots, one per rank incl. this one); mixq_exchange_finish(one_shot = 1)
    * then reduces all of them locally with a single handshake. */
   int peer_bcast;
+  /* split-K workspace (optional; M <= 128 only): with a handful of 128-row tiles most SMs would idle, so up to 4 CTAs share a
+   * tile's K range and meet through this buffer — int32 partial sums, added exactly, so the result is bit-identical to the
+   * unsplit launch.  Caller-owned device memory, ZERO-FILLED ONCE by the caller (the first 4096 bytes are per-tile counters
+   * that every launch leaves at zero again), at least 4096 + 3 * M * N * 4 bytes to allow the full split; one launch at a time
+   * per workspace.  NULL = never split. */
+  void* splitk_ws;
+  long long splitk_ws_bytes;
 } mixq_linear_args;
 
 int mixq_linear_fused(const mixq_linear_args* args /* host */, void* stream);

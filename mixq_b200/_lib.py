@@ -56,6 +56,8 @@ class LinearArgs(C.Structure):
         ("y_peer", C.c_void_p * 8),
         ("peer_cols", C.c_int),
         ("peer_bcast", C.c_int),
+        ("splitk_ws", C.c_void_p),
+        ("splitk_ws_bytes", C.c_longlong),
     ]
 
 

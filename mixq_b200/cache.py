@@ -71,6 +71,14 @@ class MixLibCache:
             self._ao = new
         return self._ao
 
+    def splitk_buffer(self) -> torch.Tensor:
+        """Zero-filled workspace for the split-K launches of small-M shapes (include/mixq.h: mixq_linear_args.splitk_ws):
+        4 KB of per-tile counters + up to three int32 partial-sum slices.  16 MB covers M <= 128 with N <= 10 922 at the
+        full split; larger N runs with fewer splits (the library checks the size)."""
+        if getattr(self, "_splitk", None) is None:
+            self._splitk = torch.zeros(16 * 1024 * 1024 // 4, dtype=torch.int32, device=self.device)
+        return self._splitk
+
     def col_over_buffer(self, K: int) -> torch.Tensor:
         if self._col_over is None or self._col_over.numel() < K:
             self._col_over = torch.zeros(K, dtype=torch.uint8, device=self.device)

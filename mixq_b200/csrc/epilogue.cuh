@@ -120,9 +120,11 @@ __device__ __forceinline__ void epilogue_chunk(const LinearParams& p, uint32_t t
 // A span of `ncols` (multiple of 16) accumulator columns of one row, as a ROLLED loop over 16-column groups: the body is
 // ~200 instructions and stays in the instruction cache (the fully unrolled 32-column form above is paced by
 // instruction fetch when only 1-2 warps per scheduler run it).  Every lane of the warp must call this.
-template <bool HAS_O>
+// SK == 1 (split-K, 1-CTA kernel): this CTA holds a PARTIAL int32 sum — store it to its workspace slice `sk_part` [M, N].
+template <bool HAS_O, int SK = 0>
 __device__ __forceinline__ void epilogue_span(const LinearParams& p, uint32_t t_int, uint32_t t_out, int row, bool row_ok,
-                                              int n0, int ncols, float xs, const __half* addend, int ld_addend) {
+                                              int n0, int ncols, float xs, const __half* addend, int ld_addend,
+                                              int32_t* sk_part = nullptr) {
   const bool has_outl = addend != nullptr;
   const bool has_bias = p.bias != nullptr;
   const bool has_res = p.residual != nullptr;
@@ -137,6 +139,13 @@ __device__ __forceinline__ void epilogue_span(const LinearParams& p, uint32_t t_
     tmem_ld_wait();
     const int n = n0 + c;
     if (!row_ok || n >= p.N) continue;
+    if (SK == 1) {
+      uint4* dst = reinterpret_cast<uint4*>(sk_part + static_cast<size_t>(row) * p.N + n);
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (n + g * 4 < p.N) dst[g] = make_uint4(acc[4 * g], acc[4 * g + 1], acc[4 * g + 2], acc[4 * g + 3]);
+      continue;
+    }
     if (raw) {
       int32_t* dst = p.y_i32 + static_cast<size_t>(row) * p.N + n;
 #pragma unroll
@@ -186,6 +195,48 @@ __device__ __forceinline__ void epilogue_span(const LinearParams& p, uint32_t t_
   }
 }
 
+
+// Split-K, the tile's last split: fold the other splits' partial sums (slices of `stride` elements at `part`, `nparts` <= 3 of
+// them) into this CTA's int32 accumulator, in place in TMEM, 16 columns at a time with the next group's loads already in
+// flight.  Integer adds: exact and order-independent, so the dequant epilogue that follows sees the unsplit accumulator.
+// Every lane of the warp must call this (tcgen05.ld / st are warp-collective); lane = accumulator row.
+__device__ __forceinline__ void splitk_fold(const LinearParams& p, uint32_t t_int, int row, bool row_ok, int n0, int ncols,
+                                            const int32_t* part, int nparts, size_t stride) {
+  auto load = [&](int c, uint4 (&pv)[3][4]) {
+    const int n = n0 + c;
+#pragma unroll
+    for (int sp = 0; sp < 3; ++sp) {
+      const uint4* src = reinterpret_cast<const uint4*>(part + sp * stride + static_cast<size_t>(row) * p.N + n);
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        pv[sp][g] = (row_ok && sp < nparts && n + g * 4 < p.N) ? __ldcg(src + g) : make_uint4(0, 0, 0, 0);
+    }
+  };
+  uint4 cur[3][4], nxt[3][4];
+  load(0, cur);
+#pragma unroll 1
+  for (int c = 0; c < ncols; c += 16) {
+    uint32_t acc[16];
+    tmem_ld_32x16(t_int + c, acc);
+    if (c + 16 < ncols) load(c + 16, nxt);
+    tmem_ld_wait();
+#pragma unroll
+    for (int sp = 0; sp < 3; ++sp)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        acc[4 * g] += cur[sp][g].x;
+        acc[4 * g + 1] += cur[sp][g].y;
+        acc[4 * g + 2] += cur[sp][g].z;
+        acc[4 * g + 3] += cur[sp][g].w;
+      }
+    tmem_st_32x16(t_int + c, acc);
+#pragma unroll
+    for (int sp = 0; sp < 3; ++sp)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) cur[sp][g] = nxt[sp][g];
+  }
+  tmem_st_wait();
+}
 
 }  // namespace mixq
 

@@ -51,13 +51,14 @@ int barrier_mode() { return g_barrier_mode.load(std::memory_order_relaxed); }
 // MIXQ_DEBUG_* tuning knobs: read once when the library loads (and again by mixq_reload_debug_env, for tests that change them),
 // never on the launch path.
 struct DebugEnv {
-  std::atomic<int> katoms{0}, stage_bytes{0}, stages{0}, ablate{0};
+  std::atomic<int> katoms{0}, stage_bytes{0}, stages{0}, ablate{0}, splits{0};
   void load() {
     auto rd = [](const char* n) { const char* e = getenv(n); return e ? atoi(e) : 0; };
     katoms.store(rd("MIXQ_DEBUG_KATOMS"));
     stage_bytes.store(rd("MIXQ_DEBUG_STAGE_BYTES"));
     stages.store(rd("MIXQ_DEBUG_STAGES"));
     ablate.store(rd("MIXQ_DEBUG_ABLATE"));
+    splits.store(rd("MIXQ_DEBUG_SPLITS"));     // cap of the split-K factor (1 = never split)
   }
   DebugEnv() { load(); }
 };
@@ -355,10 +356,12 @@ int pick_row_groups(RowQuantArgs* a, int grid, int warps_per_cta, long long smem
 // arithmetic (exported as mixq_plan_linear so that the heuristics are testable without a GPU).
 struct GemmPlan {
   int two_cta, tile_w, k_atoms, stage_bytes, nstages, tiles, tiles_per_unit, units;
+  int splits = 1;    // 1-CTA kernel: CTAs per tile along K (needs a workspace)
   int npacked = 0;   // W4 on the 2-CTA kernel: slots of the packed-row ring behind the main stages
   TmemPlan tmem;
 };
-int plan_gemm(int M, int N, int K, int bit, int n_out, bool pair, int tile_req, int sms, GemmPlan* g) {
+constexpr long long kSplitKCounterBytes = 4096;     // per-tile counters at the head of the split-K workspace
+int plan_gemm(int M, int N, int K, int bit, int n_out, bool pair, int tile_req, int sms, GemmPlan* g, long long splitk_ws_bytes = 0) {
   if (M < 1 || N < 8 || K < 16 || sms < 1) return fail(MIXQ_EINVAL, "M>=1, N>=8, K>=16 required");
   const bool w4 = bit == 4;
   // M > 128: CTA pairs (cta_group::2) own 256 x bn tiles — half the L2 -> SM bytes per MMA cycle (mixq_gemm2.cu)
@@ -369,6 +372,28 @@ int plan_gemm(int M, int N, int K, int bit, int n_out, bool pair, int tile_req, 
   int bn = two_cta ? pick_w2(tile_req, M, pair ? 2 * N : N, n_out, npairs) : pick_tile_n(tile_req, M, N, sms, n_out > 0);
   // narrow tiles are paced by the TMA op count (one op ~340 clocks of the SM's TMA unit whatever its size): two k-atoms
   // (256 bytes of K) per op and pipeline stage whenever at least three such stages fit
+  g->splits = 1;
+  if (!two_cta && splitk_ws_bytes > kSplitKCounterBytes && tile_req == 0 && g_tile_n.load(std::memory_order_relaxed) == 0) {
+    // few 128-row tiles: split K over up to 4 CTAs per tile, 128-wide tiles for parallelism.  Measured (profiles/
+    // r02_bench_linear_smallM_cap*.jsonl, r02_trace_splitk.log): the mainloop shrinks as expected, but the last split folds the
+    // partials in with row-strided 16-byte loads, ~6 us per 128-row slice — it only pays when few rows are live (M <= 32)
+    // and K is long (>= 64 k-blocks): 4096 x 11008 at M = 32 goes 32.9 -> 25.6 us, every M = 128 shape gets slower.
+    const int t128 = ((M + 127) / 128) * ((N + 127) / 128);
+    const int nk = (K + 127) / 128;
+    int S = (M <= 32 && nk >= 64) ? sms / t128 : 1;
+    if (S > 4) S = 4;
+    if (S > nk / 4) S = nk / 4;
+    if (const int cap = g_dbg.splits.load(std::memory_order_relaxed); cap >= 1) {      // MIXQ_DEBUG_SPLITS: force (tests, tuning)
+      S = sms / t128;
+      if (S > cap) S = cap;
+      if (S > nk / 4) S = nk / 4;
+    }
+    while (S > 1 && kSplitKCounterBytes + static_cast<long long>(S - 1) * M * N * 4 > splitk_ws_bytes) --S;
+    if (S >= 2 && t128 * 4 <= kSplitKCounterBytes) {
+      bn = 128;
+      g->splits = S;
+    }
+  }
   int k_atoms = (two_cta && !w4 && K % 128 == 0 && K >= 256 && bn <= 256) ? 2 : 1;
   if (g_dbg.katoms.load(std::memory_order_relaxed) == 1) k_atoms = 1;
   int stage2 = 0, nstages2 = 0;
@@ -418,7 +443,7 @@ int plan_gemm(int M, int N, int K, int bit, int n_out, bool pair, int tile_req, 
                     : (bn == 256 ? GemmCfg<256, false>::STAGES : GemmCfg<128, false>::STAGES);
     g->tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
     g->units = sms;
-    g->tiles_per_unit = (g->tiles + sms - 1) / sms;
+    g->tiles_per_unit = (g->tiles * g->splits + sms - 1) / sms;
     const int acc_cols = bn * (n_out > 0 ? 2 : 1);       // mixq_gemm.cu: s32 accumulator [+ f32 outlier accumulator]
     g->tmem.slots = (2 * acc_cols <= 512) ? 2 : 1;
     g->tmem.passes = 1;
@@ -455,6 +480,8 @@ struct GemmCall {
   void* const* y_peer = nullptr;   // tensor-parallel push (see mixq_linear_args.y_peer)
   int peer_cols = 0;
   int peer_bcast = 0;
+  void* splitk_ws = nullptr;
+  long long splitk_ws_bytes = 0;
 };
 
 int run_gemm(const GemmCall& c, cudaStream_t st) {
@@ -469,7 +496,10 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
   const bool w4 = (c.bit == 4);
   const bool pair = c.q_w_up != nullptr;
   GemmPlan gp{};
-  if (int r = plan_gemm(c.M, c.N, c.K, c.bit, c.n_out, pair, c.tile_n, di.sms, &gp)) return r;
+  // split-K only for the plain dequant epilogue into y (raw int32 output and the tensor-parallel pushes keep one CTA per tile)
+  const bool can_split = c.splitk_ws != nullptr && (reinterpret_cast<uintptr_t>(c.splitk_ws) & 15) == 0 && c.epilogue == EPI_DEQUANT_F16 &&
+                         c.peer_cols <= 0 && c.peer_bcast <= 0 && c.N % 4 == 0;
+  if (int r = plan_gemm(c.M, c.N, c.K, c.bit, c.n_out, pair, c.tile_n, di.sms, &gp, can_split ? c.splitk_ws_bytes : 0)) return r;
   if (c.peer_cols > 0) {
     // tensor-parallel push: a tile must not straddle two ranks' column slices
     if (pair || c.bias || c.outl || c.residual || c.epilogue != EPI_DEQUANT_F16 || c.y_peer == nullptr)
@@ -574,6 +604,9 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
   p.y = static_cast<__half*>(c.y);
   p.peer_cols = c.peer_cols;
   p.peer_bcast = c.peer_bcast;
+  p.splits = two_cta ? 1 : gp.splits;
+  p.sk_cnt = static_cast<uint32_t*>(c.splitk_ws);
+  p.sk_ws = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(c.splitk_ws) + kSplitKCounterBytes);
   if (c.peer_cols > 0)
     for (int j = 0; j < c.N / c.peer_cols; ++j) p.y_peer[j] = static_cast<__half*>(c.y_peer[j]);
   for (int j = 0; j < c.peer_bcast; ++j) p.y_peer[j] = static_cast<__half*>(c.y_peer[j]);
@@ -602,7 +635,7 @@ int run_gemm(const GemmCall& c, cudaStream_t st) {
     const int grid2 = coop2 ? npairs * 2 : 2 * (tiles2 < npairs ? tiles2 : npairs);
     return launch_linear2(p, grid2, coop2, st);
   }
-  const int tiles = ((c.M + 127) / 128) * ((c.N + bn - 1) / bn);
+  const int tiles = ((c.M + 127) / 128) * ((c.N + bn - 1) / bn) * p.splits;    // work units
   const bool coop = p.fused_prologue != 0;
   const int grid = coop ? di.sms : (tiles < di.sms ? tiles : di.sms);
   if (w4) return bn == 256 ? launch_linear<256, true>(p, grid, coop, st) : launch_linear<128, true>(p, grid, coop, st);
@@ -927,6 +960,8 @@ int mixq_linear_fused(const mixq_linear_args* a, void* stream) {
   c.y_peer = a->y_peer;
   c.peer_cols = a->peer_cols;
   c.peer_bcast = a->peer_bcast;
+  c.splitk_ws = a->splitk_ws;
+  c.splitk_ws_bytes = a->splitk_ws_bytes;
   return run_gemm(c, static_cast<cudaStream_t>(stream));
 }
 

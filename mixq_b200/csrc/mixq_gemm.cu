@@ -8,8 +8,13 @@
 //   warp 0 / 3  TMA producers: activations / weights (cp.async.bulk.tensor, SWIZZLE_128B boxes, mbarrier complete_tx)
 //   warp 1      MMA issuer     (one lane issues tcgen05.mma; tcgen05.commit frees smem stages / publishes TMEM)
 //   warp 2      TMEM allocator (512 columns; double-buffered accumulators when they fit)
-//   warps 4-7   epilogue       (tcgen05.ld 32x32b -> registers -> dequant/bias/SiLU -> 16-byte global stores)
+//   warps 4-7   epilogue       (tcgen05.ld 32x32b -> registers -> dequant/bias/SiLU -> per-warp staging tile -> 128-byte stores;
+//                               the coalesced epilogue of the 2-CTA kernel, scale_col of the tile staged in shared memory)
 //   warps 8-11  (W4 only) nibble unpack: packed uint8 tile -> sign-extended int8 tile in the swizzled layout
+// Split-K (p.splits > 1; M <= 128 shapes with few tiles, e.g. the per-rank shapes of a TP = 8 70B model): a work unit is
+// (tile, split) and covers 1/splits of the int8 k-blocks; the first splits - 1 units of a tile store their int32 partial to a
+// workspace slice and bump the tile's counter, the last unit (which also runs the outlier k-blocks) waits for the counter,
+// adds the partials to its own accumulator and runs the dequant epilogue.  Integer sums: bit-identical to the unsplit launch.
 // With fused_prologue every warp first runs the activation prologue (rowquant.cuh) on its share of the
 // rows, the grid meets at one barrier, and the producer — which already has the first weight tiles in
 // flight — starts feeding q_x tiles.
@@ -49,6 +54,9 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
   const int MB = (p.M + BM - 1) / BM;
   const int NB = (p.N + BN - 1) / BN;
   const int ntiles = MB * NB;
+  const int S = p.splits;                           // >= 1
+  const int nunits = ntiles * S;
+  const int nk_s = (nk + S - 1) / S;                // int8 k-blocks per split (the host keeps every split non-empty)
   const int acc_cols = BN * (nko > 0 ? 2 : 1);      // s32 accumulator [+ f32 outlier accumulator]
   const int nacc = (2 * acc_cols <= 512) ? 2 : 1;
 
@@ -90,6 +98,20 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
   // Work items of this CTA in issue order: (tile i, k-block kb), kb in [0, nkt).
   // Pre-barrier we may only touch the weight operand; the activation operand exists after phase A.
   constexpr uint32_t kStageTx = Cfg::A_BYTES + (W4 ? 0 : Cfg::B_BYTES);
+  // unit u = (tile, split): int8 k-blocks [kb0, kb0 + nki) and, for the tile's last split, the nko outlier k-blocks
+  struct Unit { int tile, split, kb0, nki, nkt; };
+  auto unit_of = [&](int u) {
+    Unit w;
+    w.tile = u / S;
+    w.split = u - w.tile * S;
+    w.kb0 = w.split * nk_s;
+    const int kb1 = (w.kb0 + nk_s < nk) ? w.kb0 + nk_s : nk;
+    w.nki = kb1 - w.kb0;
+    w.nkt = w.nki + (w.split == S - 1 ? nko : 0);
+    return w;
+  };
+  // item j of a unit -> the k-block index produce() understands: [0, nk) int8, nk + o outlier
+  auto item_kb = [&](const Unit& w, int j) { return j < w.nki ? w.kb0 + j : nk + (j - w.nki); };
   auto produce = [&](int tile, int kb, int s, bool do_act, bool do_wgt, bool arm) {
     const int m0 = (tile % MB) * BM;
     const int n0 = (tile / MB) * BN;
@@ -109,10 +131,12 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
     (void)kStageTx;
   };
 
-  const int my_tiles = (static_cast<int>(blockIdx.x) < ntiles)
-                           ? (ntiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1
+  const int my_units = (static_cast<int>(blockIdx.x) < nunits)
+                           ? (nunits - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1
                            : 0;
-  const int my_items = my_tiles * nkt;
+  int my_items = 0;
+  for (int i = 0; i < my_units; ++i) my_items += unit_of(blockIdx.x + i * gridDim.x).nkt;
+  (void)nkt;
   // phase A parks its activation rows in the LAST pipeline stages; the weight prefetch may use the others
   const int row_stages = p.fused_prologue
                              ? static_cast<int>((static_cast<size_t>(p.rq.ngroups) * p.rq.K * 2 + Cfg::STAGE_BYTES - 1) / Cfg::STAGE_BYTES)
@@ -123,9 +147,10 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
   // The quantised weights are constants: fill every free pipeline stage with them BEFORE waiting for the kernels ahead
   // of us in the stream (programmatic dependent launch) — and, with the fused prologue, before phase A.
   if (warp == 3 && lane == 0) {
-    for (int it = 0; it < n_pre; ++it) {
-      const int tile = blockIdx.x + (it / nkt) * gridDim.x;
-      produce(tile, it % nkt, it, /*act*/ false, /*wgt*/ true, /*arm*/ true);
+    int it = 0;
+    for (int i = 0; i < my_units && it < n_pre; ++i) {
+      const Unit w = unit_of(blockIdx.x + i * gridDim.x);
+      for (int j = 0; j < w.nkt && it < n_pre; ++j, ++it) produce(w.tile, item_kb(w, j), it, /*act*/ false, /*wgt*/ true, /*arm*/ true);
     }
   }
   __syncwarp();
@@ -150,15 +175,15 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
     fence_proxy_async_all();
     int it = 0, s = 0;
     uint32_t ph = 0;
-    for (int i = 0; i < my_tiles; ++i) {
-      const int tile = blockIdx.x + i * gridDim.x;
-      for (int kb = 0; kb < nkt; ++kb, ++it) {
+    for (int i = 0; i < my_units; ++i) {
+      const Unit w = unit_of(blockIdx.x + i * gridDim.x);
+      for (int j = 0; j < w.nkt; ++j, ++it) {
         if (it >= n_pre) mbar_wait(&bar_empty[s], ph ^ 1, 1, s);
         if (elect_one()) {
           if (wgt) {
-            if (it >= n_pre) produce(tile, kb, s, false, true, true);
+            if (it >= n_pre) produce(w.tile, item_kb(w, j), s, false, true, true);
           } else {
-            produce(tile, kb, s, true, false, false);
+            produce(w.tile, item_kb(w, j), s, true, false, false);
           }
         }
         __syncwarp();
@@ -171,14 +196,15 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
     constexpr uint32_t idesc_f16 = make_idesc_f16(BM, BN);
     int s = 0;
     uint32_t ph = 0;
-    for (int i = 0; i < my_tiles; ++i) {
+    for (int i = 0; i < my_units; ++i) {
+      const Unit w = unit_of(blockIdx.x + i * gridDim.x);
       const int as = i % nacc;
       const uint32_t aph = (i / nacc) & 1;
       mbar_wait(&bar_tempty[as], aph ^ 1, 2, as);
       tc_fence_after();
       const uint32_t d_int = tmem_base + as * acc_cols;
       const uint32_t d_out = d_int + BN;
-      for (int kb = 0; kb < nkt; ++kb) {
+      for (int kb = 0; kb < w.nkt; ++kb) {
         if (W4) mbar_wait(&bar_ready[s], ph, 3, s);
         mbar_wait(&bar_full[s], ph, 4, s);
         tc_fence_after();
@@ -186,12 +212,12 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
         const uint64_t db = make_sw128_kmajor_desc(smem_u32(stage_b(s)));
         if (elect_one()) {
           if (trace && i == 0 && kb == 0) trace[3] = globaltimer_ns();
-          if (kb < nk) {
+          if (kb < w.nki) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)   // 4 x (K = 32 int8 = 32 B); +2 in the >>4-encoded start address
               umma_i8(d_int, da + 2 * k, db + 2 * k, idesc_i8, (kb | k) != 0);
           } else {
-            const int kbo = kb - nk;
+            const int kbo = kb - w.nki;
             int ksteps = (p.n_out - kbo * 64 + 15) / 16;
             if (ksteps > 4) ksteps = 4;
             for (int k = 0; k < ksteps; ++k)  // K = 16 fp16 = 32 B
@@ -208,8 +234,14 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
     if (trace && lane == 0) trace[4] = globaltimer_ns();
   } else if (warp >= 4 && warp < 8) {
     const int q = warp & 3;  // TMEM lane quarter this warp may read
-    for (int i = 0; i < my_tiles; ++i) {
-      const int tile = blockIdx.x + i * gridDim.x;
+    uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES + 256 + 512;
+    const uint32_t stage_sa = smem_u32(epi_smem + (warp - 4) * kEpiStageBytes);      // this warp's 4 KB staging tile
+    __half* s_scale = reinterpret_cast<__half*>(epi_smem + Cfg::EPI_WARPS * kEpiStageBytes);
+    const uint32_t scale_sa = smem_u32(s_scale);
+    const int mode = (p.outl != nullptr || p.bias != nullptr || p.act == 1) ? 2 : (p.residual != nullptr ? 1 : 0);
+    for (int i = 0; i < my_units; ++i) {
+      const Unit w = unit_of(blockIdx.x + i * gridDim.x);
+      const int tile = w.tile;
       const int m0 = (tile % MB) * BM;
       const int n0 = (tile / MB) * BN;
       const int as = i % nacc;
@@ -218,14 +250,62 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
       const bool row_ok = row < p.M;
       float xs = 0.f;
       if (p.epilogue == EPI_DEQUANT_F16 && row_ok) xs = __half2float(p.x_scale[row]);
+      // scale_col of the tile -> shared memory while the accumulator is still being computed (every row reads all of it;
+      // fetched per 16-column group from global it cost one exposed L2 round trip per group: 6 us per 128 x 128 tile)
+      if (p.epilogue == EPI_DEQUANT_F16 && !(S > 1 && w.split < S - 1)) {
+        named_bar_sync(13, 128);        // the previous tile's readers are done with s_scale
+        for (int j = (threadIdx.x - 128) * 8; j < BN; j += 128 * 8)
+          *reinterpret_cast<uint4*>(s_scale + j) = (n0 + j < p.N) ? __ldg(reinterpret_cast<const uint4*>(p.scale_col + n0 + j)) : make_uint4(0, 0, 0, 0);
+        named_bar_sync(13, 128);
+      }
 
       mbar_wait_warp(&bar_tfull[as], aph, 5, as);
       tc_fence_after();
       const uint32_t t_int = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * acc_cols;
       const uint32_t t_out = t_int + BN;
 
-      if (nko > 0) epilogue_span<true>(p, t_int, t_out, row, row_ok, n0, BN, xs, p.outl, p.ld_outl);
-      else epilogue_span<false>(p, t_int, 0u, row, row_ok, n0, BN, xs, p.outl, p.ld_outl);
+      const bool partial = S > 1 && w.split < S - 1;
+      const size_t slice = static_cast<size_t>(p.M) * p.N;
+      if (partial) {
+        // partial sum -> this split's workspace slice; publish: every thread fences its stores, then one counter bump
+        epilogue_span<false, 1>(p, t_int, 0u, row, row_ok, n0, BN, xs, nullptr, 0, p.sk_ws + w.split * slice);
+        __threadfence();
+        named_bar_sync(13, 128);
+        if (warp == 4 && lane == 0) {
+          __threadfence();
+          atomicAdd(p.sk_cnt + tile, 1u);
+        }
+      } else {
+        if (S > 1) {
+          // the tile's last split: wait for the others (they hold SMs of this very grid and never wait for anybody), fold them in
+          if (warp == 4 && lane == 0) {
+            const uint64_t t0 = globaltimer_ns();
+            uint32_t spins = 0;
+            while (ld_acquire_u32(p.sk_cnt + tile) < static_cast<uint32_t>(S - 1)) {
+              if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > MIXQ_SPIN_TIMEOUT_NS) spin_timeout_trap(10, tile, S);
+            }
+            p.sk_cnt[tile] = 0;        // re-armed for the next launch (nobody else touches it any more in this one)
+          }
+          named_bar_sync(13, 128);
+          if (trace && warp == 4 && lane == 0) trace[6] = globaltimer_ns();    // partials have arrived
+          splitk_fold(p, t_int, row, row_ok, n0, BN, p.sk_ws, S - 1, slice);
+          if (trace && warp == 4 && lane == 0) trace[7] = globaltimer_ns();    // folded into the accumulator
+        }
+        if (p.epilogue != EPI_DEQUANT_F16) {       // raw int32 accumulators (mixlib.gemm)
+          epilogue_span<false>(p, t_int, 0u, row, row_ok, n0, BN, xs, nullptr, 0);
+        } else {
+          const int mb = m0 + q * 32;
+          if (nko > 0) {
+            if (mode == 0) epilogue_run_coalesced<true, 0>(p, stage_sa, t_int, t_out, mb, n0, BN, xs, scale_sa, lane);
+            else if (mode == 1) epilogue_run_coalesced<true, 1>(p, stage_sa, t_int, t_out, mb, n0, BN, xs, scale_sa, lane);
+            else epilogue_run_coalesced<true, 2>(p, stage_sa, t_int, t_out, mb, n0, BN, xs, scale_sa, lane);
+          } else {
+            if (mode == 0) epilogue_run_coalesced<false, 0>(p, stage_sa, t_int, 0u, mb, n0, BN, xs, scale_sa, lane);
+            else if (mode == 1) epilogue_run_coalesced<false, 1>(p, stage_sa, t_int, 0u, mb, n0, BN, xs, scale_sa, lane);
+            else epilogue_run_coalesced<false, 2>(p, stage_sa, t_int, 0u, mb, n0, BN, xs, scale_sa, lane);
+          }
+        }
+      }
       tc_fence_before();
       mbar_arrive(&bar_tempty[as]);
     }
@@ -237,10 +317,11 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
     const int t = threadIdx.x - 256;
     int s = 0;
     uint32_t ph = 0;
-    for (int i = 0; i < my_tiles; ++i) {
-      for (int kb = 0; kb < nkt; ++kb) {
+    for (int i = 0; i < my_units; ++i) {
+      const Unit w = unit_of(blockIdx.x + i * gridDim.x);
+      for (int kb = 0; kb < w.nkt; ++kb) {
         mbar_wait(&bar_full[s], ph, 6, s);
-        if (kb < nk) {
+        if (kb < w.nki) {
           for (int r = t; r < BN; r += 128) {
             const uint4* src = reinterpret_cast<const uint4*>(stage_bp(s) + r * 64);
             uint8_t* drow = stage_b(s) + r * 128;

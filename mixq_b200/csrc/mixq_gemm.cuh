@@ -32,6 +32,11 @@ struct LinearParams {
   int peer_cols;
   int peer_bcast;      // > 0: every tile goes, whole, to each of y_peer[0 .. peer_bcast) (fp16 [M,N] receive slots): the one-shot
                        // exchange for small worlds — no second phase, (world - 1) * M * N fp16 over NVLink per rank
+  // split-K (1-CTA kernel, M <= 128: a handful of tiles would leave most SMs idle): `splits` CTAs share a tile's K range, the
+  // first splits - 1 park their int32 partial in sk_ws [splits - 1][M, N] and bump sk_cnt[tile], the last one adds them up
+  int splits;
+  int32_t* sk_ws;
+  uint32_t* sk_cnt;
   int32_t* y_i32;
   int M, N, K;
   int n_out;           // outlier columns multiplied on the tensor cores (0 = none)
@@ -62,7 +67,9 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES + BP_BYTES;
   static constexpr int STAGES = W4 ? (BN == 128 ? 5 : 3) : (BN == 128 ? 6 : 4);
   static constexpr int NUM_THREADS = W4 ? 384 : 256;         // W4 adds 4 unpack warps
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 512 /*RowQuantSmem*/;
+  static constexpr int EPI_WARPS = 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 512 /*RowQuantSmem*/ +
+                                    EPI_WARPS * 32 * 128 /*epilogue staging*/ + 512 /*scale_col of the tile*/;
 };
 
 template <int BN, bool W4>

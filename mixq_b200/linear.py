@@ -299,6 +299,11 @@ class MixLinear_GEMM(nn.Module):
             ptrs, a.peer_cols, a.peer_bcast = push
             for j, pj in enumerate(ptrs):
                 a.y_peer[j] = pj
+        if M <= 128 and push is None:      # few tiles: let the library split K over several CTAs per tile
+            ws = cache.splitk_buffer()
+            a.splitk_ws, a.splitk_ws_bytes = ws.data_ptr(), ws.numel() * 4
+        else:
+            a.splitk_ws, a.splitk_ws_bytes = 0, 0
         a.act = act
         a.skip_prologue = 1 if skip_prologue else 0
         a.grid_sync = _ptr(cache.grid_sync)

@@ -278,7 +278,18 @@ def test_rmsnorm_and_fused_extract(lib, M, K, n):
 
 
 # ----------------------------------------------------------------------------- the fused single launch
-def run_fused(lib, x, qw, ws, cols, wc, bit, *, bias=None, act=0, residual=None, norm_w=None, tile=0, skip=None, up=None):
+_SPLITK_WS = {}
+
+
+def splitk_ws():
+    """One zero-filled split-K workspace for the whole session (mixq_linear_args.splitk_ws): launches leave its counters at zero."""
+    if "ws" not in _SPLITK_WS:
+        _SPLITK_WS["ws"] = torch.zeros(16 * 1024 * 1024 // 4, dtype=torch.int32, device="cuda")
+    return _SPLITK_WS["ws"]
+
+
+def run_fused(lib, x, qw, ws, cols, wc, bit, *, bias=None, act=0, residual=None, norm_w=None, tile=0, skip=None, up=None,
+              splitk=True):
     from mixq_b200 import _lib
     M, K = x.shape
     N = qw.shape[0]
@@ -315,6 +326,8 @@ def run_fused(lib, x, qw, ws, cols, wc, bit, *, bias=None, act=0, residual=None,
     a.skip_prologue = 0 if skip is None else 1
     if up is not None:
         a.q_weight_up = t["qw_up"].data_ptr(); a.scale_col_up = t["ws_up"].data_ptr(); a.weight_cache_up = t["wc_up"].data_ptr()
+    if splitk and M <= 128:     # as MixLinear_GEMM does: small-M launches may split K over several CTAs per tile
+        a.splitk_ws, a.splitk_ws_bytes = splitk_ws().data_ptr(), splitk_ws().numel() * 4
     check(lib.mixq_linear_fused(C.byref(a), st()), "mixq_linear_fused")
     torch.cuda.synchronize()
     return t
@@ -512,6 +525,42 @@ def test_launch_modes_bit_identical(lib, monkeypatch):
         check(lib.mixq_set_grid_barrier_mode(0))
     for y in ys[1:]:
         bits_equal(y, ys[0], "y across launch modes")
+
+
+@pytest.mark.parametrize("M,N,K,bit,n", [(128, 1280, 8192, 8, 41), (128, 3584, 8192, 8, 70), (128, 8192, 3584, 8, 0),
+                                         (100, 1288, 4096, 8, 41), (32, 4096, 4096, 8, 41), (7, 520, 2048, 8, 3),
+                                         (128, 1280, 8192, 4, 128), (64, 3584, 4096, 4, 128)])
+def test_split_k_bit_identical(lib, monkeypatch, M, N, K, bit, n):
+    """M <= 128 shapes with few tiles (C1; the per-rank shapes of C5) can split K over up to 4 CTAs per tile when the caller
+    hands a workspace (forced here with MIXQ_DEBUG_SPLITS: the planner itself only splits for M <= 32 and long K, where it
+    measured faster): int32 partial sums are added exactly, so y must equal the unsplit launch bit for bit — with outliers,
+    bias, residual, ragged M / N, bit 4, and launched twice in a row (the per-tile counters re-arm themselves)."""
+    monkeypatch.setenv("MIXQ_DEBUG_SPLITS", "4")
+    lib.mixq_reload_debug_env()
+    rng = np.random.default_rng(M * 31 + N)
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    cols = np.sort(rng.choice(K, n, replace=False)).astype(np.int32) if n else np.zeros(0, np.int32)
+    if n:
+        x[:, cols] *= 15
+    x = x.astype(np.float16)
+    W = (rng.standard_normal((N, K)) * 0.02).astype(np.float16)
+    if bit == 8:
+        qw, ws = O.quant_weight_w8(W)
+        wc = O.weight_cache_columns(qw, ws, cols, 8) if n else None
+    else:
+        scales = rng.random(K).astype(np.float32)
+        scales[cols] += 10
+        qw, ws, wc, cols = O.quant_weight_w4(W, scales, n)
+    bias = (rng.standard_normal(N) * 0.1).astype(np.float16)
+    res = rng.standard_normal((M, N)).astype(np.float16)
+    base = run_fused(lib, x, qw, ws, cols, wc, bit, bias=bias, residual=res, splitk=False)
+    for rep in range(2):
+        t = run_fused(lib, x, qw, ws, cols, wc, bit, bias=bias, residual=res, splitk=True)
+        bits_equal(host(t["y"]), host(base["y"]), f"y split-K launch {rep}")
+        bits_equal(host(t["q_x"]), host(base["q_x"]), "q_x")
+    assert int(splitk_ws()[:1024].abs().sum()) == 0, "split-K counters must be back at zero after the launch"
+    monkeypatch.delenv("MIXQ_DEBUG_SPLITS")
+    lib.mixq_reload_debug_env()
 
 
 # ----------------------------------------------------------------------------- properties at BASELINE.json sizes

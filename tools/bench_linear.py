@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--nout", type=int, default=41)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--eager", action="store_true")
+    ap.add_argument("--no-splitk", action="store_true", help="M <= 128: do not hand the library a split-K workspace")
     args = ap.parse_args()
     lib = _lib.load()
     shapes = SHAPES[args.shapes] if args.shapes in SHAPES else [tuple(int(v) for v in s.split("x")) for s in args.shapes.split(",")]
@@ -70,6 +71,7 @@ def main():
         ao = torch.zeros(M, cap, dtype=torch.float16, device=dev)
         y = torch.zeros(M, N, dtype=torch.float16, device=dev)
         sync = torch.zeros(1, dtype=torch.int32, device=dev)
+        skws = torch.zeros(16 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)
         x = x0.clone()
         for mode in args.modes.split(","):
             arglist = []
@@ -88,6 +90,8 @@ def main():
                 a.q_x = q_x.data_ptr(); a.x_scale = xs.data_ptr(); a.act_outliers = ao.data_ptr(); a.ld_ao = cap
                 a.sigma = 6.0; a.y = y.data_ptr(); a.grid_sync = sync.data_ptr(); a.tile_n = args.tile
                 a.skip_prologue = 1 if sub == "skip" else 0
+                if M <= 128 and not args.no_splitk:
+                    a.splitk_ws, a.splitk_ws_bytes = skws.data_ptr(), skws.numel() * 4
                 arglist.append(a)
 
             def run_all():

@@ -4,7 +4,7 @@ import torch
 sys.path.insert(0, ".")
 from mixq_b200 import _lib
 lib = _lib.load()
-M = 512
+M = int(os.environ.get('M', '512'))
 dev = "cuda"
 g = torch.Generator(device=dev).manual_seed(0)
 trace = torch.zeros(16384, dtype=torch.int64, device=dev)
@@ -25,6 +25,7 @@ for (N, K) in SHAPES:
              (torch.randn(N, cap, generator=g, device=dev) * 0.02).half()) for _ in range(4)]
     q_x = torch.zeros(M, K, dtype=torch.int8, device=dev); xs = torch.zeros(M, dtype=torch.float16, device=dev)
     ao = torch.zeros(M, cap, dtype=torch.float16, device=dev); y = torch.zeros(M, N, dtype=torch.float16, device=dev)
+    skws = torch.zeros(16 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)
     sync = torch.zeros(1, dtype=torch.int32, device=dev); x = x0.clone(); nw = torch.ones(K, dtype=torch.float16, device=dev)
     for mode in MODES:
         for it, (qw, ws, wc) in enumerate(ws_l):
@@ -38,6 +39,8 @@ for (N, K) in SHAPES:
                 a.q_weight_up = qw2.data_ptr(); a.scale_col_up = ws2.data_ptr(); a.weight_cache_up = wc2.data_ptr()
             if NORM:
                 a.norm_weight = nw.data_ptr(); a.eps = 1e-5
+            if os.environ.get('SPLITK') == '1':
+                a.splitk_ws, a.splitk_ws_bytes = skws.data_ptr(), skws.numel() * 4
             a.sigma = 6.0; a.y = y.data_ptr(); a.grid_sync = sync.data_ptr(); a.skip_prologue = 1 if mode == "skip" else 0; a.tile_n = TILE
             lib.mixq_set_trace_buffer(trace.data_ptr() if it == 3 else 0)
             trace.zero_()
@@ -52,6 +55,8 @@ for (N, K) in SHAPES:
             return (f"{(v.min()-t0)/1e3:6.2f}..{(v.max()-t0)/1e3:6.2f}" if len(v) else "      -       ")
         print(f"N={N} K={K} tile={TILE} {mode:5s} us since first CTA start: start {col(0)} | mask built {col(6)} | row0 absmax {col(7)} | prologue done {col(1)} | barrier passed {col(2)} | "
               f"first MMA {col(3)} | int MMAs issued {col(6)} | last MMA {col(4)} | epilogue done {col(5)}")
+        if os.environ.get('SPLITK') == '1':
+            print(f"    split-K finishers: partials arrived {col(6)} | folded {col(7)} | done (per CTA, us): " + " ".join(f"{(v - t0) / 1e3:.1f}" for v in t[:, 5][t[:, 5] > 0].tolist()[:48]))
         base0 = t[0, 0]
         pp = full[1536:1568].view(16, 2)
         if pp[0, 0] > 0:
