@@ -200,7 +200,8 @@ typedef struct mixq_linear_args {
   /* split-K workspace (optional; M <= 128 only): with a handful of 128-row tiles most SMs would idle, so up to 4 CTAs share a
    * tile's K range and meet through this buffer — int32 partial sums, added exactly, so the result is bit-identical to the
    * unsplit launch.  Caller-owned device memory, ZERO-FILLED ONCE by the caller (the first 4096 bytes are per-tile counters
-   * that every launch leaves at zero again), at least 4096 + 3 * M * N * 4 bytes to allow the full split; one launch at a time
+   * that every launch leaves at zero again), then one 64 KB block per (128 x 128 tile, non-final split):
+   * 4096 + ceil(M/128) * ceil(N/128) * 3 * 65536 bytes allow the full split, less caps the split factor; one launch at a time
    * per workspace.  NULL = never split. */
   void* splitk_ws;
   long long splitk_ws_bytes;

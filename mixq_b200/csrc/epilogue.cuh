@@ -120,11 +120,9 @@ __device__ __forceinline__ void epilogue_chunk(const LinearParams& p, uint32_t t
 // A span of `ncols` (multiple of 16) accumulator columns of one row, as a ROLLED loop over 16-column groups: the body is
 // ~200 instructions and stays in the instruction cache (the fully unrolled 32-column form above is paced by
 // instruction fetch when only 1-2 warps per scheduler run it).  Every lane of the warp must call this.
-// SK == 1 (split-K, 1-CTA kernel): this CTA holds a PARTIAL int32 sum — store it to its workspace slice `sk_part` [M, N].
-template <bool HAS_O, int SK = 0>
+template <bool HAS_O>
 __device__ __forceinline__ void epilogue_span(const LinearParams& p, uint32_t t_int, uint32_t t_out, int row, bool row_ok,
-                                              int n0, int ncols, float xs, const __half* addend, int ld_addend,
-                                              int32_t* sk_part = nullptr) {
+                                              int n0, int ncols, float xs, const __half* addend, int ld_addend) {
   const bool has_outl = addend != nullptr;
   const bool has_bias = p.bias != nullptr;
   const bool has_res = p.residual != nullptr;
@@ -139,13 +137,6 @@ __device__ __forceinline__ void epilogue_span(const LinearParams& p, uint32_t t_
     tmem_ld_wait();
     const int n = n0 + c;
     if (!row_ok || n >= p.N) continue;
-    if (SK == 1) {
-      uint4* dst = reinterpret_cast<uint4*>(sk_part + static_cast<size_t>(row) * p.N + n);
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-        if (n + g * 4 < p.N) dst[g] = make_uint4(acc[4 * g], acc[4 * g + 1], acc[4 * g + 2], acc[4 * g + 3]);
-      continue;
-    }
     if (raw) {
       int32_t* dst = p.y_i32 + static_cast<size_t>(row) * p.N + n;
 #pragma unroll
@@ -196,44 +187,48 @@ __device__ __forceinline__ void epilogue_span(const LinearParams& p, uint32_t t_
 }
 
 
-// Split-K, the tile's last split: fold the other splits' partial sums (slices of `stride` elements at `part`, `nparts` <= 3 of
-// them) into this CTA's int32 accumulator, in place in TMEM, 16 columns at a time with the next group's loads already in
-// flight.  Integer adds: exact and order-independent, so the dequant epilogue that follows sees the unsplit accumulator.
-// Every lane of the warp must call this (tcgen05.ld / st are warp-collective); lane = accumulator row.
-__device__ __forceinline__ void splitk_fold(const LinearParams& p, uint32_t t_int, int row, bool row_ok, int n0, int ncols,
-                                            const int32_t* part, int nparts, size_t stride) {
-  auto load = [&](int c, uint4 (&pv)[3][4]) {
-    const int n = n0 + c;
-#pragma unroll
-    for (int sp = 0; sp < 3; ++sp) {
-      const uint4* src = reinterpret_cast<const uint4*>(part + sp * stride + static_cast<size_t>(row) * p.N + n);
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-        pv[sp][g] = (row_ok && sp < nparts && n + g * 4 < p.N) ? __ldcg(src + g) : make_uint4(0, 0, 0, 0);
-    }
-  };
-  uint4 cur[3][4], nxt[3][4];
-  load(0, cur);
+// Split-K (1-CTA kernel).  A partial int32 accumulator tile (128 rows x 128 columns) travels through a 64 KB workspace block
+// laid out [16-column group g][row][16]: every tcgen05.ld group of a warp (32 rows x 64 bytes) is 2 KB of contiguous memory —
+// coalesced stores on the way out, ONE bulk copy per block into the finisher's (idle) pipeline stages on the way in, and
+// conflict-free 16-byte shared-memory reads in the fold.  Every lane of the warp must call these (tcgen05.ld / st are
+// warp-collective); row_in_tile = TMEM lane = 32 * quarter + lane.
+constexpr int kSplitKBlockInts = 128 * 128;
+__device__ __forceinline__ void splitk_stage_partial(uint32_t t_int, uint32_t block_sa, int row_in_tile) {
+  // TMEM -> the block layout in (idle) shared memory; one bulk store moves it to the workspace afterwards
 #pragma unroll 1
-  for (int c = 0; c < ncols; c += 16) {
-    uint32_t acc[16];
-    tmem_ld_32x16(t_int + c, acc);
-    if (c + 16 < ncols) load(c + 16, nxt);
+  for (int g = 0; g < 8; g += 2) {
+    uint32_t acc[32];
+    tmem_ld_32x32(t_int + g * 16, acc);
     tmem_ld_wait();
 #pragma unroll
-    for (int sp = 0; sp < 3; ++sp)
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t dst = block_sa + static_cast<uint32_t>((g + h) * 128 + row_in_tile) * 64u;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        acc[4 * g] += cur[sp][g].x;
-        acc[4 * g + 1] += cur[sp][g].y;
-        acc[4 * g + 2] += cur[sp][g].z;
-        acc[4 * g + 3] += cur[sp][g].w;
+      for (int v = 0; v < 4; ++v)
+        sts128(dst + v * 16, make_uint4(acc[16 * h + 4 * v], acc[16 * h + 4 * v + 1], acc[16 * h + 4 * v + 2], acc[16 * h + 4 * v + 3]));
+    }
+  }
+}
+// The tile's last split: add `nparts` blocks (already in shared memory at parts_sa, 64 KB apart) to the accumulator, in place in
+// TMEM.  Integer adds: exact and order-independent, so the dequant epilogue that follows sees the unsplit accumulator.
+__device__ __forceinline__ void splitk_fold_smem(uint32_t t_int, uint32_t parts_sa, int nparts, int row_in_tile) {
+#pragma unroll 1
+  for (int g = 0; g < 8; ++g) {
+    uint32_t acc[16];
+    tmem_ld_32x16(t_int + g * 16, acc);
+    tmem_ld_wait();
+    for (int sp = 0; sp < nparts; ++sp) {
+      const uint32_t src = parts_sa + static_cast<uint32_t>(sp) * (kSplitKBlockInts * 4) + static_cast<uint32_t>(g * 128 + row_in_tile) * 64u;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const uint4 pv = lds128(src + v * 16);
+        acc[4 * v] += pv.x;
+        acc[4 * v + 1] += pv.y;
+        acc[4 * v + 2] += pv.z;
+        acc[4 * v + 3] += pv.w;
       }
-    tmem_st_32x16(t_int + c, acc);
-#pragma unroll
-    for (int sp = 0; sp < 3; ++sp)
-#pragma unroll
-      for (int g = 0; g < 4; ++g) cur[sp][g] = nxt[sp][g];
+    }
+    tmem_st_32x16(t_int + g * 16, acc);
   }
   tmem_st_wait();
 }

@@ -374,21 +374,24 @@ int plan_gemm(int M, int N, int K, int bit, int n_out, bool pair, int tile_req, 
   // (256 bytes of K) per op and pipeline stage whenever at least three such stages fit
   g->splits = 1;
   if (!two_cta && splitk_ws_bytes > kSplitKCounterBytes && tile_req == 0 && g_tile_n.load(std::memory_order_relaxed) == 0) {
-    // few 128-row tiles: split K over up to 4 CTAs per tile, 128-wide tiles for parallelism.  Measured (profiles/
-    // r02_bench_linear_smallM_cap*.jsonl, r02_trace_splitk.log): the mainloop shrinks as expected, but the last split folds the
-    // partials in with row-strided 16-byte loads, ~6 us per 128-row slice — it only pays when few rows are live (M <= 32)
-    // and K is long (>= 64 k-blocks): 4096 x 11008 at M = 32 goes 32.9 -> 25.6 us, every M = 128 shape gets slower.
+    // few 128-row tiles: one SM lands ~63 B/clk, a 128 x 128 tile's k-block (32 KB) costs ~0.27 us whatever else idles.
+    // Split K over S <= 4 CTAs per tile (single wave: t128 * S <= SMs; every split keeps >= 4 k-blocks) when the model
+    //   t(S) = nk / S * 0.27 us + (S > 1 ? 5.0 + 1.0 (S - 1) : 0)      [partial store + counter + bulk copies + fold]
+    // says it pays (constants from profiles/r02_trace_splitk_v2.log: 4096 x 4096 at M = 32 must NOT split, 17.8 vs 19.9 us).
     const int t128 = ((M + 127) / 128) * ((N + 127) / 128);
     const int nk = (K + 127) / 128;
-    int S = (M <= 32 && nk >= 64) ? sms / t128 : 1;
-    if (S > 4) S = 4;
-    if (S > nk / 4) S = nk / 4;
-    if (const int cap = g_dbg.splits.load(std::memory_order_relaxed); cap >= 1) {      // MIXQ_DEBUG_SPLITS: force (tests, tuning)
-      S = sms / t128;
-      if (S > cap) S = cap;
-      if (S > nk / 4) S = nk / 4;
+    int smax = sms / t128;
+    if (smax > 4) smax = 4;
+    if (smax > nk / 4) smax = nk / 4;
+    if (const int cap = g_dbg.splits.load(std::memory_order_relaxed); cap >= 1 && smax > cap) smax = cap;   // MIXQ_DEBUG_SPLITS
+    while (smax > 1 && kSplitKCounterBytes + static_cast<long long>(t128) * (smax - 1) * 65536 > splitk_ws_bytes) --smax;
+    int S = 1;
+    double best = nk * 0.27;
+    for (int c = 2; c <= smax; ++c) {
+      const double t = static_cast<double>((nk + c - 1) / c) * 0.27 + 5.0 + 1.0 * (c - 1);
+      if (t < best - 0.5) { best = t; S = c; }
     }
-    while (S > 1 && kSplitKCounterBytes + static_cast<long long>(S - 1) * M * N * 4 > splitk_ws_bytes) --S;
+    if (g_dbg.splits.load(std::memory_order_relaxed) >= 2 && smax >= 2) S = smax;      // forced (tests, tuning)
     if (S >= 2 && t128 * 4 <= kSplitKCounterBytes) {
       bn = 128;
       g->splits = S;

@@ -11,10 +11,12 @@
 //   warps 4-7   epilogue       (tcgen05.ld 32x32b -> registers -> dequant/bias/SiLU -> per-warp staging tile -> 128-byte stores;
 //                               the coalesced epilogue of the 2-CTA kernel, scale_col of the tile staged in shared memory)
 //   warps 8-11  (W4 only) nibble unpack: packed uint8 tile -> sign-extended int8 tile in the swizzled layout
-// Split-K (p.splits > 1; M <= 128 shapes with few tiles, e.g. the per-rank shapes of a TP = 8 70B model): a work unit is
-// (tile, split) and covers 1/splits of the int8 k-blocks; the first splits - 1 units of a tile store their int32 partial to a
-// workspace slice and bump the tile's counter, the last unit (which also runs the outlier k-blocks) waits for the counter,
-// adds the partials to its own accumulator and runs the dequant epilogue.  Integer sums: bit-identical to the unsplit launch.
+// Split-K (p.splits > 1; M <= 128 shapes with few tiles, e.g. the per-rank shapes of a TP = 8 70B model: one SM lands only
+// ~63 B/clk, so a 128 x 128 tile's mainloop is bound by ONE SM's share of the L2 bandwidth): a work unit is (tile, split) and
+// covers 1/splits of the int8 k-blocks; the first splits - 1 units of a tile store their int32 partial to a 64 KB workspace
+// block and bump the tile's counter, the last unit (which also runs the outlier k-blocks) waits for the counter, bulk-copies
+// the blocks into its idle pipeline stages, folds them into its TMEM accumulator and runs the dequant epilogue.  Integer sums:
+// bit-identical to the unsplit launch.  A split launch is a single wave (units <= SMs, planned on the host).
 // With fused_prologue every warp first runs the activation prologue (rowquant.cuh) on its share of the
 // rows, the grid meets at one barrier, and the producer — which already has the first weight tiles in
 // flight — starts feeding q_x tiles.
@@ -39,7 +41,8 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
   uint64_t* bar_ready = bar_empty + STAGES;  // W4: unpacked B tile is ready for the MMA
   uint64_t* bar_tfull = bar_ready + STAGES;
   uint64_t* bar_tempty = bar_tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+  uint64_t* bar_sk = bar_tempty + 2;          // split-K: the other splits' partial tiles have landed in shared memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_sk + 1);
 
   auto stage_a = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
   auto stage_b = [&](int s) { return smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
@@ -78,6 +81,7 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
       mbar_init(&bar_tfull[s], 1);
       mbar_init(&bar_tempty[s], 128);
     }
+    mbar_init(bar_sk, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -239,6 +243,7 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
     __half* s_scale = reinterpret_cast<__half*>(epi_smem + Cfg::EPI_WARPS * kEpiStageBytes);
     const uint32_t scale_sa = smem_u32(s_scale);
     const int mode = (p.outl != nullptr || p.bias != nullptr || p.act == 1) ? 2 : (p.residual != nullptr ? 1 : 0);
+    uint32_t sk_uses = 0;      // finished split tiles so far (phase of bar_sk)
     for (int i = 0; i < my_units; ++i) {
       const Unit w = unit_of(blockIdx.x + i * gridDim.x);
       const int tile = w.tile;
@@ -265,19 +270,27 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
       const uint32_t t_out = t_int + BN;
 
       const bool partial = S > 1 && w.split < S - 1;
-      const size_t slice = static_cast<size_t>(p.M) * p.N;
+      // split-K workspace: tile t owns S - 1 blocks of 64 KB, one per non-final split
+      int32_t* sk_blocks = p.sk_ws + static_cast<size_t>(tile) * (S - 1) * kSplitKBlockInts;
       if (partial) {
-        // partial sum -> this split's workspace slice; publish: every thread fences its stores, then one counter bump
-        epilogue_span<false, 1>(p, t_int, 0u, row, row_ok, n0, BN, xs, nullptr, 0, p.sk_ws + w.split * slice);
-        __threadfence();
+        // partial sum -> shared memory (the pipeline stages are idle: single wave, this is the CTA's only unit) -> ONE bulk store
+        // into this split's workspace block -> counter bump.  (Direct 16-byte stores + __threadfence by 128 threads took 4 us.)
+        splitk_stage_partial(t_int, smem_u32(smem), q * 32 + lane);
+        fence_proxy_async_smem();
         named_bar_sync(13, 128);
         if (warp == 4 && lane == 0) {
+          bulk_store(sk_blocks + static_cast<size_t>(w.split) * kSplitKBlockInts, smem_u32(smem), kSplitKBlockInts * 4);
+          tma_store_commit();
+          tma_store_wait_all<0>();     // the writes are complete, not just read out of shared memory
+          fence_proxy_async_all();
           __threadfence();
           atomicAdd(p.sk_cnt + tile, 1u);
         }
       } else {
         if (S > 1) {
-          // the tile's last split: wait for the others (they hold SMs of this very grid and never wait for anybody), fold them in
+          // the tile's last split: wait for the others (they hold SMs of this very grid and never wait for anybody), bring their
+          // blocks into the pipeline stages — idle by now: a split launch is a single wave, this is the CTA's only unit — with
+          // one bulk copy each, and fold them into the accumulator
           if (warp == 4 && lane == 0) {
             const uint64_t t0 = globaltimer_ns();
             uint32_t spins = 0;
@@ -285,10 +298,15 @@ mixq_linear_kernel(const __grid_constant__ LinearParams p) {
               if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > MIXQ_SPIN_TIMEOUT_NS) spin_timeout_trap(10, tile, S);
             }
             p.sk_cnt[tile] = 0;        // re-armed for the next launch (nobody else touches it any more in this one)
+            fence_proxy_async_all();   // (generic-proxy acquire above -> the async-proxy reads of the bulk copies below)
+            mbar_arrive_expect_tx(bar_sk, static_cast<uint32_t>(S - 1) * (kSplitKBlockInts * 4));
+            for (int sp = 0; sp < S - 1; ++sp)
+              bulk_load(smem + sp * (kSplitKBlockInts * 4), sk_blocks + static_cast<size_t>(sp) * kSplitKBlockInts, kSplitKBlockInts * 4, bar_sk);
+            if (trace) trace[6] = globaltimer_ns();    // partials have arrived in the workspace
           }
-          named_bar_sync(13, 128);
-          if (trace && warp == 4 && lane == 0) trace[6] = globaltimer_ns();    // partials have arrived
-          splitk_fold(p, t_int, row, row_ok, n0, BN, p.sk_ws, S - 1, slice);
+          mbar_wait_warp(bar_sk, sk_uses & 1u, 11, tile);
+          ++sk_uses;
+          splitk_fold_smem(t_int, smem_u32(smem), S - 1, q * 32 + lane);
           if (trace && warp == 4 && lane == 0) trace[7] = globaltimer_ns();    // folded into the accumulator
         }
         if (p.epilogue != EPI_DEQUANT_F16) {       // raw int32 accumulators (mixlib.gemm)
