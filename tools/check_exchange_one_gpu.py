@@ -80,6 +80,9 @@ def run(world, one_shot, quant, M=64, N=1024, Ktot=2048):
                     ptrs = [recv[j][b].data_ptr() + r * slot * 2 for j in range(world)]
                     push = (ptrs, Ns, 0)
                 lins[r](xs[r].clone(), None, True, push=push)
+        # On one device the ranks' GEMMs (one CTA per SM, grid barrier) must not share the SMs with another rank's spinning finish
+        # kernel: let the pushes land first.  (On N GPUs every device runs one rank and the finish kernel follows its GEMM directly.)
+        torch.cuda.synchronize()
         for r in range(world):
             with torch.cuda.stream(streams[r]):
                 a = _lib.ExchangePollArgs()
