@@ -37,6 +37,8 @@ def parse():
     ap.add_argument("--bit", type=int, default=8, choices=[4, 8])
     ap.add_argument("--layers", type=int, default=None, help="debug: fewer layers (the number is reported, never default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full-lm-head", action="store_true",
+                    help="N > 1: keep the fp16 lm_head replicated (default: vocab-parallel, every rank computes its slice of the logits)")
     ap.add_argument("--kv-len", type=int, default=-1,
                     help="KV-cache variant of the metric: every sequence already holds this many tokens (-1: the largest power of "
                          "two minus one, up to 1023, whose cache fits beside the model at N=1; 0: off)")
@@ -369,6 +371,19 @@ def run_mixq(args):
     logits_steady = model.step(tok0)
     launches_per_step = _lib.launch_count() - n0
     tp_parity = tp_parity_check(args, cfg, model, tok0, rank, world) if world > 1 else None
+    vocab_parallel = None
+    if world > 1 and not args.full_lm_head and cfg.vocab % world == 0:
+        # Megatron-style vocab-parallel head: every rank keeps vocab / N rows of the fp16 lm_head and computes its slice of the
+        # logits; the next token is the best of the ranks' local maxima.  Checked here against the full head.
+        model.shard_lm_head()
+        model._rank_barrier()
+        shard = model.step(tok0)
+        v = cfg.vocab // world
+        want = logits_steady[:, rank * v:(rank + 1) * v].float()
+        rel_v = float((shard.float() - want).norm() / want.norm())
+        same_tok = bool(torch.equal(model.argmax(shard), torch.argmax(model.gather_logits(shard), dim=-1)))
+        vocab_parallel = {"rows_per_rank": v, "rel_vs_full_head_slice": rel_v, "distributed_argmax_equals_argmax_of_gathered": same_tok}
+        assert rel_v <= 1e-3 and same_tok, vocab_parallel
     model.capture(tok0)
     dev_tokens = [t.cuda() for t in host_tokens]
     torch.cuda.synchronize()
@@ -401,7 +416,7 @@ def run_mixq(args):
     f0.record()
     for i in range(args.steps):
         logits = model.replay(host_tokens[i % n_tok_sets])          # pinned host -> static device buffer (H2D)
-        host_next.copy_(torch.argmax(logits, dim=-1), non_blocking=True)   # result D2H
+        host_next.copy_(model.argmax(logits), non_blocking=True)   # result D2H (vocab-parallel head: + one tiny all-gather)
         torch.cuda.current_stream().synchronize()
     f1.record()
     barrier()
@@ -572,12 +587,16 @@ def run_mixq(args):
                        "l2": "weights (>= 6 GB per step) exceed the 126 MB L2: inputs larger than L2, no flush",
                        "outliers_layer0": {k: m._n_ind for k, m in model.layers[0].items() if isinstance(m, MixLinear_GEMM)},
                        "cuda_graph": True, "programmatic_dependent_launch": True,
+                       "lm_head": ("fp16, replicated" if vocab_parallel is None else
+                                   f"fp16, vocab-parallel: {vocab_parallel['rows_per_rank']} rows per rank, logits stay sharded; next token = best of "
+                                   "the ranks' local maxima (e2e includes that exchange)"),
                        "exchange": (None if world == 1 else ((type(model.xchg).__name__ + " kernel, " + ("two-shot" if model_xchg_two_shot else "one-shot"))
                                                               if model_xchg else "nccl all-reduce + add"))},
             "e2e": {"value": B / (ms_e2e * 1e-3 / args.steps), "unit": "tokens/s", "h2d_bytes_per_step": B * 8,
                     "d2h_bytes_per_step": B * 8, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,
             "tp_parity": tp_parity,
+            "vocab_parallel_check": vocab_parallel,
             "kv_variant": kv_variant,
             "step_breakdown_us": {"linear_us": tot_t * len(model.layers) * 1e6,
                                   "exchange_us": None if exchange_us is None else exchange_us * 2 * len(model.layers),

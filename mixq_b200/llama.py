@@ -149,6 +149,7 @@ class LlamaDecoder:
         # attention + o_proj's activation prologue in one launch (MIXQ_FUSE_ATTN_QUANT=0: separate launches)
         self.fuse_attn_quant = os.environ.get("MIXQ_FUSE_ATTN_QUANT", "1") != "0"
         self.fuse_xchg_quant = os.environ.get("MIXQ_TP_FUSE_QUANT", "1") != "0"
+        self.vocab_parallel = False
         self.graph = None
         self._static_tokens = None
         self._static_logits = None
@@ -314,6 +315,41 @@ class LlamaDecoder:
                                          cfg.hidden, self._stream()), "final norm")
         return torch.matmul(hn, self.lm_head.t())
 
+    # ------------------------------------------------------------------ vocab-parallel lm_head (tensor parallel only)
+    def shard_lm_head(self):
+        """Keep only this rank's vocab / world rows of the fp16 lm_head: step() then returns the logits shard [B, vocab / world]
+        (columns rank * v .. (rank + 1) * v of the full logits) — the Megatron vocab-parallel head; `gather_logits` rebuilds the
+        full tensor where somebody needs it, `argmax` picks the next token without moving the logits."""
+        if self.world == 1 or self.vocab_parallel:
+            return
+        if self.cfg.vocab % self.world:
+            raise ValueError("vocab must be divisible by the tensor-parallel world size")
+        v = self.cfg.vocab // self.world
+        self.lm_head = self.lm_head[self.rank * v:(self.rank + 1) * v].contiguous()
+        self.vocab_parallel = True
+        self.graph = None          # a captured step still holds the full head
+
+    def gather_logits(self, local: torch.Tensor) -> torch.Tensor:
+        if not self.vocab_parallel:
+            return local
+        import torch.distributed as dist
+        parts = [torch.empty_like(local) for _ in range(self.world)]
+        dist.all_gather(parts, local.contiguous(), group=self.group)
+        return torch.cat(parts, dim=-1)
+
+    def argmax(self, logits: torch.Tensor) -> torch.Tensor:
+        """Next-token ids [B] from step()'s output: plain argmax, or — vocab-parallel — the best of the ranks' local maxima
+        (ties go to the lower index, like torch.argmax over the full row)."""
+        if not self.vocab_parallel:
+            return torch.argmax(logits, dim=-1)
+        import torch.distributed as dist
+        val, idx = torch.max(logits.float(), dim=-1)
+        mine = torch.stack((val, (idx + self.rank * logits.shape[-1]).float()), dim=-1).contiguous()     # ids < 2^24: exact in fp32
+        allc = torch.empty((self.world,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
+        dist.all_gather_into_tensor(allc, mine, group=self.group)
+        best = torch.argmax(allc[..., 0], dim=0)         # first rank with the maximum = lowest vocabulary index among ties
+        return allc[..., 1].gather(0, best.unsqueeze(0)).squeeze(0).long()
+
     def _norm_then_linear(self, h, ln_w, lin):
         """Discovery-phase path: the reference's two-step sequence (norm.py:24-28 then linear.py:165, fused mode)."""
         from .norm import FasterTransformerRMSNorm
@@ -444,6 +480,7 @@ class LlamaDecoder:
         self.fuse_swiglu = batch > 128
         self.fuse_attn_quant = os.environ.get("MIXQ_FUSE_ATTN_QUANT", "1") != "0"
         self.fuse_xchg_quant = os.environ.get("MIXQ_TP_FUSE_QUANT", "1") != "0"
+        self.vocab_parallel = False
         self.graph = self._static_tokens = self._static_logits = self.kv = None
         self.lib = _lib.load()
         self.xchg = None
