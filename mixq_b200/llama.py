@@ -342,13 +342,8 @@ class LlamaDecoder:
         (ties go to the lower index, like torch.argmax over the full row)."""
         if not self.vocab_parallel:
             return torch.argmax(logits, dim=-1)
-        import torch.distributed as dist
-        val, idx = torch.max(logits.float(), dim=-1)
-        mine = torch.stack((val, (idx + self.rank * logits.shape[-1]).float()), dim=-1).contiguous()     # ids < 2^24: exact in fp32
-        allc = torch.empty((self.world,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
-        dist.all_gather_into_tensor(allc, mine, group=self.group)
-        best = torch.argmax(allc[..., 0], dim=0)         # first rank with the maximum = lowest vocabulary index among ties
-        return allc[..., 1].gather(0, best.unsqueeze(0)).squeeze(0).long()
+        from .tp import vocab_parallel_argmax
+        return vocab_parallel_argmax(logits, self.rank, self.world, self.group)
 
     def _norm_then_linear(self, h, ln_w, lin):
         """Discovery-phase path: the reference's two-step sequence (norm.py:24-28 then linear.py:165, fused mode)."""

@@ -397,6 +397,21 @@ class PushExchange:
         self._keep = None
 
 
+def vocab_parallel_argmax(local_logits: torch.Tensor, rank: int, world: int, group=None) -> torch.Tensor:
+    """Next-token ids [B] when every rank holds the logits of vocab / world consecutive vocabulary rows (vocab-parallel lm_head):
+    each rank takes its local maximum, the (value, global index) pairs are all-gathered — 8 bytes per row and rank instead of the
+    logits — and the best pair wins; ties go to the lowest vocabulary index, like torch.argmax over the gathered row.
+    Works on any backend (NCCL on the GPUs, gloo in the CPU tests)."""
+    import torch.distributed as dist
+    val, idx = torch.max(local_logits.float(), dim=-1)
+    mine = torch.stack((val, (idx + rank * local_logits.shape[-1]).float()), dim=-1).contiguous()     # ids < 2^24: exact in fp32
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    allc = torch.stack(parts, dim=0)                    # [world, B, 2]
+    best = torch.argmax(allc[..., 0], dim=0)            # first rank holding the maximum = lowest vocabulary index among ties
+    return allc[..., 1].gather(0, best.unsqueeze(0)).squeeze(0).long()
+
+
 def make_exchange(rows: int, cols: int, rank: int, world: int, group=None, device="cuda", kind: str = "auto"):
     """kind: "push" (reduce-scatter fused into the GEMM epilogue + finish kernel; the default), "push-nomc" (the same without
     the multicast broadcast), "multicast" (NVLS all-reduce kernel), "peer" (CUDA-IPC peer-memory all-reduce kernel),

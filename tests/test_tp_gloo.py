@@ -131,3 +131,41 @@ def test_tp_exchange_oracle_properties():
     assert np.abs(y8.astype(np.float64) - exact).max() <= np.abs(exact).max() * 2 ** -10   # within fp16 rounding of the true sum
     with_res = O.tp_exchange(parts, res)
     assert np.array_equal(with_res, (y8.astype(np.float32) + res.astype(np.float32)).astype(np.float16))
+
+
+def _argmax_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mixq_b200 import tp
+    g = torch.Generator().manual_seed(3)
+    full = torch.randn(16, 64, generator=g).half()
+    full[0, 5] = full[0, 40] = 9.0            # a tie across the two shards: the lower index must win
+    full[1, 33] = full[1, 34] = 9.0           # a tie inside one shard
+    full[2, :] = -3.0                         # all equal: index 0
+    v = full.shape[1] // world
+    got = tp.vocab_parallel_argmax(full[:, rank * v:(rank + 1) * v], rank, world)
+    q.put((rank, got.tolist(), torch.argmax(full.float(), dim=-1).tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_vocab_parallel_argmax_two_ranks():
+    """The next-token pick of the vocab-parallel lm_head (mixq_b200/tp.py: vocab_parallel_argmax) == torch.argmax over the full
+    logits row on every rank, ties included."""
+    world = 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_argmax_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, got, want in res:
+        assert got == want, (rank, got, want)
+    assert res[0][1][:3] == [5, 33, 0]
