@@ -57,6 +57,9 @@ typedef struct mixq_linear_plan {
   int tmem_cols;      /* TMEM columns in use (<= 512) */
 } mixq_linear_plan;
 int mixq_plan_linear(int M, int N, int K, int bit, int n_ind, int swiglu_pair, int tile_n, int sms, mixq_linear_plan* out);
+/* How many CTAs per tile a launch with a split-K workspace of `splitk_ws_bytes` would use along K (1 = no split; see
+ * mixq_linear_args.splitk_ws).  Host-only, no launch; sms <= 0 = the current device.  < 0 on bad arguments. */
+int mixq_plan_split_k(int M, int N, int K, int bit, int n_ind, int sms, long long splitk_ws_bytes);
 /* Programmatic dependent launch (default on; MIXQ_PDL=0 in the environment or on = 0 turns it off): every kernel of the
  * library is launched so that its CTAs may take an SM as soon as the previous kernel's CTA there has exited, set up, and
  * prefetch constants (the quantised weights) while the previous kernel drains; each kernel waits for its predecessors

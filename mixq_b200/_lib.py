@@ -183,6 +183,7 @@ SIGNATURES = {
     "mixq_set_pdl": [_i],
     "mixq_set_grid_barrier_mode": [_i],
     "mixq_plan_linear": [_i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(LinearPlan)],
+    "mixq_plan_split_k": [_i, _i, _i, _i, _i, _i, _ll],
     "mixq_set_trace_buffer": [_vp],
     "mixq_version": [],
     "mixq_launch_count": [],

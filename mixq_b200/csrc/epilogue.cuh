@@ -28,11 +28,7 @@ __device__ __forceinline__ __half* y_base(const LinearParams& p, int n, int& ld)
 
 // Destinations of the tile that holds output column n: ONE (y, or the owning rank's slot) unless the broadcast push is on.
 // A rolled loop around a single call site: the epilogue is instruction-fetch sensitive, its body must not be duplicated.
-#ifdef MIXQ_AB_NO_BCAST
-__device__ __forceinline__ int y_ndest(const LinearParams& p) { return 1; }
-#else
 __device__ __forceinline__ int y_ndest(const LinearParams& p) { return p.peer_bcast > 0 ? p.peer_bcast : 1; }
-#endif
 __device__ __forceinline__ __half* y_dest(const LinearParams& p, int n, int d, int& ld) {
   if (p.peer_bcast > 0) {
     ld = p.N;

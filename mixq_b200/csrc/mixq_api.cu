@@ -781,6 +781,21 @@ int mixq_set_grid_barrier_mode(int mode) {
   return 0;
 }
 
+int mixq_plan_split_k(int M, int N, int K, int bit, int n_ind, int sms, long long splitk_ws_bytes) {
+  if ((bit != 8 && bit != 4) || K % 16 != 0 || N % 8 != 0) {
+    fail(MIXQ_EINVAL, "bit must be 8 or 4, K % 16 == 0 and N % 8 == 0 required");
+    return -1;
+  }
+  if (sms <= 0) {
+    DeviceInfo di;
+    if (device_info(&di)) return -1;
+    sms = di.sms;
+  }
+  GemmPlan g{};
+  if (plan_gemm(M, N, K, bit, n_ind, false, 0, sms, &g, splitk_ws_bytes)) return -1;
+  return g.two_cta ? 1 : g.splits;
+}
+
 int mixq_set_pdl(int on) {
   g_pdl.store(on ? 1 : 0, std::memory_order_relaxed);
   return 0;

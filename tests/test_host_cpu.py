@@ -249,6 +249,21 @@ def test_launch_plan_headline_shapes():
     assert rc != 0 and b"pair" in _lib.load().mixq_last_error()
 
 
+def test_split_k_plan():
+    """The planner's split-K choices for the small-M shapes (host-only; csrc/mixq_api.cu: plan_gemm's cost model fitted to
+    profiles/r02_trace_splitk_v3.log): long-K few-tile launches split, the rest — and everything without a workspace — do not."""
+    lib = _lib.load()
+    ws = 16 * 1024 * 1024
+    S = lambda M, N, K, w=ws: lib.mixq_plan_split_k(M, N, K, 8, 41, 148, w)
+    assert S(128, 1280, 8192) == 4 and S(128, 3584, 8192) == 4            # C5 W_pack / up / gate per rank: 10 and 28 tiles
+    assert S(128, 8192, 3584) == 1 and S(128, 8192, 1024) == 1            # 64 tiles, short K: the fixed cost would not pay
+    assert S(32, 4096, 4096) == 1 and S(32, 4096, 11008) == 4             # C1: 4096^2 measured slower split, down_proj faster
+    assert S(512, 4096, 4096) == 1                                         # M > 128: the 2-CTA kernel never splits
+    assert S(128, 1280, 8192, 0) == 1                                      # no workspace
+    assert S(128, 1280, 8192, 4096 + 10 * 65536) == 2                      # a small workspace caps the factor
+    assert lib.mixq_plan_split_k(128, 1280, 8190, 8, 0, 148, ws) < 0
+
+
 def test_launch_plan_invariants_over_all_configs():
     """Every Linear shape of BASELINE.json's configs (7B / 8B / 70B, TP 1..8, batch 32..512, 0..200 outlier columns) gets a
     plan that fits the hardware: TMEM <= 512 columns, pipeline <= 192 KB, resident outlier stages, passes cover the tile."""
