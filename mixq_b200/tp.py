@@ -271,13 +271,16 @@ def _symmetric_alloc(total_bytes: int, rank: int, world: int, group=None, device
 
 
 class PushExchange:
-    """The FUSED row-parallel exchange (include/mixq.h: mixq_linear_args.y_peer + mixq_exchange_finish).
+    """The FUSED row-parallel exchange (include/mixq.h: mixq_linear_args.y_peer + mixq_exchange_finish_poll[_quant]).
 
     Reduce-scatter half: the row-parallel MixLinear's epilogue warps store column slice j of this rank's partial straight into
     rank j's receive slot over NVLink (`push_targets()` hands the slot pointers to MixLinear_GEMM.forward(..., push=)), so the
-    transfer rides under the GEMM's own tail.  All-gather half: `reduce(residual)` launches the small finish kernel — handshake,
-    local fp32 reduction of this rank's slice in rank order (+ residual, a separate fp16 rounding), broadcast of the slice into
-    every rank's result buffer (multimem.st through the NVSwitch when a multicast mapping exists), handshake.
+    transfer rides under the GEMM's own tail.  All-gather half: `reduce(residual)` launches the small finish kernel — local fp32
+    reduction of this rank's slice in rank order (+ residual, a separate fp16 rounding), the slice stored into every rank's
+    result buffer (peer stores, or multimem.st through the NVSwitch), the other slices collected.
+    sync="poll" (default): no handshake at all — slots and result buffers hold a sentinel until data lands, readers spin on the
+    data itself and re-arm what they consume; `reduce(..., quant=)` also runs the next Linear's activation prologue on the
+    assembled rows.  sync="flags": the release/acquire flag protocol (two handshakes, or one with one_shot).
     Bit-identical on all ranks and equal to oracle.mixq_oracle.tp_exchange (rank-order fp32 sum).
     The returned result buffer is valid until the NEXT reduce() has run (which re-arms it in the polling form)."""
 
