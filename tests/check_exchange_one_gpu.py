@@ -11,7 +11,8 @@ checked where only one GPU is available (the driver's test box):
   * three exchanges in a row through the two alternating buffer sets (consumers re-arm what they read).
 
 The ranks' finish kernels wait for each other's data, so they must be co-resident: rows <= 64 keeps every grid small.
-Run in its own process (tests/test_gpu_exchange_one_gpu.py): a protocol bug would end in the library's stall trap.
+Run in its own process by tests/test_gpu_exchange_one_gpu.py (a protocol bug would end in the library's stall trap); it lives
+under tests/ because it calls the oracle, which is test infrastructure.
 """
 import ctypes as C
 import os
