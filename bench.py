@@ -113,7 +113,7 @@ def cpu_layer_sample(cfg_name, batch, bit, budget_s=12.0, build_only=False):
         g = (g.astype(np.float32) * u.astype(np.float32)).astype(np.float16)
         return (down.forward(g, None, True).astype(np.float32) + h).astype(np.float16)
 
-    desc = f"1 of {cfg.layers} decoder layers (5 MixLinears + 2 fused norms, M={batch}), numpy f64 BLAS"
+    desc = f"1 of {cfg.layers} decoder layers (5 MixLinears + 2 fused norms, M={batch}), numpy on the host BLAS (exact int GEMM in fp32 K-chunks)"
     if build_only:
         return (lambda: one_layer(h)), os.cpu_count(), desc
     one_layer(h)   # warm BLAS
@@ -172,8 +172,10 @@ def run_reference(args):
         "impl": "reference", "metric": "llama_decode_tokens_per_s", "value": val, "unit": "tokens/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+        # the GPU arm's workload, word for word; only `parallelism` says where it ran
         "config": {"workload": f"{args.model} W{args.bit}A{args.bit}O16 decode step, batch {args.batch}, q_len 1, empty KV cache "
-                               "(benchflops.py:96-128)", "parallelism": "cpu", "bit": args.bit},
+                               "(benchflops.py:96-128), ~1% forced outlier channels",
+                   "layers": cfg.layers, "global_batch": args.batch, "parallelism": "host cpu (rank 0)", "bit": args.bit},
         "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": desc + f", x{cfg.layers} layers extrapolated"},
         "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
